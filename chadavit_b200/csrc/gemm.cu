@@ -1,0 +1,297 @@
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a:  C[M,N] (+)= op(A)[M,K] * op(B)[N,K]^T
+//   * operands bf16, accumulate fp32 in TMEM (double-buffered accumulators: epilogue of tile i overlaps MMA of tile i+1)
+//   * TMA (cp.async.bulk.tensor) loads into 128B/64B-swizzled smem stages, mbarrier full/empty ring
+//   * warp 0 = TMA producer, warp 1 = MMA issuer (single thread), warps 2..5 = epilogue (TMEM -> regs -> global)
+//   * either operand may be K-major ([rows,K] row-major) or MN-major ([K,rows] row-major); the latter is what the
+//     weight-gradient (dW = dY^T X) and input-gradient (dX = dY W) products of the encoder need without transposes
+//   * epilogue: bias, ReLU, residual add, ReLU-mask, fp32 / bf16 store, split-K fp32 atomics, tokenizer scatter
+#include "common.cuh"
+#include "chadavit_b200.h"
+#include "internal.h"
+
+namespace cb {
+
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN <= 128) ? 6 : (BN <= 192 ? 5 : 4);
+  static constexpr int ACC_STRIDE = (BN <= 128) ? 128 : 256;  // TMEM columns between the two accumulators
+  static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+// MODE: 0 = K-major (128B swizzle, 64-element K rows), 1 = MN-major 64-element blocks (128B swizzle),
+//       2 = MN-major 32-element blocks (64B swizzle)
+template <int MODE>
+__device__ __forceinline__ uint64_t operand_desc(uint32_t saddr, int k16) {
+  if (MODE == 0) return umma_smem_desc(saddr + k16 * 32, 16, 1024, 3);
+  if (MODE == 1) return umma_smem_desc(saddr + k16 * 2048, 64 * 128, 1024, 3);
+  return umma_smem_desc(saddr + k16 * 1024, 64 * 64, 512, 2);
+}
+
+template <int MODE>
+__device__ __forceinline__ void operand_load(void* smem, const CUtensorMap* tm, uint64_t* bar, int k0, int r0) {
+  if (MODE == 0) tma_load_2d(smem, tm, bar, k0, r0);
+  else if (MODE == 1) tma_load_3d(smem, tm, bar, 0, k0, r0 / 64);
+  else tma_load_3d(smem, tm, bar, 0, k0, r0 / 32);
+}
+
+template <int BN, int AMODE, int BMODE>
+__global__ void __launch_bounds__(192, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + Cfg::STAGES * Cfg::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + Cfg::STAGES;
+  uint64_t* acc_full = bars + 2 * Cfg::STAGES;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_m = (g.M + BM - 1) / BM, num_n = (g.N + BN - 1) / BN;
+  const int kb_total = (g.K + BK - 1) / BK;
+  const int kb_per = (kb_total + g.k_splits - 1) / g.k_splits;
+  const int num_tiles = num_m * num_n * g.k_splits;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < Cfg::STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int split = tile / (num_m * num_n), mn = tile % (num_m * num_n);
+        const int m0 = (mn / num_n) * BM, n0 = (mn % num_n) * BN;
+        const int kb0 = split * kb_per, kb1 = min(kb0 + kb_per, kb_total);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
+          operand_load<AMODE>(sA + s * Cfg::A_BYTES, &tmA, &full[s], kb * BK, m0);
+          operand_load<BMODE>(sB + s * Cfg::B_BYTES, &tmB, &full[s], kb * BK, n0);
+          if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, AMODE != 0, BMODE != 0);
+      int s = 0; uint32_t ph = 0; int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int split = tile / (num_m * num_n);
+        const int kb0 = split * kb_per, kb1 = min(kb0 + kb_per, kb_total);
+        const int buf = it & 1; const uint32_t aph = (it >> 1) & 1;
+        mbar_wait(&acc_empty[buf], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * Cfg::ACC_STRIDE;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + s * Cfg::A_BYTES), b_addr = smem_u32(sB + s * Cfg::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_ss(d_tmem, operand_desc<AMODE>(a_addr, k), operand_desc<BMODE>(b_addr, k), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          tc_commit(&empty[s]);
+          if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+        }
+        tc_commit(&acc_full[buf]);
+      }
+    }
+  } else {
+    // ---------------- epilogue: warp w owns TMEM lanes 32*(w&3) .. +31  == rows of the tile
+    const int q = warp & 3;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int split = tile / (num_m * num_n), mn = tile % (num_m * num_n);
+      const int m0 = (mn / num_n) * BM, n0 = (mn % num_n) * BN;
+      const int kb0 = split * kb_per, kb1 = min(kb0 + kb_per, kb_total);
+      const int buf = it & 1; const uint32_t aph = (it >> 1) & 1;
+      mbar_wait(&acc_full[buf], aph);
+      tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+      const bool row_ok = row < g.M && kb1 > kb0;
+      const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + buf * Cfg::ACC_STRIDE;
+      const long out_row = row;
+      const float* pos_row = nullptr; const float* chan_row = nullptr; bool is_cls = false;
+      if ((g.flags & CB_EPI_TOKENIZE) && row_ok) {
+        int lo = 0, hi = g.nseq;  // largest b with cu[b] <= row
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (__ldg(g.cu + mid) <= row) lo = mid; else hi = mid; }
+        const int off = row - __ldg(g.cu + lo);
+        if (off == 0) { is_cls = true; pos_row = g.cls_row; }
+        else {
+          const int c = (off - 1) / g.npatch, p = (off - 1) - c * g.npatch;
+          pos_row = g.pos + (long)p * g.N;
+          if (g.chan_tok) chan_row = g.chan_tok + (long)c * g.N;
+        }
+      }
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t r[32];
+        tmem_ld32(t_addr + c, r);
+        tmem_ld_wait();
+        if (!row_ok) continue;
+#pragma unroll
+        for (int j8 = 0; j8 < 4; ++j8) {
+          const int n = n0 + c + j8 * 8;
+          if (n >= g.N) break;
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = is_cls ? 0.f : __uint_as_float(r[j8 * 8 + j]) * g.alpha;
+          if (g.bias && split == 0 && !is_cls) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(g.bias + n));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(g.bias + n + 4));
+            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+          }
+          if (pos_row) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(pos_row + n));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(pos_row + n + 4));
+            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+          }
+          if (chan_row) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(chan_row + n));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(chan_row + n + 4));
+            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+          }
+          if (g.flags & CB_EPI_RELU) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          if (g.flags & (CB_EPI_RESIDUAL | CB_EPI_RELU_MASK)) {
+            const uint4 a = __ldg(reinterpret_cast<const uint4*>(g.aux + (long)row * g.ld_aux + n));
+            const uint32_t au[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 f = unpack_bf16(au[j]);
+              if (g.flags & CB_EPI_RESIDUAL) { v[2 * j] += f.x; v[2 * j + 1] += f.y; }
+              else { v[2 * j] = f.x > 0.f ? v[2 * j] : 0.f; v[2 * j + 1] = f.y > 0.f ? v[2 * j + 1] : 0.f; }
+            }
+          }
+          if (g.flags & CB_EPI_ATOMIC) {
+            float* dst = reinterpret_cast<float*>(g.C) + out_row * g.ldc + n;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) atomicAdd(dst + j, v[j]);
+          } else if (g.flags & CB_EPI_OUT_F32) {
+            float* dst = reinterpret_cast<float*>(g.C) + out_row * g.ldc + n;
+            *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+          } else {
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(g.C) + out_row * g.ldc + n;
+            *reinterpret_cast<uint4*>(dst) =
+                make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------ host
+static int encode_operand(CUtensorMap* tm, const void* base, int rows, int K, int ld, int mode, int tile_rows) {
+  if (mode == 0) {  // [rows, K] row-major, inner = K
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)rows};
+    uint64_t strides[1] = {(uint64_t)ld * 2};
+    uint32_t box[2] = {64, (uint32_t)tile_rows};
+    return make_tmap(tm, base, 2, dims, strides, box, 3);
+  }
+  const int blk = mode == 1 ? 64 : 32;  // [K, rows] row-major viewed as (blk, K, rows/blk)
+  uint64_t dims[3] = {(uint64_t)blk, (uint64_t)K, (uint64_t)(rows / blk)};
+  uint64_t strides[2] = {(uint64_t)ld * 2, (uint64_t)blk * 2};
+  uint32_t box[3] = {(uint32_t)blk, 64, (uint32_t)(tile_rows / blk)};
+  return make_tmap(tm, base, 3, dims, strides, box, mode == 1 ? 3 : 2);
+}
+
+template <int BN, int AMODE, int BMODE>
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CB_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, AMODE, BMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int num_tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN) * g.k_splits;
+  const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+  gemm_kernel<BN, AMODE, BMODE><<<grid, 192, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, g);
+  CB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int BN>
+static int dispatch_modes(int am, int bm, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, cudaStream_t s) {
+  switch (am * 3 + bm) {
+    case 0: return launch<BN, 0, 0>(tmA, tmB, g, s);
+    case 1: return launch<BN, 0, 1>(tmA, tmB, g, s);
+    case 2: return launch<BN, 0, 2>(tmA, tmB, g, s);
+    case 4: return launch<BN, 1, 1>(tmA, tmB, g, s);
+    case 5: return launch<BN, 1, 2>(tmA, tmB, g, s);
+    case 7: return launch<BN, 2, 1>(tmA, tmB, g, s);
+    case 8: return launch<BN, 2, 2>(tmA, tmB, g, s);
+    default: set_error("gemm: unsupported operand layout combination a=%d b=%d", am, bm); return 1;
+  }
+}
+
+int gemm_run(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, GemmArgs g, cudaStream_t stream) {
+  CB_CHECK(g.M > 0 && g.N > 0 && g.K > 0, "gemm: empty problem M=%d N=%d K=%d", g.M, g.N, g.K);
+  CB_CHECK(g.N % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && g.ldc % 4 == 0, "gemm: N, lda, ldb must be multiples of 8 (N=%d lda=%d ldb=%d)", g.N, lda, ldb);
+  CB_CHECK((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.C) & 15) == 0,
+           "gemm: operands must be 16-byte aligned");
+  int am = 0, bm = 0;
+  if (a_mn) { CB_CHECK(g.M % 32 == 0, "gemm: MN-major A needs M %% 32 == 0 (M=%d)", g.M); am = (g.M % 64 == 0) ? 1 : 2; }
+  if (b_mn) { CB_CHECK(g.N % 32 == 0, "gemm: MN-major B needs N %% 32 == 0 (N=%d)", g.N); bm = (g.N % 64 == 0) ? 1 : 2; }
+  const int BN = (g.N % 192 == 0 && g.N % 256 != 0) ? 192 : (g.N >= 256 ? 256 : 128);
+  if (g.k_splits < 1) g.k_splits = 1;
+  const int kb_total = (g.K + BK - 1) / BK;
+  if (g.k_splits > kb_total) g.k_splits = kb_total;
+  if (g.k_splits > 1) {
+    // every split must own at least one k-block, otherwise its tile would store garbage
+    const int kb_per = (kb_total + g.k_splits - 1) / g.k_splits;
+    g.k_splits = (kb_total + kb_per - 1) / kb_per;
+    CB_CHECK(g.flags & CB_EPI_ATOMIC, "gemm: split-K requires the atomic epilogue");
+  }
+  CUtensorMap tmA, tmB;
+  if (encode_operand(&tmA, A, g.M, g.K, lda, am, BM)) return 1;
+  if (encode_operand(&tmB, B, g.N, g.K, ldb, bm, BN)) return 1;
+  if (BN == 192) return dispatch_modes<192>(am, bm, tmA, tmB, g, stream);
+  if (BN == 256) return dispatch_modes<256>(am, bm, tmA, tmB, g, stream);
+  return dispatch_modes<128>(am, bm, tmA, tmB, g, stream);
+}
+
+}  // namespace cb
+
+extern "C" int cb_gemm_bf16(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* C, int ldc, int M,
+                            int N, int K, const float* bias, const void* aux, int ld_aux, int flags, float alpha,
+                            int k_splits, void* stream) {
+  cb::GemmArgs g{};
+  g.M = M; g.N = N; g.K = K; g.k_splits = k_splits; g.C = C; g.ldc = ldc; g.bias = bias;
+  g.aux = reinterpret_cast<const __nv_bfloat16*>(aux); g.ld_aux = ld_aux; g.flags = flags; g.alpha = alpha;
+  CB_CHECK(!(flags & CB_EPI_TOKENIZE), "cb_gemm_bf16: use cb_tokenize_fwd for the tokenizer epilogue");
+  CB_CHECK(!(flags & (CB_EPI_RESIDUAL | CB_EPI_RELU_MASK)) || aux, "cb_gemm_bf16: aux pointer required by flags");
+  return cb::gemm_run(A, lda, a_mn, B, ldb, b_mn, g, reinterpret_cast<cudaStream_t>(stream));
+}

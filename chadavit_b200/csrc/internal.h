@@ -1,0 +1,31 @@
+// Declarations shared between translation units of libchadavit_b200 (not part of the public C ABI).
+#pragma once
+#include "common.cuh"
+
+namespace cb {
+
+struct GemmArgs {
+  int M, N, K;
+  int k_splits;
+  void* C;
+  int ldc;
+  const float* bias;
+  const __nv_bfloat16* aux;
+  int ld_aux;
+  int flags;
+  float alpha;
+  // tokenizer epilogue (CB_EPI_TOKENIZE): A rows are already in packed token order (CLS rows hold zeros);
+  // row t of sequence b (cu[b] <= t < cu[b+1]): off = t - cu[b]; off == 0 -> CLS row = cls_row, else
+  // c = (off-1)/npatch, p = (off-1)%npatch: acc + bias + pos[p] + chan_tok[c]        (chada_vit.py:245-265)
+  const int* cu;          // [nseq+1]
+  int nseq;
+  const float* pos;       // [npatch, N] fp32 (already interpolated if needed)
+  const float* chan_tok;  // [max_ch, N] fp32 or null
+  const float* cls_row;   // [N] fp32 = cls_token + pos_embed[0]
+  int npatch;
+};
+
+// C = op(A) op(B)^T with the epilogue in g.flags; see gemm.cu
+int gemm_run(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, GemmArgs g, cudaStream_t stream);
+
+}  // namespace cb

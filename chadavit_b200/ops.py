@@ -1,0 +1,195 @@
+"""Thin Python wrappers over the C ABI: torch tensors in, raw device pointers across the boundary.
+
+PyTorch is used only for device memory and streams.  Every function launches on the current CUDA stream and is
+asynchronous.  There is no CPU path: CPU tensors raise.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+EPI_RELU, EPI_RESIDUAL, EPI_RELU_MASK, EPI_OUT_F32, EPI_ATOMIC = 1, 2, 4, 8, 16
+bf16 = torch.bfloat16
+
+
+def _p(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("chadavit_b200 ops need CUDA tensors (no CPU fallback)")
+    return t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _call(name: str, *args) -> None:
+    lib = _lib.load()
+    _lib.launch_count += 1
+    _lib.check(getattr(lib, name)(*args), name)
+
+
+def sync_check() -> None:
+    _call("cb_sync_check", _stream())
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+def gemm(A: torch.Tensor, B: torch.Tensor, *, a_mn: bool = False, b_mn: bool = False, bias: Optional[torch.Tensor] = None,
+         aux: Optional[torch.Tensor] = None, flags: int = 0, out: Optional[torch.Tensor] = None, alpha: float = 1.0,
+         k_splits: int = 1) -> torch.Tensor:
+    """C[M,N] (+)= alpha * op(A) op(B)^T.  a_mn/b_mn: the operand is stored [K, M] / [K, N] (MN-major)."""
+    assert A.dtype == bf16 and B.dtype == bf16 and A.dim() == 2 and B.dim() == 2
+    assert A.stride(1) == 1 and B.stride(1) == 1
+    M, K = (A.shape[1], A.shape[0]) if a_mn else (A.shape[0], A.shape[1])
+    N, Kb = (B.shape[1], B.shape[0]) if b_mn else (B.shape[0], B.shape[1])
+    assert K == Kb, f"K mismatch {K} vs {Kb}"
+    if out is None:
+        out = torch.empty(M, N, device=A.device, dtype=torch.float32 if flags & (EPI_OUT_F32 | EPI_ATOMIC) else bf16)
+    assert out.shape == (M, N) and out.stride(1) == 1
+    _call("cb_gemm_bf16", _p(A), A.stride(0), int(a_mn), _p(B), B.stride(0), int(b_mn), _p(out), out.stride(0), M, N, K,
+          _p(bias), _p(aux), aux.stride(0) if aux is not None else 0, flags, float(alpha), k_splits, _stream())
+    return out
+
+
+def splitk_for(K: int, tiles: int, target_ctas: int = 148) -> int:
+    """Number of K splits so that a weight-gradient GEMM with `tiles` output tiles fills the GPU."""
+    kb = (K + 63) // 64
+    return max(1, min(kb, (target_ctas + tiles - 1) // tiles))
+
+
+# ------------------------------------------------------------------------------------------------ LayerNorm
+def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, *, in_idx: Optional[torch.Tensor] = None,
+                  out_f32: bool = False, save_stats: bool = True):
+    D = x.shape[-1]
+    rows = in_idx.numel() if in_idx is not None else x.shape[0]
+    y = None if out_f32 else torch.empty(rows, D, device=x.device, dtype=bf16)
+    y32 = torch.empty(rows, D, device=x.device, dtype=torch.float32) if out_f32 else None
+    mean = torch.empty(rows, device=x.device, dtype=torch.float32) if save_stats else None
+    rstd = torch.empty(rows, device=x.device, dtype=torch.float32) if save_stats else None
+    _call("cb_layernorm_fwd", _p(x), _p(in_idx), _p(gamma), _p(beta), _p(y), _p(y32), _p(mean), _p(rstd), rows, D, float(eps), _stream())
+    return (y32 if out_f32 else y), mean, rstd
+
+
+def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor, *,
+                  dgamma: torch.Tensor, dbeta: torch.Tensor, dcolsum: Optional[torch.Tensor] = None,
+                  dres: Optional[torch.Tensor] = None, idx: Optional[torch.Tensor] = None, dx: Optional[torch.Tensor] = None):
+    D = x.shape[-1]
+    rows = dy.shape[0]
+    if dx is None:
+        dx = torch.empty_like(x) if idx is None else torch.zeros_like(x)
+    is32 = dy.dtype == torch.float32
+    _call("cb_layernorm_bwd", None if is32 else _p(dy), _p(dy) if is32 else None, _p(x), _p(idx), _p(gamma), _p(mean), _p(rstd),
+          _p(dres), _p(dx), _p(dgamma), _p(dbeta), _p(dcolsum), rows, D, _stream())
+    return dx
+
+
+def colsum(x: torch.Tensor, out: torch.Tensor) -> None:
+    _call("cb_colsum_bf16", _p(x), x.stride(0), _p(out), x.shape[0], x.shape[1], _stream())
+
+
+def cast_bf16(src: torch.Tensor, dst: Optional[torch.Tensor] = None) -> torch.Tensor:
+    assert src.dtype == torch.float32 and src.is_contiguous()
+    if dst is None:
+        dst = torch.empty(src.shape, device=src.device, dtype=bf16)
+    _call("cb_cast_f32_bf16", _p(src), _p(dst), src.numel(), _stream())
+    return dst
+
+
+# ------------------------------------------------------------------------------------------------ varlen bookkeeping
+class PackedLayout:
+    """Host-side index bookkeeping for one ragged batch (bit-exact contract).
+
+    counts[b] = C_b channels of image b.  Sequence b owns packed rows [cu[b], cu[b+1]) with 1 + C_b*N rows.
+    Everything is derived from Python ints (list_num_channels) -> no device synchronisation.
+    """
+
+    def __init__(self, counts: Sequence[int], npatch: int, device, max_channels: int = 10):
+        counts = [int(c) for c in counts]
+        for c in counts:
+            if c < 1 or c > max_channels:
+                raise ValueError(f"number of channels per image must be in [1, {max_channels}], got {c}")
+        self.counts = counts
+        self.npatch = npatch
+        self.B = len(counts)
+        self.G = sum(counts)
+        lens = np.array([1 + c * npatch for c in counts], dtype=np.int64)
+        cu = np.zeros(self.B + 1, dtype=np.int32)
+        cu[1:] = np.cumsum(lens)
+        self.cu_host = cu
+        self.T = int(cu[-1])
+        self.max_seqlen = int(lens.max())
+        chan_img = np.repeat(np.arange(self.B, dtype=np.int32), counts)
+        chan_idx = np.concatenate([np.arange(c, dtype=np.int32) for c in counts])
+        self.chan_img_host, self.chan_idx_host = chan_img, chan_idx
+        self.device = device
+        self.cu = torch.from_numpy(cu).to(device, non_blocking=True)
+        self.chan_img = torch.from_numpy(chan_img).to(device, non_blocking=True)
+        self.chan_idx = torch.from_numpy(chan_idx).to(device, non_blocking=True)
+        self._work = {}
+
+    def attn_work(self, nheads: int, tile: int = 128) -> torch.Tensor:
+        """(n_work, 4) int32 {q_row0, seq_start, seq_end, head}, longest sequences first (LPT order)."""
+        if (nheads, tile) not in self._work:
+            items = []
+            order = np.argsort(-(self.cu_host[1:] - self.cu_host[:-1]), kind="stable")
+            for b in order:
+                s, e = int(self.cu_host[b]), int(self.cu_host[b + 1])
+                for h in range(nheads):
+                    for q0 in range(s, e, tile):
+                        items.append((q0, s, e, h))
+            w = torch.tensor(items, dtype=torch.int32).reshape(-1, 4)
+            self._work[(nheads, tile)] = w.to(self.device, non_blocking=True)
+        return self._work[(nheads, tile)]
+
+    def non_cls_rows(self) -> torch.Tensor:
+        """Packed rows of all patch tokens in (b, c, p) order (return_all_tokens=True output order, chada_vit.py:283-287)."""
+        if not hasattr(self, "_noncls"):
+            rows = np.concatenate([np.arange(self.cu_host[b] + 1, self.cu_host[b + 1], dtype=np.int32) for b in range(self.B)])
+            self._noncls = torch.from_numpy(rows).to(self.device, non_blocking=True)
+        return self._noncls
+
+
+# ------------------------------------------------------------------------------------------------ tokenizer / attention
+def tokenize_fwd(x: torch.Tensor, lay: PackedLayout, patch: int, w_pe_bf16: torch.Tensor, b_pe: torch.Tensor, pos_patch: torch.Tensor,
+                 cls_row: torch.Tensor, chan_tok: Optional[torch.Tensor]) -> Tuple[torch.Tensor, torch.Tensor]:
+    G, one, H, W = x.shape
+    if one != 1:
+        raise ValueError("ChAdaViT expects a (sum_channels, 1, H, W) tensor")
+    if G != lay.G:
+        raise ValueError(f"x has {G} channel images but list_num_channels sums to {lay.G}")
+    if H % patch or W % patch:
+        raise ValueError(f"image size {H}x{W} must be a multiple of the patch size {patch}")
+    if x.dtype != torch.float32:
+        x = x.float()
+    if not (x.stride(3) == 1 and x.stride(2) == W and x.stride(0) == H * W):  # size-1 dim is stride-agnostic (channels_last)
+        x = x.contiguous()
+    D = w_pe_bf16.shape[0]
+    patches = torch.empty(lay.T, patch * patch, device=x.device, dtype=bf16)
+    tokens = torch.empty(lay.T, D, device=x.device, dtype=bf16)
+    _call("cb_tokenize_fwd", _p(x), G, H, W, patch, _p(lay.cu), _p(lay.chan_img), lay.B, _p(w_pe_bf16), _p(b_pe), _p(pos_patch),
+          _p(cls_row), _p(chan_tok), _p(patches), _p(tokens), lay.T, D, _stream())
+    return tokens, patches
+
+
+def tokenize_bwd(dtokens: torch.Tensor, patches: torch.Tensor, lay: PackedLayout, *, dw_pe, db_pe, dpos_patch, dcls_row, dchan_tok) -> None:
+    T, D = dtokens.shape
+    pe = patches.shape[1]
+    ks = splitk_for(T, ((D + 127) // 128) * ((pe + 255) // 256))
+    _call("cb_tokenize_bwd", _p(dtokens), _p(patches), _p(lay.cu), _p(lay.chan_img), _p(lay.chan_idx), lay.G, lay.B, lay.npatch, pe,
+          T, D, _p(dw_pe), _p(db_pe), _p(dpos_patch), _p(dcls_row), _p(dchan_tok), ks, _stream())
+
+
+def attn_fwd(qkv: torch.Tensor, lay: PackedLayout, nheads: int, *, need_lse: bool = True) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    T, D3 = qkv.shape
+    D = D3 // 3
+    d = D // nheads
+    work = lay.attn_work(nheads)
+    out = torch.empty(T, D, device=qkv.device, dtype=bf16)
+    lse = torch.empty(nheads, T, device=qkv.device, dtype=torch.float32) if need_lse else None
+    _call("cb_attn_varlen_fwd", _p(qkv), _p(work), work.shape[0], _p(out), _p(lse), T, D, nheads, float(d) ** -0.5, _stream())
+    return out, lse

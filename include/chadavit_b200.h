@@ -1,0 +1,104 @@
+/*
+ * chadavit_b200 — C ABI of the B200 (sm_100a) hot path for ChAda-ViT + DINO.
+ *
+ * Drop-in boundary.  The reference (nicoboou/chadavit) is pure Python/PyTorch; the "FFI" a
+ * maintainer binds is therefore a ctypes/cffi stub inside the reference's own modules:
+ *     src/backbones/vit/chada_vit.py   ChAdaViT.forward / channel_aware_tokenization / TransformerEncoderLayer
+ *     src/methods/dino.py:32-111       DINOHead
+ *     src/losses/dino.py:69-118        DINOLoss.forward / update_center
+ *     src/utils/momentum.py:63-74      MomentumUpdater.update
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; cb_last_error() gives the message (thread local).
+ *     Nothing throws, nothing calls exit().  There is NO CPU fallback: all pointers are device pointers.
+ *   - every buffer is owned and allocated by the caller (torch); the library allocates nothing persistent.
+ *   - `stream` is a cudaStream_t passed as void*; all entry points are asynchronous on that stream.
+ *   - bf16 tensors are passed as `const void*` (raw __nv_bfloat16 storage), fp32 as `float*`, indices as int32.
+ *   - packed varlen token layout (replaces the reference's pad-to-10-channels + key-padding mask,
+ *     chada_vit.py:226-268):  tokens (T, D) row-major, cu_seqlens int32 (B+1), sequence b owns rows
+ *     [cu[b], cu[b+1]) = 1 + C_b*N rows: row cu[b] is CLS, row cu[b]+1+c*N+p is patch p of channel c.
+ */
+#ifndef CHADAVIT_B200_H
+#define CHADAVIT_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CHADAVIT_B200_VERSION 1
+
+/* ---- epilogue flags of cb_gemm_bf16 ---- */
+#define CB_EPI_RELU 1       /* C = max(C, 0)                                  (linear1 + F.relu, chada_vit.py:115)   */
+#define CB_EPI_RESIDUAL 2   /* C += aux                                       (x + attn / x + ff, chada_vit.py:99-100) */
+#define CB_EPI_RELU_MASK 4  /* C = aux > 0 ? C : 0                            (backward of F.relu)                    */
+#define CB_EPI_OUT_F32 8    /* store fp32 instead of bf16                                                             */
+#define CB_EPI_ATOMIC 16    /* fp32 atomic accumulate into C (split-K weight gradients)                               */
+#define CB_EPI_TOKENIZE 32  /* internal: tokenizer scatter epilogue (use cb_tokenize_fwd)                             */
+
+const char* cb_last_error(void);
+int cb_version(void);
+int cb_num_sms(void);
+/* synchronise `stream` and report any asynchronous kernel failure */
+int cb_sync_check(void* stream);
+
+/*
+ * C[M,N] (+)= alpha * op(A)[M,K] · op(B)[N,K]^T (+ bias[N]) with the epilogue in `flags`; bf16 operands, fp32
+ * accumulation on the tcgen05 tensor cores.  a_mn = 0: A is [M,K] row-major (lda);  a_mn = 1: A is stored [K,M]
+ * row-major (lda).  Same for B / b_mn with [N,K] vs [K,N].  Replaces every nn.Linear / F.linear on the path
+ * (MHA in/out projection chada_vit.py:106, linear1/linear2 :115, DINOHead.mlp / last_layer dino.py:65-81) and
+ * their autograd backward products.  N, lda, ldb multiples of 8; MN-major dims multiples of 32.
+ */
+int cb_gemm_bf16(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* C, int ldc, int M, int N,
+                 int K, const float* bias, const void* aux, int ld_aux, int flags, float alpha, int k_splits,
+                 void* stream);
+
+/*
+ * TokenLearner + channel_aware_tokenization (chada_vit.py:118-134, 219-270) on the packed layout.
+ *   x           fp32 (G,1,H,W): channel images in one_channel_collate_fn order (channels_strategies.py:31-85)
+ *   cu_seqlens  int32 [B+1];  chan_img int32 [G] = image index b of channel image g
+ *   w_pe bf16 [D, patch*patch] (token_learner.proj.weight), b_pe fp32 [D]
+ *   pos_patch fp32 [N, D] (pos_embed[0,0,1:], bicubic-resized by the caller when N != 196, chada_vit.py:201-217)
+ *   cls_row fp32 [D] = cls_token + pos_embed[0,0,0];  chan_tok fp32 [max_ch, D] or NULL (chada_vit.py:248)
+ *   patches_ws  bf16 [T, patch*patch] workspace (kept for cb_tokenize_bwd);  tokens bf16 [T, D] output
+ */
+int cb_tokenize_fwd(const float* x, int G, int H, int W, int patch, const int* cu_seqlens, const int* chan_img, int B,
+                    const void* w_pe, const float* b_pe, const float* pos_patch, const float* cls_row,
+                    const float* chan_tok, void* patches_ws, void* tokens, int T, int D, void* stream);
+/* gradients of the tokenizer parameters from dtokens bf16 [T,D]; all outputs fp32 and ACCUMULATED (+=):
+ * dw_pe [D,patch_elems], db_pe [D], dpos_patch [N,D], dcls_row [D] (-> cls_token and pos_embed[0]), dchan_tok [max_ch,D] or NULL */
+int cb_tokenize_bwd(const void* dtokens, const void* patches_ws, const int* cu_seqlens, const int* chan_img,
+                    const int* chan_idx, int G, int B, int npatch, int patch_elems, int T, int D, float* dw_pe,
+                    float* db_pe, float* dpos_patch, float* dcls_row, float* dchan_tok, int k_splits, void* stream);
+/* plain unfold + cast (patch rows in channel-image order), used by tests */
+int cb_im2col_bf16(const float* x, void* patches, int G, int H, int W, int patch, void* stream);
+
+/*
+ * nn.LayerNorm over the last dim (norm1 / norm2 / final norm, chada_vit.py:96,99,100,281).  x bf16 [*, D];
+ * row r of the output normalises input row in_idx[r] (or r when in_idx is NULL: the CLS gather of chada_vit.py:289
+ * is in_idx = cu_seqlens).  Either output may be NULL: y bf16 [rows,D], y_f32 fp32 [rows,D].  mean/rstd fp32 [rows].
+ */
+int cb_layernorm_fwd(const void* x, const int* in_idx, const float* gamma, const float* beta, void* y, float* y_f32,
+                     float* mean, float* rstd, int rows, int D, float eps, void* stream);
+/* dx[idx[r]] = dLN(dy[r]) (+ dres[idx[r]]);  dgamma/dbeta/dcolsum (= column sum of dLN) fp32 [D], ACCUMULATED. */
+int cb_layernorm_bwd(const void* dy, const float* dy_f32, const void* x, const int* idx, const float* gamma,
+                     const float* mean, const float* rstd, const void* dres, void* dx, float* dgamma, float* dbeta,
+                     float* dcolsum, int rows, int D, void* stream);
+/* out[n] += sum_t x[t,n]  (bias gradients);  x bf16 [T,N] with row stride ld */
+int cb_colsum_bf16(const void* x, int ld, float* out, int T, int N, void* stream);
+int cb_cast_f32_bf16(const float* in, void* out, long n, void* stream);
+int cb_gather_rows_f32(const void* x, const int* idx, float* out, int rows, int D, void* stream);
+
+/*
+ * Packed varlen multi-head self-attention forward (nn.MultiheadAttention inside _sa_block, chada_vit.py:105-111).
+ *   qkv bf16 [T, 3D] (= in_proj output: q | k | v, head h in columns h*d..(h+1)*d of each third)
+ *   work int32 [n_work, 4] = {first query row (global), seq_start, seq_end, head}: one entry per 128-query tile,
+ *        built on the host from list_num_channels (no device sync), longest sequences first
+ *   out bf16 [T, D];  lse fp32 [H, T] (log-sum-exp of the scaled scores, natural log) or NULL
+ */
+int cb_attn_varlen_fwd(const void* qkv, const int* work, int n_work, void* out, float* lse, int T, int D, int H,
+                       float softmax_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHADAVIT_B200_H */

@@ -1,0 +1,244 @@
+"""TEST INFRASTRUCTURE — CPU fp32 restatement of the reference's ChAda-ViT / DINO hot path.
+
+Parity status: PINNED against the reference's own modules (tests/golden/*.npz, see
+oracle/__init__.py).  This file restates, with plain torch fp32 CPU arithmetic and the
+reference's *padded + key-padding-mask* algorithm (NOT the packed varlen layout the CUDA
+path uses), every function of SURVEY.md §8(a):
+
+  tokenize_padded       src/backbones/vit/chada_vit.py:118-134 (TokenLearner), :219-270
+  interp_pos_embed      src/backbones/vit/chada_vit.py:185-217
+  encoder_layer         src/backbones/vit/chada_vit.py:75-116 (+ torch F.multi_head_attention_forward math)
+  backbone_forward      src/backbones/vit/chada_vit.py:272-289
+  dino_head             src/methods/dino.py:98-111 (+ weight_norm :78-81)
+  dino_loss             src/losses/dino.py:69-118
+  ema_update / cosine_tau   src/utils/momentum.py:63-87
+  dino_step             src/methods/base.py:695-707,1216-1218 + src/methods/dino.py:279,296,313-317
+
+Parameters are dicts keyed by the reference's state-dict names.  All functions are
+differentiable through torch autograd, which is how the tests obtain reference gradients.
+It is also the "port" CPU baseline timed by bench.py (cpu_baseline / --impl reference).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+FFN_DIM = 2048      # hard-coded in the reference: chada_vit.py:160
+PAD_CHANNELS = 10   # forward() always pads to 10: chada_vit.py:219,274
+
+
+# --------------------------------------------------------------------------- tokenizer
+def patch_embed(x: Tensor, w: Tensor, b: Tensor, patch: int) -> Tensor:
+    """TokenLearner.forward (chada_vit.py:130-134): Conv2d(1->D,k=s=patch) == unfold + GEMM.
+    x (G,1,H,W) -> (G, N, D), patch index p = py*(W/patch)+px."""
+    G, _, H, W = x.shape
+    hp, wp = H // patch, W // patch
+    cols = x[:, 0, : hp * patch, : wp * patch].reshape(G, hp, patch, wp, patch).permute(0, 1, 3, 2, 4)
+    cols = cols.reshape(G, hp * wp, patch * patch)
+    return cols @ w.reshape(w.shape[0], -1).t() + b
+
+
+def interp_pos_embed(pos_embed: Tensor, npatch: int, w: int, h: int, patch: int) -> Tensor:
+    """add_pos_encoding_per_channel(..., class_pos_embed=False) (chada_vit.py:185-217) -> (1,1,npatch,D)."""
+    N = pos_embed.shape[2] - 1
+    if npatch == N and w == h:
+        return pos_embed[:, :, 1:]
+    dim = pos_embed.shape[-1]
+    w0, h0 = w // patch + 0.1, h // patch + 0.1
+    s = int(math.sqrt(N))
+    pp = F.interpolate(pos_embed[:, :, 1:].reshape(1, s, s, dim).permute(0, 3, 1, 2),
+                       scale_factor=(w0 / math.sqrt(N), h0 / math.sqrt(N)), mode="bicubic")
+    assert int(w0) == pp.shape[-2] and int(h0) == pp.shape[-1]
+    return pp.permute(0, 2, 3, 1).reshape(1, -1, dim).unsqueeze(0)
+
+
+def tokenize_padded(x: Tensor, counts: Sequence[int], P: Dict[str, Tensor], patch: int,
+                    max_channels_model: int) -> Tuple[Tensor, Tensor]:
+    """channel_aware_tokenization (chada_vit.py:219-270): returns (B, 1+10N, D) and bool mask (B, 1+10N)."""
+    _, _, w, h = x.shape
+    tok = patch_embed(x, P["token_learner.proj.weight"], P["token_learner.proj.bias"], patch)
+    N, D = tok.shape[1], tok.shape[2]
+    chunks = torch.split(tok, list(counts), dim=0)
+    padded = torch.stack([torch.cat([c, tok.new_zeros(PAD_CHANNELS - c.shape[0], N, D)], 0)
+                          if c.shape[0] < PAD_CHANNELS else c for c in chunks], 0)      # (B,10,N,D)
+    B = padded.shape[0]
+    mask = (padded.reshape(B, -1, D) == 0).all(-1)                                       # :239
+    padded = padded + interp_pos_embed(P["pos_embed"], N, w, h, patch)                   # :245
+    if max_channels_model == PAD_CHANNELS:                                               # :248-250
+        padded = padded + P["channel_token"]
+    emb = padded.reshape(B, -1, D)
+    cls = (P["cls_token"] + P["pos_embed"][:, :, 0]).expand(B, -1, -1)                   # :259-262
+    emb = torch.cat([cls, emb], 1)
+    mask = torch.cat([mask.new_zeros(B, 1), mask], 1)
+    return emb, mask
+
+
+# --------------------------------------------------------------------------- encoder
+def mha(u: Tensor, mask: Tensor, w_in: Tensor, b_in: Tensor, w_o: Tensor, b_o: Tensor, nhead: int) -> Tensor:
+    """nn.MultiheadAttention(batch_first) self-attention with a bool key-padding mask."""
+    B, S, D = u.shape
+    d = D // nhead
+    qkv = u @ w_in.t() + b_in
+    q, k, v = qkv.split(D, dim=-1)
+    q = q.reshape(B, S, nhead, d).transpose(1, 2)
+    k = k.reshape(B, S, nhead, d).transpose(1, 2)
+    v = v.reshape(B, S, nhead, d).transpose(1, 2)
+    s = (q @ k.transpose(-1, -2)) / math.sqrt(d)
+    s = s.masked_fill(mask[:, None, None, :], float("-inf"))
+    a = torch.softmax(s, -1) @ v
+    return a.transpose(1, 2).reshape(B, S, D) @ w_o.t() + b_o
+
+
+def encoder_layer(x: Tensor, mask: Tensor, P: Dict[str, Tensor], pre: str, nhead: int, eps: float = 1e-5) -> Tensor:
+    """TransformerEncoderLayer.forward, norm_first=False branch (chada_vit.py:95-100): norm1 is applied twice."""
+    D = x.shape[-1]
+    g1, b1 = P[pre + "norm1.weight"], P[pre + "norm1.bias"]
+    u = F.layer_norm(x, (D,), g1, b1, eps)
+    a = mha(u, mask, P[pre + "self_attn.in_proj_weight"], P[pre + "self_attn.in_proj_bias"],
+            P[pre + "self_attn.out_proj.weight"], P[pre + "self_attn.out_proj.bias"], nhead)
+    y = F.layer_norm(x + a, (D,), g1, b1, eps)
+    ff = torch.relu(y @ P[pre + "linear1.weight"].t() + P[pre + "linear1.bias"]) @ P[pre + "linear2.weight"].t() \
+        + P[pre + "linear2.bias"]
+    return F.layer_norm(y + ff, (D,), P[pre + "norm2.weight"], P[pre + "norm2.bias"], eps)
+
+
+def backbone_forward(x: Tensor, index: int, list_num_channels: List[List[int]], P: Dict[str, Tensor], *,
+                     nhead: int, final_eps: float, patch: int = 16, return_all_tokens: bool = False,
+                     max_channels_model: int = 10, depth: int = 12) -> Tensor:
+    """ChAdaViT.forward (chada_vit.py:272-289)."""
+    counts = list_num_channels[index]
+    h, mask = tokenize_padded(x, counts, P, patch, max_channels_model)
+    for i in range(depth):
+        h = encoder_layer(h, mask, P, f"blocks.{i}.", nhead)
+    D = h.shape[-1]
+    h = F.layer_norm(h, (D,), P["norm.weight"], P["norm.bias"], final_eps)
+    if return_all_tokens:
+        return h[:, 1:][~mask[:, 1:]]
+    return h[:, 0]
+
+
+# --------------------------------------------------------------------------- DINO head / loss / EMA
+def dino_head(f: Tensor, P: Dict[str, Tensor]) -> Tensor:
+    """DINOHead.forward with use_bn=False, num_layers=3 (src/methods/dino.py:61-111)."""
+    h = F.gelu(f @ P["mlp.0.weight"].t() + P["mlp.0.bias"])
+    h = F.gelu(h @ P["mlp.2.weight"].t() + P["mlp.2.bias"])
+    h = h @ P["mlp.4.weight"].t() + P["mlp.4.bias"]
+    h = h / h.norm(dim=-1, keepdim=True).clamp_min(1e-12)                                # F.normalize
+    v, g = P["last_layer.weight_v"], P["last_layer.weight_g"]
+    w = v * (g / v.norm(dim=1, keepdim=True))                                            # weight_norm, dim=0
+    return h @ w.t()
+
+
+def teacher_temp(epoch: int, warmup_teacher_temp: float, teacher_temp_: float, warmup_epochs: int) -> float:
+    """teacher_temp_schedule[epoch] (src/losses/dino.py:62-67): linspace warm-up then constant."""
+    if epoch < warmup_epochs:
+        if warmup_epochs == 1:
+            return float(warmup_teacher_temp)
+        return float(warmup_teacher_temp + (teacher_temp_ - warmup_teacher_temp) * epoch / (warmup_epochs - 1))
+    return float(teacher_temp_)
+
+
+def dino_loss(student: Tensor, teacher: Tensor, center: Tensor, *, student_temp: float, teacher_temp: float,
+              num_large_crops: int = 2, center_momentum: float = 0.9, world_size: int = 1,
+              all_reduce_sum=None) -> Tuple[Tensor, Tensor]:
+    """DINOLoss.forward + update_center (src/losses/dino.py:69-118). Returns (loss, new_center)."""
+    s = (student / student_temp).chunk(num_large_crops)
+    q = torch.softmax((teacher - center) / teacher_temp, -1).detach().chunk(2)
+    total, n = 0.0, 0
+    for iq, qq in enumerate(q):
+        for iv, v in enumerate(s):
+            if iv == iq:
+                continue
+            total = total + torch.sum(-qq * F.log_softmax(v, -1), -1).mean()
+            n += 1
+    total = total / n
+    with torch.no_grad():
+        bc = teacher.sum(0, keepdim=True)
+        if all_reduce_sum is not None:
+            bc = all_reduce_sum(bc)
+        bc = bc / world_size / len(teacher)
+        new_center = center * center_momentum + bc * (1 - center_momentum)
+    return total, new_center
+
+
+def ema_update(online: Sequence[Tensor], momentum: Sequence[Tensor], tau: float) -> List[Tensor]:
+    """MomentumUpdater.update (src/utils/momentum.py:73-74)."""
+    return [tau * m + (1 - tau) * o for o, m in zip(online, momentum)]
+
+
+def cosine_tau(base_tau: float, final_tau: float, cur_step: int, max_steps: int) -> float:
+    """MomentumUpdater.update_tau (src/utils/momentum.py:84-87)."""
+    return final_tau - (final_tau - base_tau) * (math.cos(math.pi * cur_step / max_steps) + 1) / 2
+
+
+def dino_step(crops: Sequence[Tensor], list_num_channels: List[List[int]], student: Dict[str, Tensor],
+              student_head: Dict[str, Tensor], teacher: Dict[str, Tensor], teacher_head: Dict[str, Tensor],
+              center: Tensor, *, nhead: int, final_eps: float, num_large_crops: int = 2, student_temp: float = 0.1,
+              teacher_temp: float = 0.07, run_local_crops: bool = True) -> Tuple[Tensor, Tensor]:
+    """One DINO training-step forward with the reference wiring: the student head and the
+    loss see only the large crops; small crops go through the student backbone and are discarded.
+    Returns (loss, new_center)."""
+    z = []
+    for i in range(num_large_crops):
+        f = backbone_forward(crops[i], i, list_num_channels, student, nhead=nhead, final_eps=final_eps)
+        z.append(dino_head(f, student_head))
+    if run_local_crops:
+        for i, xc in enumerate(crops[num_large_crops:]):   # base.py:701-707: index restarts at 0 (Q12)
+            backbone_forward(xc, i, list_num_channels, student, nhead=nhead, final_eps=final_eps)
+    with torch.no_grad():
+        mz = []
+        for i in range(num_large_crops):
+            f = backbone_forward(crops[i], i, list_num_channels, teacher, nhead=nhead, final_eps=final_eps)
+            mz.append(dino_head(f, teacher_head))
+    return dino_loss(torch.cat(z), torch.cat(mz), center, student_temp=student_temp, teacher_temp=teacher_temp,
+                     num_large_crops=num_large_crops)
+
+
+# --------------------------------------------------------------------------- helpers for tests
+def backbone_shapes(D: int, depth: int = 12, patch: int = 16, npatch: int = 196, max_ch: int = 10) -> Dict[str, tuple]:
+    """State-dict names/shapes of ChAdaViT, in the reference's registration order."""
+    s: Dict[str, tuple] = {
+        "cls_token": (1, 1, D), "channel_token": (1, max_ch, 1, D), "pos_embed": (1, 1, npatch + 1, D),
+        "token_learner.proj.weight": (D, 1, patch, patch), "token_learner.proj.bias": (D,),
+    }
+    for i in range(depth):
+        p = f"blocks.{i}."
+        s[p + "self_attn.in_proj_weight"] = (3 * D, D)
+        s[p + "self_attn.in_proj_bias"] = (3 * D,)
+        s[p + "self_attn.out_proj.weight"] = (D, D)
+        s[p + "self_attn.out_proj.bias"] = (D,)
+        s[p + "linear1.weight"] = (FFN_DIM, D)
+        s[p + "linear1.bias"] = (FFN_DIM,)
+        s[p + "linear2.weight"] = (D, FFN_DIM)
+        s[p + "linear2.bias"] = (D,)
+        s[p + "norm1.weight"] = (D,)
+        s[p + "norm1.bias"] = (D,)
+        s[p + "norm2.weight"] = (D,)
+        s[p + "norm2.bias"] = (D,)
+    s["norm.weight"] = (D,)
+    s["norm.bias"] = (D,)
+    return s
+
+
+def head_shapes(in_dim: int, K: int, hidden: int = 2048, bottleneck: int = 256) -> Dict[str, tuple]:
+    return {
+        "mlp.0.weight": (hidden, in_dim), "mlp.0.bias": (hidden,),
+        "mlp.2.weight": (hidden, hidden), "mlp.2.bias": (hidden,),
+        "mlp.4.weight": (bottleneck, hidden), "mlp.4.bias": (bottleneck,),
+        "last_layer.weight_g": (K, 1), "last_layer.weight_v": (K, bottleneck),
+    }
+
+
+def packed_index(counts: Sequence[int], npatch: int) -> Tuple[List[int], List[int]]:
+    """cu_seqlens and, for every packed row, its row in the reference's padded (B,1+10N) layout."""
+    cu, rows = [0], []
+    S_pad = 1 + PAD_CHANNELS * npatch
+    for b, c in enumerate(counts):
+        n = 1 + c * npatch
+        rows.extend(b * S_pad + r for r in range(n))
+        cu.append(cu[-1] + n)
+    return cu, rows
