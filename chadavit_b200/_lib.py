@@ -20,14 +20,16 @@ SIGNATURES = {
     "cb_sync_check": [_vp],
     "cb_gemm_bf16": [_vp, _i, _i, _vp, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _f, _i, _vp],
     "cb_im2col_bf16": [_vp, _vp, _i, _i, _i, _i, _vp],
-    "cb_tokenize_fwd": [_vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
-    "cb_tokenize_bwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp],
+    "cb_tokenize_fwd": [_vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
+    "cb_tokenize_bwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp],
+    "cb_small_matmul_f32": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "cb_layernorm_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp],
     "cb_layernorm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
     "cb_colsum_bf16": [_vp, _i, _vp, _i, _i, _vp],
     "cb_cast_f32_bf16": [_vp, _vp, _l, _vp],
     "cb_gather_rows_f32": [_vp, _vp, _vp, _i, _i, _vp],
     "cb_attn_varlen_fwd": [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _f, _vp],
+    "cb_attn_varlen_bwd": [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _f, _vp],
 }
 
 _lib = None

@@ -1,0 +1,304 @@
+"""B200-native ChAda-ViT backbone behind the reference's API (src/backbones/vit/chada_vit.py).
+
+Same class names, constructor, ``forward(x, index, list_num_channels)`` contract, attributes and ``state_dict`` keys as
+the reference (chada_vit.py:136-339), but the arithmetic runs on a PACKED varlen token buffer through the sm_100a
+kernels of libchadavit_b200 (tokenizer GEMM with fused embedding epilogue, tcgen05 GEMMs, varlen flash-style
+attention, LayerNorm, and their backward kernels).  The torch submodules (``nn.Conv2d``, ``nn.MultiheadAttention``,
+``nn.Linear``, ``nn.LayerNorm``) are kept ONLY as parameter containers so that names, shapes, registration order and the
+default initialisation are the reference's; their ``forward`` is never called.  There is no CPU path.
+
+Block semantics reproduced exactly: ``a = MHA(norm1(x)); x = norm1(x + a); x = norm2(x + W2 relu(W1 x))``.
+"""
+from __future__ import annotations
+
+import math
+from functools import partial
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+from ..arena import ParamArena
+
+FFN_DIM = 2048      # chada_vit.py:160 (dim_feedforward hard-coded)
+PAD_CHANNELS = 10   # chada_vit.py:219 (forward always pads to 10; here: the upper bound on channels per image)
+
+
+def trunc_normal_(tensor: torch.Tensor, mean: float = 0.0, std: float = 1.0, a: float = -2.0, b: float = 2.0) -> torch.Tensor:
+    """Same algorithm as src/utils/misc.py:134-178 (inverse-CDF truncated normal)."""
+    def norm_cdf(v):
+        return (1.0 + math.erf(v / math.sqrt(2.0))) / 2.0
+    with torch.no_grad():
+        lo, hi = norm_cdf((a - mean) / std), norm_cdf((b - mean) / std)
+        tensor.uniform_(2 * lo - 1, 2 * hi - 1).erfinv_().mul_(std * math.sqrt(2.0)).add_(mean).clamp_(min=a, max=b)
+    return tensor
+
+
+class TransformerEncoderLayer(nn.Module):
+    """Parameter container with the reference layer's attribute names (chada_vit.py:29-116).  The computation
+    lives in ChAdaViT._block_fwd/_block_bwd on the packed layout."""
+
+    def __init__(self, d_model: int, nhead: int, dim_feedforward: int = FFN_DIM, dropout: float = 0.0,
+                 layer_norm_eps: float = 1e-5, batch_first: bool = True):
+        super().__init__()
+        if dropout != 0.0:
+            raise NotImplementedError("chadavit_b200: dropout / drop_path > 0 is not supported (the reference never enables it)")
+        self.self_attn = nn.MultiheadAttention(d_model, nhead, dropout=0.0, batch_first=batch_first)
+        self.linear1 = nn.Linear(d_model, dim_feedforward)
+        self.dropout = nn.Dropout(0.0)
+        self.linear2 = nn.Linear(dim_feedforward, d_model)
+        self.norm_first = False
+        self.norm1 = nn.LayerNorm(d_model, eps=layer_norm_eps)
+        self.norm2 = nn.LayerNorm(d_model, eps=layer_norm_eps)
+        self.dropout1 = nn.Dropout(0.0)
+        self.dropout2 = nn.Dropout(0.0)
+
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError("TransformerEncoderLayer is executed by ChAdaViT on the packed token buffer; call the backbone")
+
+
+class TokenLearner(nn.Module):
+    """Image to patch embedding (chada_vit.py:118-134): parameter container + geometry."""
+
+    def __init__(self, img_size: int = 224, patch_size: int = 16, in_chans: int = 1, embed_dim: int = 768):
+        super().__init__()
+        self.img_size = img_size
+        self.patch_size = patch_size
+        self.num_patches = (img_size // patch_size) * (img_size // patch_size)
+        self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=patch_size, stride=patch_size)
+
+    def forward(self, x):  # pragma: no cover
+        raise RuntimeError("TokenLearner is fused into the packed tokenizer kernel; call the backbone")
+
+
+class _Saved:
+    """Activations kept for the backward pass of one backbone call."""
+    __slots__ = ("lay", "patches", "blocks", "x_last", "fin_idx", "fin_mean", "fin_rstd", "interp", "hw")
+
+
+class _BackboneFn(torch.autograd.Function):
+    """Autograd bridge: ONE node for the whole backbone so ``loss.backward()`` of the unchanged callers works."""
+
+    @staticmethod
+    def forward(ctx, module: "ChAdaViT", x: torch.Tensor, counts: Tuple[int, ...], *params):
+        out, saved = module._forward_impl(x, counts, save=True)
+        ctx.module, ctx.saved = module, saved
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        m: ChAdaViT = ctx.module
+        gflat = torch.zeros_like(m.arena.fp32)
+        m._backward_impl(ctx.saved, dout.contiguous().float(), gflat)
+        ctx.saved = None
+        grads = tuple(m.arena.g32(n, gflat) if p.requires_grad else None for n, p in zip(m.arena.names, m.arena.params))
+        return (None, None, None) + grads
+
+
+class ChAdaViT(nn.Module):
+    """Channel Adaptive Vision Transformer (drop-in for chada_vit.py:136-330)."""
+
+    def __init__(self, img_size=[224], in_chans=1, embed_dim=192, patch_size=16, num_classes=0, depth=12, num_heads=12,
+                 drop_rate=0., drop_path_rate=0., norm_layer=nn.LayerNorm, return_all_tokens=True, max_number_channels=10, **kwargs):
+        super().__init__()
+        if drop_rate != 0.0 or drop_path_rate != 0.0:
+            raise NotImplementedError("chadavit_b200: drop_rate / drop_path_rate > 0 is not supported (reference default is 0)")
+        if in_chans != 1:
+            raise ValueError("ChAdaViT tokenises one channel at a time (in_chans must be 1)")
+        if embed_dim % num_heads or embed_dim % 32:
+            raise ValueError("embed_dim must be a multiple of 32 and divisible by num_heads")
+        if embed_dim // num_heads not in (16, 32, 64, 96, 128):
+            raise ValueError(f"unsupported head_dim {embed_dim // num_heads}: the sm_100a attention kernels support 16/32/64/96/128")
+        self.num_features = self.embed_dim = embed_dim
+        self.max_channels = max_number_channels
+        self.num_heads = num_heads
+        self.depth = depth
+        self.token_learner = TokenLearner(img_size=img_size[0], patch_size=patch_size, in_chans=in_chans, embed_dim=embed_dim)
+        num_patches = self.token_learner.num_patches
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, embed_dim))
+        self.channel_token = nn.Parameter(torch.zeros(1, self.max_channels, 1, embed_dim))
+        self.pos_embed = nn.Parameter(torch.zeros(1, 1, num_patches + 1, embed_dim))
+        self.pos_drop = nn.Dropout(p=0.0)
+        self.blocks = nn.ModuleList([TransformerEncoderLayer(embed_dim, num_heads, FFN_DIM, 0.0) for _ in range(depth)])
+        self.norm = norm_layer(embed_dim)
+        self.head = nn.Linear(embed_dim, num_classes) if num_classes > 0 else nn.Identity()
+        self.return_all_tokens = return_all_tokens
+        trunc_normal_(self.pos_embed, std=.02)
+        trunc_normal_(self.cls_token, std=.02)
+        trunc_normal_(self.channel_token, std=.02)
+        self.apply(self._init_weights)          # chada_vit.py:171-183 (Conv2d / in_proj keep torch defaults)
+        self._arena: Optional[ParamArena] = None
+        self._layouts: Dict[tuple, ops.PackedLayout] = {}
+        self._interp: Dict[tuple, torch.Tensor] = {}
+
+    @staticmethod
+    def _init_weights(m):
+        if isinstance(m, nn.Linear):
+            trunc_normal_(m.weight, std=.02)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+        elif isinstance(m, nn.LayerNorm):
+            nn.init.constant_(m.bias, 0)
+            nn.init.constant_(m.weight, 1.0)
+
+    # ------------------------------------------------------------------ parameter plumbing
+    @property
+    def arena(self) -> ParamArena:
+        if self._arena is None:
+            self._arena = ParamArena(self)
+        return self._arena
+
+    def _ready(self) -> ParamArena:
+        a = self.arena
+        a.ensure()
+        if a.fp32.device.type != "cuda":
+            raise RuntimeError("chadavit_b200.ChAdaViT runs on CUDA (sm_100a) only: move the module to the GPU; there is no CPU fallback")
+        a.refresh_bf16()
+        return a
+
+    def _layout(self, counts: Sequence[int], npatch: int, device) -> ops.PackedLayout:
+        key = (tuple(counts), npatch, str(device))
+        lay = self._layouts.get(key)
+        if lay is None:
+            if len(self._layouts) > 64:
+                self._layouts.clear()
+            lay = self._layouts[key] = ops.PackedLayout(counts, npatch, device, PAD_CHANNELS)
+        return lay
+
+    def _interp_matrix(self, hp: int, wp: int, H: int, W: int, device) -> torch.Tensor:
+        """(hp*wp, N0) fp32 map equal to the reference's bicubic resize of the patch position grid
+        (add_pos_encoding_per_channel, chada_vit.py:201-217, incl. the DINO +0.1 trick); built once per geometry."""
+        key = (hp, wp, str(device))
+        if key not in self._interp:
+            N0 = self.pos_embed.shape[2] - 1
+            s = int(math.sqrt(N0))
+            eye = torch.eye(N0).reshape(1, N0, s, s)
+            w0, h0 = H // self.token_learner.patch_size + 0.1, W // self.token_learner.patch_size + 0.1
+            m = F.interpolate(eye, scale_factor=(w0 / math.sqrt(N0), h0 / math.sqrt(N0)), mode="bicubic")
+            assert int(w0) == m.shape[-2] and int(h0) == m.shape[-1]
+            self._interp[key] = m.reshape(N0, -1).t().contiguous().to(device)
+        return self._interp[key]
+
+    # ------------------------------------------------------------------ public API (reference signatures)
+    def forward(self, x: torch.Tensor, index: int, list_num_channels: List[List[int]]) -> torch.Tensor:
+        counts = tuple(int(c) for c in list_num_channels[index])
+        if not x.is_cuda:
+            raise RuntimeError("chadavit_b200.ChAdaViT needs CUDA inputs (no CPU fallback)")
+        self._ready()
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.arena.params):
+            return _BackboneFn.apply(self, x, counts, *self.arena.params)
+        return self._forward_impl(x, counts, save=False)[0]
+
+    def get_last_selfattention(self, x):
+        raise NotImplementedError("get_last_selfattention (main_attn.py) is outside the accelerated path in this round")
+
+    # ------------------------------------------------------------------ forward on the packed layout
+    def _forward_impl(self, x: torch.Tensor, counts: Sequence[int], save: bool):
+        a = self.arena
+        D, P = self.embed_dim, self.token_learner.patch_size
+        G, _, H, W = x.shape
+        hp, wp = H // P, W // P
+        N, N0 = hp * wp, self.pos_embed.shape[2] - 1
+        lay = self._layout(counts, N, x.device)
+        pos = a.v32("pos_embed").view(N0 + 1, D)
+        interp = None
+        if N == N0 and H == W:
+            pos_patch = pos[1:]
+        else:
+            interp = self._interp_matrix(hp, wp, H, W, x.device)
+            pos_patch = ops.small_matmul_f32(interp, pos[1:])
+        chan = a.v32("channel_token").view(self.max_channels, D) if self.max_channels == PAD_CHANNELS else None  # chada_vit.py:248
+        tok, patches = ops.tokenize_fwd(x, lay, P, a.v16("token_learner.proj.weight").view(D, P * P), a.v32("token_learner.proj.bias"),
+                                        pos_patch, pos[0], a.v32("cls_token").view(D), chan)
+        blocks = []
+        h = tok
+        for i in range(self.depth):
+            h, sv = self._block_fwd(i, h, lay, save)
+            blocks.append(sv)
+        idx = lay.non_cls_rows() if self.return_all_tokens else lay.cu[:-1]
+        out, mean, rstd = ops.layernorm_fwd(h, a.v32("norm.weight"), a.v32("norm.bias"), self.norm.eps, in_idx=idx, out_f32=True, save_stats=save)
+        if not save:
+            return out, None
+        s = _Saved()
+        s.lay, s.patches, s.blocks, s.x_last, s.fin_idx, s.fin_mean, s.fin_rstd, s.interp, s.hw = lay, patches, blocks, h, idx, mean, rstd, interp, (H, W)
+        return out, s
+
+    def _block_fwd(self, i: int, x: torch.Tensor, lay: ops.PackedLayout, save: bool):
+        a, pre = self.arena, f"blocks.{i}."
+        eps = self.blocks[i].norm1.eps
+        g1, b1 = a.v32(pre + "norm1.weight"), a.v32(pre + "norm1.bias")
+        u, m1a, r1a = ops.layernorm_fwd(x, g1, b1, eps, save_stats=save)
+        qkv = ops.gemm(u, a.v16(pre + "self_attn.in_proj_weight"), bias=a.v32(pre + "self_attn.in_proj_bias"))
+        att, lse = ops.attn_fwd(qkv, lay, self.num_heads, need_lse=save)
+        z1 = ops.gemm(att, a.v16(pre + "self_attn.out_proj.weight"), bias=a.v32(pre + "self_attn.out_proj.bias"), aux=x, flags=ops.EPI_RESIDUAL)
+        y, m1b, r1b = ops.layernorm_fwd(z1, g1, b1, eps, save_stats=save)
+        hid = ops.gemm(y, a.v16(pre + "linear1.weight"), bias=a.v32(pre + "linear1.bias"), flags=ops.EPI_RELU)
+        z2 = ops.gemm(hid, a.v16(pre + "linear2.weight"), bias=a.v32(pre + "linear2.bias"), aux=y, flags=ops.EPI_RESIDUAL)
+        out, m2, r2 = ops.layernorm_fwd(z2, a.v32(pre + "norm2.weight"), a.v32(pre + "norm2.bias"), self.blocks[i].norm2.eps, save_stats=save)
+        if not save:
+            return out, None
+        return out, (x, u, m1a, r1a, qkv, att, lse, z1, m1b, r1b, y, hid, z2, m2, r2)
+
+    # ------------------------------------------------------------------ backward on the packed layout
+    def _backward_impl(self, s: _Saved, dout: torch.Tensor, gflat: torch.Tensor) -> None:
+        """Accumulates parameter gradients of one backbone call into the fp32 arena-shaped buffer ``gflat``."""
+        a = self.arena
+        g = lambda n: a.g32(n, gflat)  # noqa: E731
+        D, P = self.embed_dim, self.token_learner.patch_size
+        lay = s.lay
+        # final norm (+ CLS / all-token gather): rows not selected get zero gradient
+        dx = ops.layernorm_bwd(dout, s.x_last, a.v32("norm.weight"), s.fin_mean, s.fin_rstd, dgamma=g("norm.weight"),
+                               dbeta=g("norm.bias"), idx=s.fin_idx)
+        for i in reversed(range(self.depth)):
+            dx = self._block_bwd(i, s.blocks[i], dx, lay, gflat)
+            s.blocks[i] = None
+        N0 = self.pos_embed.shape[2] - 1
+        dpos = g("pos_embed").view(N0 + 1, D)
+        dpos_patch = dpos[1:] if s.interp is None else torch.zeros(lay.npatch, D, device=dx.device, dtype=torch.float32)
+        dchan = g("channel_token").view(self.max_channels, D) if self.max_channels == PAD_CHANNELS else None
+        ops.tokenize_bwd(dx, s.patches, lay, dw_pe=g("token_learner.proj.weight").view(D, P * P), db_pe=g("token_learner.proj.bias"),
+                         dpos_patch=dpos_patch, dpos0=dpos[0], dcls_tok=g("cls_token").view(D), dchan_tok=dchan)
+        if s.interp is not None:  # pos_embed receives gradient through the bicubic resize (SURVEY.md §8c probe)
+            ops.small_matmul_f32(s.interp, dpos_patch, trans_a=True, out=dpos[1:], accumulate=True)
+
+    def _block_bwd(self, i: int, sv, dxo: torch.Tensor, lay: ops.PackedLayout, gflat: torch.Tensor) -> torch.Tensor:
+        a, pre = self.arena, f"blocks.{i}."
+        g = lambda n: a.g32(pre + n, gflat)  # noqa: E731
+        x, u, m1a, r1a, qkv, att, lse, z1, m1b, r1b, y, hid, z2, m2, r2 = sv
+        T, D = x.shape
+        A = ops.EPI_ATOMIC
+        sk = lambda tiles: ops.splitk_for(T, tiles)  # noqa: E731
+        mt = lambda n: (n + 127) // 128  # noqa: E731
+        # x' = LN2(z2), z2 = y + relu(y W1^T + b1) W2^T + b2
+        dz2 = ops.layernorm_bwd(dxo, z2, a.v32(pre + "norm2.weight"), m2, r2, dgamma=g("norm2.weight"), dbeta=g("norm2.bias"),
+                                dcolsum=g("linear2.bias"))
+        ops.gemm(dz2, hid, a_mn=True, b_mn=True, flags=A, out=g("linear2.weight"), k_splits=sk(mt(D) * (FFN_DIM // 256)))
+        dh = ops.gemm(dz2, a.v16(pre + "linear2.weight"), b_mn=True, aux=hid, flags=ops.EPI_RELU_MASK)
+        ops.colsum(dh, g("linear1.bias"))
+        ops.gemm(dh, y, a_mn=True, b_mn=True, flags=A, out=g("linear1.weight"), k_splits=sk(mt(FFN_DIM) * mt(D)))
+        dy = ops.gemm(dh, a.v16(pre + "linear1.weight"), b_mn=True, aux=dz2, flags=ops.EPI_RESIDUAL)
+        # y = LN1(z1), z1 = x + att Wo^T + bo      (second use of norm1: gradients accumulate)
+        dz1 = ops.layernorm_bwd(dy, z1, a.v32(pre + "norm1.weight"), m1b, r1b, dgamma=g("norm1.weight"), dbeta=g("norm1.bias"),
+                                dcolsum=g("self_attn.out_proj.bias"))
+        ops.gemm(dz1, att, a_mn=True, b_mn=True, flags=A, out=g("self_attn.out_proj.weight"), k_splits=sk(mt(D) * mt(D)))
+        datt = ops.gemm(dz1, a.v16(pre + "self_attn.out_proj.weight"), b_mn=True)
+        dqkv = ops.attn_bwd(datt, qkv, att, lse, lay, self.num_heads)
+        ops.colsum(dqkv, g("self_attn.in_proj_bias"))
+        ops.gemm(dqkv, u, a_mn=True, b_mn=True, flags=A, out=g("self_attn.in_proj_weight"), k_splits=sk(mt(3 * D) * mt(D)))
+        du = ops.gemm(dqkv, a.v16(pre + "self_attn.in_proj_weight"), b_mn=True)
+        # u = LN1(x) (first use) ; dx = dLN1(du) + dz1 (residual into z1)
+        return ops.layernorm_bwd(du, x, a.v32(pre + "norm1.weight"), m1a, r1a, dgamma=g("norm1.weight"), dbeta=g("norm1.bias"), dres=dz1)
+
+
+def chada_vit(**kwargs):
+    """Factory with the reference's semantics (chada_vit.py:333-339): depth 12, 2 heads, final LayerNorm eps 1e-6."""
+    return ChAdaViT(patch_size=kwargs['patch_size'], embed_dim=kwargs['embed_dim'], depth=12, num_heads=2,
+                    norm_layer=partial(nn.LayerNorm, eps=1e-6), return_all_tokens=kwargs['return_all_tokens'],
+                    max_number_channels=kwargs['max_number_channels'])
+
+
+def vit_channels(method, *args, **kwargs):
+    """src/backbones/vit/__init__.py:57-59."""
+    return chada_vit(**kwargs)

@@ -1,0 +1,385 @@
+// Varlen multi-head self-attention backward for sm_100a (autograd of the SDPA inside nn.MultiheadAttention,
+// chada_vit.py:105-111).  One pass, flash-style recompute:
+//   work item = (sequence, head, 128-row KV tile); the CTA loops over the sequence's 128-row Q tiles
+//     S^T  = K Q^T            (SS MMA, M = kv, N = q)            -> TMEM
+//     dP^T = V dO^T           (SS MMA)                           -> TMEM
+//     P^T  = exp2(S^T*c - LSE),  dS^T = scale * P^T o (dP^T - delta)      (128 threads, 1 thread = 1 kv row)
+//     dV  += P^T dO           (TS MMA, P^T bf16 in TMEM, dO consumed MN-major from its TMA tile)
+//     dK  += dS^T Q           (SS MMA, dS^T bf16 in swizzled smem, Q MN-major)
+//     dQ_i = dS K             (SS MMA: the SAME dS^T smem tile read MN-major, K MN-major) -> TMEM -> fp32 atomics
+//   dK/dV stay in TMEM for the whole work item and are written once as bf16 into dqkv[:, D:3D].
+// delta = rowsum(dO o O) and the fp32->bf16 conversion of the dQ accumulator are small row-wise kernels below.
+#include "common.cuh"
+#include "chadavit_b200.h"
+#include "internal.h"
+
+namespace cb {
+
+template <int HD>
+struct BwdCfg {
+  static constexpr int CHUNK = (HD % 64 == 0) ? 64 : (HD % 32 == 0 ? 32 : 16);
+  static constexpr int NCH = HD / CHUNK;
+  static constexpr int SWZ = CHUNK == 64 ? 3 : (CHUNK == 32 ? 2 : 1);
+  static constexpr int CHUNK_BYTES = 128 * CHUNK * 2;
+  static constexpr int TILE_BYTES = NCH * CHUNK_BYTES;
+  static constexpr int SBO = 8 * CHUNK * 2;
+  static constexpr int QDO_STAGES = HD <= 96 ? 2 : 1;
+  static constexpr int DS_BYTES = 128 * 128 * 2;  // two [128 x 64] 128B-swizzled sub-tiles
+  static constexpr int SMEM_BYTES = TILE_BYTES * (2 + 2 * QDO_STAGES) + DS_BYTES + 1024 /*lse,delta*/ + 1024 + 256;
+  static constexpr int COL_S = 0, COL_DP = 128, COL_DK = 256, COL_DV = 384;
+};
+
+__device__ __forceinline__ float fast_exp2_b(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+struct AttnBwdArgs {
+  const int4* work;  // {kv_row0 (global row), seq_start, seq_end, head}
+  int n_work;
+  const float* lse;    // [H, T]
+  const float* delta;  // [H, T]
+  float* dq_acc;       // [T, D] fp32, zero-initialised
+  __nv_bfloat16* dqkv; // [T, 3D]: dK -> cols [D,2D), dV -> cols [2D,3D)
+  int T, D;
+  float scale, scale_log2;
+};
+
+template <int HD>
+__global__ void __launch_bounds__(192, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO, const AttnBwdArgs a) {
+  using Cfg = BwdCfg<HD>;
+  constexpr int NS = Cfg::QDO_STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + Cfg::TILE_BYTES;
+  uint8_t* sQ = sV + Cfg::TILE_BYTES;                  // [NS]
+  uint8_t* sDO = sQ + NS * Cfg::TILE_BYTES;            // [NS]
+  uint8_t* sDS = sDO + NS * Cfg::TILE_BYTES;           // dS^T
+  float* sLSE = reinterpret_cast<float*>(sDS + Cfg::DS_BYTES);
+  float* sDelta = sLSE + 128;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + 128);
+  uint64_t* kv_full = bars + 0;
+  uint64_t* kv_empty = bars + 1;
+  uint64_t* qdo_full = bars + 2;           // [NS]
+  uint64_t* qdo_empty = qdo_full + NS;     // [NS]
+  uint64_t* s_full = qdo_empty + NS;
+  uint64_t* dp_full = s_full + 1;
+  uint64_t* p_ready = dp_full + 1;         // 128 arrivals
+  uint64_t* dq_full = p_ready + 1;
+  uint64_t* dq_drained = dq_full + 1;      // 128 arrivals
+  uint64_t* dkv_full = dq_drained + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dkv_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQKV);
+    tma_prefetch_desc(&tmDO);
+    mbar_init(kv_full, 1); mbar_init(kv_empty, 1);
+    for (int i = 0; i < NS; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
+    mbar_init(s_full, 1); mbar_init(dp_full, 1); mbar_init(p_ready, 128); mbar_init(dq_full, 1); mbar_init(dq_drained, 128);
+    mbar_init(dkv_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t it = 0, wi = 0;
+      for (int w = blockIdx.x; w < a.n_work; w += gridDim.x, ++wi) {
+        const int4 wk = a.work[w];
+        const int head = wk.w;
+        const int nq = (wk.z - wk.y + 127) / 128;
+        mbar_wait(kv_empty, (wi & 1) ^ 1);
+        mbar_expect_tx(kv_full, 2 * Cfg::TILE_BYTES);
+#pragma unroll
+        for (int c = 0; c < Cfg::NCH; ++c) {
+          tma_load_2d(sK + c * Cfg::CHUNK_BYTES, &tmQKV, kv_full, a.D + head * HD + c * Cfg::CHUNK, wk.x);
+          tma_load_2d(sV + c * Cfg::CHUNK_BYTES, &tmQKV, kv_full, 2 * a.D + head * HD + c * Cfg::CHUNK, wk.x);
+        }
+        for (int i = 0; i < nq; ++i, ++it) {
+          const int s = it % NS; const uint32_t ph = (it / NS) & 1;
+          mbar_wait(&qdo_empty[s], ph ^ 1);
+          mbar_expect_tx(&qdo_full[s], 2 * Cfg::TILE_BYTES);
+          const int row = wk.y + i * 128;
+#pragma unroll
+          for (int c = 0; c < Cfg::NCH; ++c) {
+            tma_load_2d(sQ + s * Cfg::TILE_BYTES + c * Cfg::CHUNK_BYTES, &tmQKV, &qdo_full[s], head * HD + c * Cfg::CHUNK, row);
+            tma_load_2d(sDO + s * Cfg::TILE_BYTES + c * Cfg::CHUNK_BYTES, &tmDO, &qdo_full[s], head * HD + c * Cfg::CHUNK, row);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);   // S^T, dP^T : both K-major
+      constexpr uint32_t idesc_dv = umma_idesc_bf16(128, HD, false, true);    // dV (TS) / dK (SS): B MN-major
+      constexpr uint32_t idesc_dq = umma_idesc_bf16(128, HD, true, true);     // dQ: A (dS^T) MN-major, B (K) MN-major
+      const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), ds_addr = smem_u32(sDS);
+      uint32_t it = 0, wi = 0;
+      for (int w = blockIdx.x; w < a.n_work; w += gridDim.x, ++wi) {
+        const int4 wk = a.work[w];
+        const int nq = (wk.z - wk.y + 127) / 128;
+        mbar_wait(kv_full, wi & 1);
+        for (int i = 0; i < nq; ++i, ++it) {
+          const int s = it % NS; const uint32_t ph = (it / NS) & 1;
+          const uint32_t q_addr = smem_u32(sQ + s * Cfg::TILE_BYTES), do_addr = smem_u32(sDO + s * Cfg::TILE_BYTES);
+          mbar_wait(&qdo_full[s], ph);
+          tc_fence_after();
+          // S^T = K Q^T
+#pragma unroll
+          for (int kk = 0; kk < HD / 16; ++kk) {
+            const int c = (kk * 16) / Cfg::CHUNK, off = ((kk * 16) % Cfg::CHUNK) * 2;
+            umma_ss(tmem_base + Cfg::COL_S, umma_smem_desc(k_addr + c * Cfg::CHUNK_BYTES + off, 16, Cfg::SBO, Cfg::SWZ),
+                    umma_smem_desc(q_addr + c * Cfg::CHUNK_BYTES + off, 16, Cfg::SBO, Cfg::SWZ), idesc_s, kk > 0 ? 1u : 0u);
+          }
+          tc_commit(s_full);
+          // dP^T = V dO^T   (its TMEM region held dQ of the previous iteration: wait until that was drained)
+          if (it > 0) { mbar_wait(dq_drained, (it - 1) & 1); tc_fence_after(); }
+#pragma unroll
+          for (int kk = 0; kk < HD / 16; ++kk) {
+            const int c = (kk * 16) / Cfg::CHUNK, off = ((kk * 16) % Cfg::CHUNK) * 2;
+            umma_ss(tmem_base + Cfg::COL_DP, umma_smem_desc(v_addr + c * Cfg::CHUNK_BYTES + off, 16, Cfg::SBO, Cfg::SWZ),
+                    umma_smem_desc(do_addr + c * Cfg::CHUNK_BYTES + off, 16, Cfg::SBO, Cfg::SWZ), idesc_s, kk > 0 ? 1u : 0u);
+          }
+          tc_commit(dp_full);
+          mbar_wait(p_ready, it & 1);
+          tc_fence_after();
+          // dV += P^T dO   (A = P^T in TMEM; B = dO tile read MN-major: N = HD, K = q)
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            umma_ts(tmem_base + Cfg::COL_DV, tmem_base + Cfg::COL_S + kk * 8,
+                    umma_smem_desc(do_addr + kk * 16 * Cfg::CHUNK * 2, Cfg::CHUNK_BYTES, Cfg::SBO, Cfg::SWZ), idesc_dv,
+                    (i > 0 || kk > 0) ? 1u : 0u);
+          // dK += dS^T Q   (A = dS^T smem K-major: two [128x64] sub-tiles; B = Q tile MN-major)
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            umma_ss(tmem_base + Cfg::COL_DK, umma_smem_desc(ds_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024, 3),
+                    umma_smem_desc(q_addr + kk * 16 * Cfg::CHUNK * 2, Cfg::CHUNK_BYTES, Cfg::SBO, Cfg::SWZ), idesc_dv,
+                    (i > 0 || kk > 0) ? 1u : 0u);
+          // dQ_i = dS K    (A = dS^T smem read MN-major: M = q (2 blocks of 64, LBO 16 KB), K = kv; B = K tile MN-major)
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            umma_ss(tmem_base + Cfg::COL_DP, umma_smem_desc(ds_addr + kk * 2048, 16384, 1024, 3),
+                    umma_smem_desc(k_addr + kk * 16 * Cfg::CHUNK * 2, Cfg::CHUNK_BYTES, Cfg::SBO, Cfg::SWZ), idesc_dq, kk > 0 ? 1u : 0u);
+          tc_commit(dq_full);
+          tc_commit(&qdo_empty[s]);
+        }
+        tc_commit(dkv_full);
+        tc_commit(kv_empty);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax-backward / dQ drain / dK,dV epilogue
+    const int q4 = warp & 3;
+    const int r = q4 * 32 + lane;               // kv row of this thread inside the tile; also q row when draining dQ
+    const int tid128 = (warp - 2) * 32 + lane;  // 0..127
+    const uint32_t lane_addr = tmem_base + (uint32_t(q4 * 32) << 16);
+    const float LOG2E = 1.4426950408889634f;
+    uint32_t it = 0, wi = 0;
+    for (int w = blockIdx.x; w < a.n_work; w += gridDim.x, ++wi) {
+      const int4 wk = a.work[w];
+      const int head = wk.w;
+      const int nq = (wk.z - wk.y + 127) / 128;
+      const bool kv_ok = wk.x + r < wk.z;
+      for (int i = 0; i < nq; ++i, ++it) {
+        const int q0 = wk.y + i * 128;
+        // stage LSE / delta of this q tile (all 128 threads need all 128 values)
+        {
+          const int t = q0 + tid128;
+          const bool ok = t < wk.z;
+          sLSE[tid128] = ok ? a.lse[(long)head * a.T + t] * LOG2E : INFINITY;   // +inf -> p = 0 for rows past the sequence
+          sDelta[tid128] = ok ? a.delta[(long)head * a.T + t] : 0.f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        mbar_wait(s_full, it & 1);
+        mbar_wait(dp_full, it & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c4 = 0; c4 < 4; ++c4) {
+          uint32_t sr[32], dpr[32];
+          tmem_ld32(lane_addr + Cfg::COL_S + c4 * 32, sr);
+          tmem_ld32(lane_addr + Cfg::COL_DP + c4 * 32, dpr);
+          tmem_ld_wait();
+          uint32_t pp[16], dsp[16];
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            float p0 = fast_exp2_b(__uint_as_float(sr[j]) * a.scale_log2 - sLSE[c4 * 32 + j]);
+            float p1 = fast_exp2_b(__uint_as_float(sr[j + 1]) * a.scale_log2 - sLSE[c4 * 32 + j + 1]);
+            if (!kv_ok) { p0 = 0.f; p1 = 0.f; }
+            const float d0 = p0 * (__uint_as_float(dpr[j]) - sDelta[c4 * 32 + j]) * a.scale;
+            const float d1 = p1 * (__uint_as_float(dpr[j + 1]) - sDelta[c4 * 32 + j + 1]) * a.scale;
+            pp[j >> 1] = pack_bf16(p0, p1);
+            dsp[j >> 1] = pack_bf16(d0, d1);
+          }
+          tmem_st16(lane_addr + Cfg::COL_S + c4 * 16, pp);
+          // dS^T row r, q columns [32*c4, 32*c4+32) -> sub-tile (c4>>1), 16B chunks 4*(c4&1) .. +3, 128B swizzle
+          uint8_t* base = sDS + (c4 >> 1) * 16384 + r * 128;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int chunk = ((c4 & 1) * 4 + k) ^ (r & 7);
+            *reinterpret_cast<uint4*>(base + chunk * 16) = make_uint4(dsp[4 * k], dsp[4 * k + 1], dsp[4 * k + 2], dsp[4 * k + 3]);
+          }
+        }
+        tmem_st_wait();
+        fence_proxy_async();   // generic-proxy smem writes (dS^T) -> visible to the tensor-core (async) proxy
+        tc_fence_before();
+        mbar_arrive(p_ready);
+        // ---- drain dQ_i (rows = q) with fp32 atomics
+        mbar_wait(dq_full, it & 1);
+        tc_fence_after();
+        {
+          const int t = q0 + r;
+          const bool ok = t < wk.z;
+          float* dst = a.dq_acc + (long)t * a.D + head * HD;
+#pragma unroll
+          for (int c = 0; c < HD; c += 32) {
+            if (HD - c >= 32) {
+              uint32_t o[32];
+              tmem_ld32(lane_addr + Cfg::COL_DP + c, o);
+              tmem_ld_wait();
+              if (ok) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                  atomicAdd(reinterpret_cast<float4*>(dst + c + j), make_float4(__uint_as_float(o[j]), __uint_as_float(o[j + 1]),
+                                                                               __uint_as_float(o[j + 2]), __uint_as_float(o[j + 3])));
+              }
+            } else {
+              uint32_t o[16];
+              tmem_ld16(lane_addr + Cfg::COL_DP + c, o);
+              tmem_ld_wait();
+              if (ok) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                  atomicAdd(reinterpret_cast<float4*>(dst + c + j), make_float4(__uint_as_float(o[j]), __uint_as_float(o[j + 1]),
+                                                                               __uint_as_float(o[j + 2]), __uint_as_float(o[j + 3])));
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(dq_drained);
+      }
+      // ---- dK, dV of this kv tile -> bf16 into dqkv
+      mbar_wait(dkv_full, wi & 1);
+      tc_fence_after();
+      {
+        __nv_bfloat16* dk_dst = a.dqkv + (long)(wk.x + r) * (3 * a.D) + a.D + head * HD;
+        __nv_bfloat16* dv_dst = dk_dst + a.D;
+#pragma unroll
+        for (int which = 0; which < 2; ++which) {
+          __nv_bfloat16* dst = which ? dv_dst : dk_dst;
+          const uint32_t col = which ? Cfg::COL_DV : Cfg::COL_DK;
+#pragma unroll
+          for (int c = 0; c < HD; c += 16) {
+            uint32_t o[16];
+            tmem_ld16(lane_addr + col + c, o);
+            tmem_ld_wait();
+            if (kv_ok) {
+              *reinterpret_cast<uint4*>(dst + c) = make_uint4(pack_bf16(__uint_as_float(o[0]), __uint_as_float(o[1])), pack_bf16(__uint_as_float(o[2]), __uint_as_float(o[3])),
+                                                              pack_bf16(__uint_as_float(o[4]), __uint_as_float(o[5])), pack_bf16(__uint_as_float(o[6]), __uint_as_float(o[7])));
+              *reinterpret_cast<uint4*>(dst + c + 8) = make_uint4(pack_bf16(__uint_as_float(o[8]), __uint_as_float(o[9])), pack_bf16(__uint_as_float(o[10]), __uint_as_float(o[11])),
+                                                                  pack_bf16(__uint_as_float(o[12]), __uint_as_float(o[13])), pack_bf16(__uint_as_float(o[14]), __uint_as_float(o[15])));
+            }
+          }
+        }
+      }
+      tc_fence_before();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// delta[h, t] = sum_c dO[t, h*d + c] * O[t, h*d + c]     (one warp per token row)
+__global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ dO, const __nv_bfloat16* __restrict__ O, float* __restrict__ delta, int T,
+                                  int D, int H) {
+  const int lane = threadIdx.x & 31;
+  const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= T) return;
+  const int d = D / H;
+  for (int h = 0; h < H; ++h) {
+    float acc = 0.f;
+    for (int c = lane * 2; c < d; c += 64) {
+      const float2 x = unpack_bf16(*reinterpret_cast<const uint32_t*>(dO + (long)t * D + h * d + c));
+      const float2 y = unpack_bf16(*reinterpret_cast<const uint32_t*>(O + (long)t * D + h * d + c));
+      acc += x.x * y.x + x.y * y.y;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) delta[(long)h * T + t] = acc;
+  }
+}
+
+// dqkv[t, 0:D] = bf16(dq_acc[t, :])
+__global__ void attn_dq_convert_kernel(const float* __restrict__ dq, __nv_bfloat16* __restrict__ dqkv, long T, int D) {
+  const long i = (blockIdx.x * (long)blockDim.x + threadIdx.x) * 8;
+  if (i >= T * D) return;
+  const long t = i / D; const int c = (int)(i % D);
+  const float4 x = *reinterpret_cast<const float4*>(dq + i), y = *reinterpret_cast<const float4*>(dq + i + 4);
+  *reinterpret_cast<uint4*>(dqkv + t * 3 * D + c) = make_uint4(pack_bf16(x.x, x.y), pack_bf16(x.z, x.w), pack_bf16(y.x, y.y), pack_bf16(y.z, y.w));
+}
+
+template <int HD>
+static int launch_bwd(const void* qkv, const void* dO, const AttnBwdArgs& a, cudaStream_t stream) {
+  using Cfg = BwdCfg<HD>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CB_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  CUtensorMap tq, td;
+  {
+    uint64_t dims[2] = {(uint64_t)(3 * a.D), (uint64_t)a.T};
+    uint64_t strides[1] = {(uint64_t)(3 * a.D) * 2};
+    uint32_t box[2] = {(uint32_t)Cfg::CHUNK, 128};
+    if (make_tmap(&tq, qkv, 2, dims, strides, box, Cfg::SWZ)) return 1;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)a.D, (uint64_t)a.T};
+    uint64_t strides[1] = {(uint64_t)a.D * 2};
+    uint32_t box[2] = {(uint32_t)Cfg::CHUNK, 128};
+    if (make_tmap(&td, dO, 2, dims, strides, box, Cfg::SWZ)) return 1;
+  }
+  const int grid = a.n_work < num_sms() ? a.n_work : num_sms();
+  attn_bwd_kernel<HD><<<grid, 192, Cfg::SMEM_BYTES, stream>>>(tq, td, a);
+  CB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace cb
+
+extern "C" int cb_attn_varlen_bwd(const void* dout, const void* qkv, const void* out, const float* lse, const int* work, int n_work,
+                                  float* delta_ws, float* dq_acc_ws, void* dqkv, int T, int D, int H, float softmax_scale, void* stream) {
+  using namespace cb;
+  CB_CHECK(T > 0 && H > 0 && D % H == 0 && n_work > 0 && D % 8 == 0, "attn_bwd: bad shape T=%d D=%d H=%d n_work=%d", T, D, H, n_work);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  CB_CUDA(cudaMemsetAsync(dq_acc_ws, 0, (size_t)T * D * sizeof(float), s));
+  attn_delta_kernel<<<(T + 7) / 8, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(dout), reinterpret_cast<const __nv_bfloat16*>(out), delta_ws, T, D, H);
+  CB_CUDA(cudaGetLastError());
+  AttnBwdArgs a{};
+  a.work = reinterpret_cast<const int4*>(work); a.n_work = n_work; a.lse = lse; a.delta = delta_ws; a.dq_acc = dq_acc_ws;
+  a.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv); a.T = T; a.D = D; a.scale = softmax_scale; a.scale_log2 = softmax_scale * 1.4426950408889634f;
+  int rc;
+  switch (D / H) {
+    case 16: rc = launch_bwd<16>(qkv, dout, a, s); break;
+    case 32: rc = launch_bwd<32>(qkv, dout, a, s); break;
+    case 64: rc = launch_bwd<64>(qkv, dout, a, s); break;
+    case 96: rc = launch_bwd<96>(qkv, dout, a, s); break;
+    case 128: rc = launch_bwd<128>(qkv, dout, a, s); break;
+    default: set_error("attn_bwd: unsupported head_dim %d (supported: 16, 32, 64, 96, 128)", D / H); return 1;
+  }
+  if (rc) return rc;
+  const long n8 = ((long)T * D + 7) / 8;
+  attn_dq_convert_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, s>>>(dq_acc_ws, reinterpret_cast<__nv_bfloat16*>(dqkv), T, D);
+  CB_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -131,12 +131,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const bool row_ok = row < g.M && kb1 > kb0;
       const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + buf * Cfg::ACC_STRIDE;
       const long out_row = row;
-      const float* pos_row = nullptr; const float* chan_row = nullptr; bool is_cls = false;
+      const float* pos_row = nullptr; const float* chan_row = nullptr; bool is_cls = false;  // for CLS rows: pos_row = pos0, chan_row = cls_tok
       if ((g.flags & CB_EPI_TOKENIZE) && row_ok) {
         int lo = 0, hi = g.nseq;  // largest b with cu[b] <= row
         while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (__ldg(g.cu + mid) <= row) lo = mid; else hi = mid; }
         const int off = row - __ldg(g.cu + lo);
-        if (off == 0) { is_cls = true; pos_row = g.cls_row; }
+        if (off == 0) { is_cls = true; pos_row = g.pos0; chan_row = g.cls_tok; }
         else {
           const int c = (off - 1) / g.npatch, p = (off - 1) - c * g.npatch;
           pos_row = g.pos + (long)p * g.N;

@@ -21,7 +21,8 @@ struct GemmArgs {
   int nseq;
   const float* pos;       // [npatch, N] fp32 (already interpolated if needed)
   const float* chan_tok;  // [max_ch, N] fp32 or null
-  const float* cls_row;   // [N] fp32 = cls_token + pos_embed[0]
+  const float* cls_tok;   // [N] fp32 cls_token
+  const float* pos0;      // [N] fp32 pos_embed[0,0,0]  (CLS row = cls_tok + pos0)
   int npatch;
 };
 

@@ -222,6 +222,17 @@ __global__ void gather_rows_kernel(const __nv_bfloat16* __restrict__ x, const in
   if (i < (long)rows * D) { const int r = (int)(i / D), c = (int)(i % D); out[i] = __bfloat162float(x[(long)idx[r] * D + c]); }
 }
 
+// C[M,N] (+)= A[M,K] B[K,N] (trans_a: A is stored [K,M]) in fp32 — only for the tiny positional-embedding resize
+// (N' x 196 interpolation matrix times pos_embed), never on token-sized data.
+__global__ void small_matmul_f32_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C, int M, int N,
+                                        int K, int trans_a, int accumulate) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x, m = blockIdx.y;
+  if (n >= N) return;
+  float acc = 0.f;
+  for (int k = 0; k < K; ++k) acc += (trans_a ? A[(long)k * M + m] : A[(long)m * K + k]) * B[(long)k * N + n];
+  if (accumulate) C[(long)m * N + n] += acc; else C[(long)m * N + n] = acc;
+}
+
 }  // namespace cb
 
 using namespace cb;
@@ -291,6 +302,14 @@ extern "C" int cb_gather_rows_f32(const void* x, const int* idx, float* out, int
   CB_CHECK(rows > 0 && D > 0, "gather_rows: rows=%d D=%d", rows, D);
   const long n = (long)rows * D;
   gather_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, STREAM>>>(BF(x), idx, out, rows, D);
+  CB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int cb_small_matmul_f32(const float* A, const float* B, float* C, int M, int N, int K, int trans_a, int accumulate,
+                                   void* stream) {
+  CB_CHECK(M > 0 && N > 0 && K > 0 && M <= 65535, "small_matmul: M=%d N=%d K=%d", M, N, K);
+  small_matmul_f32_kernel<<<dim3((N + 127) / 128, M), 128, 0, STREAM>>>(A, B, C, M, N, K, trans_a, accumulate);
   CB_CUDA(cudaGetLastError());
   return 0;
 }

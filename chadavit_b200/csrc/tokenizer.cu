@@ -43,11 +43,11 @@ __global__ void im2col_packed_kernel(const float* __restrict__ x, __nv_bfloat16*
 // Embedding gradients from dTok (T,D) bf16.  grid = npatch + G + 1 blocks, blockDim = D/2 threads (2 columns each):
 //   block p < npatch           : dpos_patch[p]  += sum_g dTok[row(g,p)]
 //   block npatch + g           : dchan[c_g]     += sum_p dTok[row(g,p)],  dbias += same
-//   block npatch + G           : dcls_row       += sum_b dTok[cu[b]]
+//   block npatch + G           : dcls_tok, dpos0 += sum_b dTok[cu[b]]
 __global__ void tokenizer_embed_bwd_kernel(const __nv_bfloat16* __restrict__ dtok, const int* __restrict__ chan_img,
                                            const int* __restrict__ chan_idx, const int* __restrict__ cu, int G, int B, int npatch,
                                            int D, float* __restrict__ dpos_patch, float* __restrict__ dchan, float* __restrict__ dbias,
-                                           float* __restrict__ dcls_row) {
+                                           float* __restrict__ dcls_tok, float* __restrict__ dpos0) {
   const int col = threadIdx.x * 2;
   if (col >= D) return;
   float a0 = 0.f, a1 = 0.f;
@@ -73,7 +73,8 @@ __global__ void tokenizer_embed_bwd_kernel(const __nv_bfloat16* __restrict__ dto
       const float2 f = unpack_bf16(*reinterpret_cast<const uint32_t*>(dtok + (long)cu[b] * D + col));
       a0 += f.x; a1 += f.y;
     }
-    atomicAdd(dcls_row + col, a0); atomicAdd(dcls_row + col + 1, a1);
+    atomicAdd(dcls_tok + col, a0); atomicAdd(dcls_tok + col + 1, a1);
+    atomicAdd(dpos0 + col, a0); atomicAdd(dpos0 + col + 1, a1);
   }
 }
 
@@ -83,8 +84,8 @@ using namespace cb;
 #define STREAM reinterpret_cast<cudaStream_t>(stream)
 
 extern "C" int cb_tokenize_fwd(const float* x, int G, int H, int W, int patch, const int* cu_seqlens, const int* chan_img, int B,
-                               const void* w_pe, const float* b_pe, const float* pos_patch, const float* cls_row,
-                               const float* chan_tok, void* patches_ws, void* tokens, int T, int D, void* stream) {
+                               const void* w_pe, const float* b_pe, const float* pos_patch, const float* pos0,
+                               const float* cls_tok, const float* chan_tok, void* patches_ws, void* tokens, int T, int D, void* stream) {
   CB_CHECK(G > 0 && B > 0 && patch % 8 == 0 && H >= patch && W >= patch && W % 4 == 0, "tokenize_fwd: bad shape G=%d B=%d H=%d W=%d patch=%d", G, B, H, W, patch);
   const int npatch = (H / patch) * (W / patch), PP = patch * patch;
   CB_CHECK(T == B + G * npatch, "tokenize_fwd: T=%d != B + G*N = %d (index bookkeeping)", T, B + G * npatch);
@@ -96,16 +97,17 @@ extern "C" int cb_tokenize_fwd(const float* x, int G, int H, int W, int patch, c
   CB_CUDA(cudaGetLastError());
   GemmArgs g{};
   g.M = T; g.N = D; g.K = PP; g.k_splits = 1; g.C = tokens; g.ldc = D; g.bias = b_pe; g.flags = CB_EPI_TOKENIZE; g.alpha = 1.f;
-  g.cu = cu_seqlens; g.nseq = B; g.pos = pos_patch; g.chan_tok = chan_tok; g.cls_row = cls_row; g.npatch = npatch;
+  g.cu = cu_seqlens; g.nseq = B; g.pos = pos_patch; g.chan_tok = chan_tok; g.cls_tok = cls_tok; g.pos0 = pos0; g.npatch = npatch;
   return gemm_run(patches_ws, PP, 0, w_pe, PP, 0, g, STREAM);
 }
 
 extern "C" int cb_tokenize_bwd(const void* dtokens, const void* patches_ws, const int* cu_seqlens, const int* chan_img,
                                const int* chan_idx, int G, int B, int npatch, int patch_elems, int T, int D, float* dw_pe,
-                               float* db_pe, float* dpos_patch, float* dcls_row, float* dchan_tok, int k_splits, void* stream) {
+                               float* db_pe, float* dpos_patch, float* dpos0, float* dcls_tok, float* dchan_tok, int k_splits,
+                               void* stream) {
   CB_CHECK(T == B + G * npatch && D % 32 == 0 && D <= 2048, "tokenize_bwd: bad shape T=%d B=%d G=%d N=%d D=%d", T, B, G, npatch, D);
   tokenizer_embed_bwd_kernel<<<npatch + G + 1, D / 2, 0, STREAM>>>(reinterpret_cast<const __nv_bfloat16*>(dtokens), chan_img, chan_idx,
-                                                                     cu_seqlens, G, B, npatch, D, dpos_patch, dchan_tok, db_pe, dcls_row);
+                                                                     cu_seqlens, G, B, npatch, D, dpos_patch, dchan_tok, db_pe, dcls_tok, dpos0);
   CB_CUDA(cudaGetLastError());
   // dW_pe[D, P²] += dTok^T[D, T] · patches[T, P²]   (CLS rows of `patches` are zero)
   GemmArgs g{};

@@ -156,7 +156,7 @@ class PackedLayout:
 
 # ------------------------------------------------------------------------------------------------ tokenizer / attention
 def tokenize_fwd(x: torch.Tensor, lay: PackedLayout, patch: int, w_pe_bf16: torch.Tensor, b_pe: torch.Tensor, pos_patch: torch.Tensor,
-                 cls_row: torch.Tensor, chan_tok: Optional[torch.Tensor]) -> Tuple[torch.Tensor, torch.Tensor]:
+                 pos0: torch.Tensor, cls_tok: torch.Tensor, chan_tok: Optional[torch.Tensor]) -> Tuple[torch.Tensor, torch.Tensor]:
     G, one, H, W = x.shape
     if one != 1:
         raise ValueError("ChAdaViT expects a (sum_channels, 1, H, W) tensor")
@@ -172,16 +172,16 @@ def tokenize_fwd(x: torch.Tensor, lay: PackedLayout, patch: int, w_pe_bf16: torc
     patches = torch.empty(lay.T, patch * patch, device=x.device, dtype=bf16)
     tokens = torch.empty(lay.T, D, device=x.device, dtype=bf16)
     _call("cb_tokenize_fwd", _p(x), G, H, W, patch, _p(lay.cu), _p(lay.chan_img), lay.B, _p(w_pe_bf16), _p(b_pe), _p(pos_patch),
-          _p(cls_row), _p(chan_tok), _p(patches), _p(tokens), lay.T, D, _stream())
+          _p(pos0), _p(cls_tok), _p(chan_tok), _p(patches), _p(tokens), lay.T, D, _stream())
     return tokens, patches
 
 
-def tokenize_bwd(dtokens: torch.Tensor, patches: torch.Tensor, lay: PackedLayout, *, dw_pe, db_pe, dpos_patch, dcls_row, dchan_tok) -> None:
+def tokenize_bwd(dtokens: torch.Tensor, patches: torch.Tensor, lay: PackedLayout, *, dw_pe, db_pe, dpos_patch, dpos0, dcls_tok, dchan_tok) -> None:
     T, D = dtokens.shape
     pe = patches.shape[1]
     ks = splitk_for(T, ((D + 127) // 128) * ((pe + 255) // 256))
     _call("cb_tokenize_bwd", _p(dtokens), _p(patches), _p(lay.cu), _p(lay.chan_img), _p(lay.chan_idx), lay.G, lay.B, lay.npatch, pe,
-          T, D, _p(dw_pe), _p(db_pe), _p(dpos_patch), _p(dcls_row), _p(dchan_tok), ks, _stream())
+          T, D, _p(dw_pe), _p(db_pe), _p(dpos_patch), _p(dpos0), _p(dcls_tok), _p(dchan_tok), ks, _stream())
 
 
 def attn_fwd(qkv: torch.Tensor, lay: PackedLayout, nheads: int, *, need_lse: bool = True) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
@@ -193,3 +193,29 @@ def attn_fwd(qkv: torch.Tensor, lay: PackedLayout, nheads: int, *, need_lse: boo
     lse = torch.empty(nheads, T, device=qkv.device, dtype=torch.float32) if need_lse else None
     _call("cb_attn_varlen_fwd", _p(qkv), _p(work), work.shape[0], _p(out), _p(lse), T, D, nheads, float(d) ** -0.5, _stream())
     return out, lse
+
+
+def attn_bwd(dout: torch.Tensor, qkv: torch.Tensor, out: torch.Tensor, lse: torch.Tensor, lay: PackedLayout, nheads: int) -> torch.Tensor:
+    """dqkv [T, 3D] bf16 from d(attention output) [T, D] bf16."""
+    T, D3 = qkv.shape
+    D = D3 // 3
+    d = D // nheads
+    work = lay.attn_work(nheads)
+    delta = torch.empty(nheads, T, device=qkv.device, dtype=torch.float32)
+    dq_acc = torch.empty(T, D, device=qkv.device, dtype=torch.float32)
+    dqkv = torch.empty(T, D3, device=qkv.device, dtype=bf16)
+    _call("cb_attn_varlen_bwd", _p(dout), _p(qkv), _p(out), _p(lse), _p(work), work.shape[0], _p(delta), _p(dq_acc), _p(dqkv), T, D,
+          nheads, float(d) ** -0.5, _stream())
+    return dqkv
+
+
+def small_matmul_f32(A: torch.Tensor, B: torch.Tensor, *, trans_a: bool = False, out: Optional[torch.Tensor] = None,
+                     accumulate: bool = False) -> torch.Tensor:
+    """fp32 C (+)= op(A) @ B for the tiny pos-embed resize map only."""
+    M, K = (A.shape[1], A.shape[0]) if trans_a else A.shape
+    N = B.shape[1]
+    assert B.shape[0] == K and A.is_contiguous() and B.is_contiguous()
+    if out is None:
+        out = torch.empty(M, N, device=A.device, dtype=torch.float32)
+    _call("cb_small_matmul_f32", _p(A), _p(B), _p(out), M, N, K, int(trans_a), int(accumulate), _stream())
+    return out

@@ -58,17 +58,19 @@ int cb_gemm_bf16(const void* A, int lda, int a_mn, const void* B, int ldb, int b
  *   cu_seqlens  int32 [B+1];  chan_img int32 [G] = image index b of channel image g
  *   w_pe bf16 [D, patch*patch] (token_learner.proj.weight), b_pe fp32 [D]
  *   pos_patch fp32 [N, D] (pos_embed[0,0,1:], bicubic-resized by the caller when N != 196, chada_vit.py:201-217)
- *   cls_row fp32 [D] = cls_token + pos_embed[0,0,0];  chan_tok fp32 [max_ch, D] or NULL (chada_vit.py:248)
+ *   pos0 fp32 [D] = pos_embed[0,0,0], cls_tok fp32 [D] = cls_token (CLS row = cls_tok + pos0, chada_vit.py:259-262)
+ *   chan_tok fp32 [max_ch, D] or NULL (chada_vit.py:248)
  *   patches_ws  bf16 [T, patch*patch] workspace (kept for cb_tokenize_bwd);  tokens bf16 [T, D] output
  */
 int cb_tokenize_fwd(const float* x, int G, int H, int W, int patch, const int* cu_seqlens, const int* chan_img, int B,
-                    const void* w_pe, const float* b_pe, const float* pos_patch, const float* cls_row,
-                    const float* chan_tok, void* patches_ws, void* tokens, int T, int D, void* stream);
+                    const void* w_pe, const float* b_pe, const float* pos_patch, const float* pos0,
+                    const float* cls_tok, const float* chan_tok, void* patches_ws, void* tokens, int T, int D, void* stream);
 /* gradients of the tokenizer parameters from dtokens bf16 [T,D]; all outputs fp32 and ACCUMULATED (+=):
- * dw_pe [D,patch_elems], db_pe [D], dpos_patch [N,D], dcls_row [D] (-> cls_token and pos_embed[0]), dchan_tok [max_ch,D] or NULL */
+ * dw_pe [D,patch_elems], db_pe [D], dpos_patch [N,D], dpos0 [D], dcls_tok [D], dchan_tok [max_ch,D] or NULL */
 int cb_tokenize_bwd(const void* dtokens, const void* patches_ws, const int* cu_seqlens, const int* chan_img,
                     const int* chan_idx, int G, int B, int npatch, int patch_elems, int T, int D, float* dw_pe,
-                    float* db_pe, float* dpos_patch, float* dcls_row, float* dchan_tok, int k_splits, void* stream);
+                    float* db_pe, float* dpos_patch, float* dpos0, float* dcls_tok, float* dchan_tok, int k_splits,
+                    void* stream);
 /* plain unfold + cast (patch rows in channel-image order), used by tests */
 int cb_im2col_bf16(const float* x, void* patches, int G, int H, int W, int patch, void* stream);
 
@@ -87,6 +89,9 @@ int cb_layernorm_bwd(const void* dy, const float* dy_f32, const void* x, const i
 int cb_colsum_bf16(const void* x, int ld, float* out, int T, int N, void* stream);
 int cb_cast_f32_bf16(const float* in, void* out, long n, void* stream);
 int cb_gather_rows_f32(const void* x, const int* idx, float* out, int rows, int D, void* stream);
+/* tiny fp32 C[M,N] (+)= op(A) B[K,N] for the bicubic pos-embed resize map (chada_vit.py:201-217); trans_a: A stored [K,M] */
+int cb_small_matmul_f32(const float* A, const float* B, float* C, int M, int N, int K, int trans_a, int accumulate,
+                        void* stream);
 
 /*
  * Packed varlen multi-head self-attention forward (nn.MultiheadAttention inside _sa_block, chada_vit.py:105-111).
@@ -97,6 +102,13 @@ int cb_gather_rows_f32(const void* x, const int* idx, float* out, int rows, int 
  */
 int cb_attn_varlen_fwd(const void* qkv, const int* work, int n_work, void* out, float* lse, int T, int D, int H,
                        float softmax_scale, void* stream);
+
+/*
+ * Backward of cb_attn_varlen_fwd.  dout bf16 [T,D] (gradient of `out`), qkv/out/lse as saved by the forward, `work`
+ * the same tile list.  Workspaces (caller-allocated): delta_ws fp32 [H,T], dq_acc_ws fp32 [T,D].  dqkv bf16 [T,3D].
+ */
+int cb_attn_varlen_bwd(const void* dout, const void* qkv, const void* out, const float* lse, const int* work, int n_work,
+                       float* delta_ws, float* dq_acc_ws, void* dqkv, int T, int D, int H, float softmax_scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -76,10 +76,11 @@ def test_tokenizer_fwd_bwd(D, hw, counts, max_ch):
     assert lay.cu_host.tolist() == cu
     dev = {k: v.cuda() for k, v in P.items()}
     pos_patch = O.interp_pos_embed(P["pos_embed"], npatch, hw, hw, 16)[0, 0].contiguous().cuda()
-    cls_row = (P["cls_token"][0, 0] + P["pos_embed"][0, 0, 0]).cuda()
+    pos0 = P["pos_embed"][0, 0, 0].contiguous().cuda()
+    cls_tok = P["cls_token"][0, 0].contiguous().cuda()
     chan = dev["channel_token"][0, :, 0].contiguous() if max_ch == 10 else None
     w_bf = dev["token_learner.proj.weight"].reshape(D, 256).to(torch.bfloat16)
-    tok, patches = ops.tokenize_fwd(x.cuda(), lay, 16, w_bf, dev["token_learner.proj.bias"], pos_patch, cls_row, chan)
+    tok, patches = ops.tokenize_fwd(x.cuda(), lay, 16, w_bf, dev["token_learner.proj.bias"], pos_patch, pos0, cls_tok, chan)
     ops.sync_check()
     err = (tok.float().cpu() - ref).abs().max().item()
     print(f"tokenizer D={D} hw={hw}: max err {err:.3e}")
@@ -91,13 +92,14 @@ def test_tokenizer_fwd_bwd(D, hw, counts, max_ch):
     emb2, _ = O.tokenize_padded(x.to(torch.bfloat16).float(), counts, Pg, 16, max_ch)
     (emb2.reshape(-1, D)[rows] * dtok.float()).sum().backward()
     dw = torch.zeros(D, 256, device="cuda"); dbias = torch.zeros(D, device="cuda")
-    dpos = torch.zeros(npatch, D, device="cuda"); dcls = torch.zeros(D, device="cuda")
+    dpos = torch.zeros(npatch, D, device="cuda"); dcls = torch.zeros(D, device="cuda"); dpos0 = torch.zeros(D, device="cuda")
     dchan = torch.zeros(10, D, device="cuda") if max_ch == 10 else None
-    ops.tokenize_bwd(dtok.cuda(), patches, lay, dw_pe=dw, db_pe=dbias, dpos_patch=dpos, dcls_row=dcls, dchan_tok=dchan)
+    ops.tokenize_bwd(dtok.cuda(), patches, lay, dw_pe=dw, db_pe=dbias, dpos_patch=dpos, dpos0=dpos0, dcls_tok=dcls, dchan_tok=dchan)
     ops.sync_check()
     assert (dw.cpu() - Pg["token_learner.proj.weight"].grad.reshape(D, 256)).abs().max().item() < 0.05
     assert (dbias.cpu() - Pg["token_learner.proj.bias"].grad).abs().max().item() < 0.05
     assert (dcls.cpu() - Pg["cls_token"].grad[0, 0]).abs().max().item() < 1e-3
+    assert (dpos0.cpu() - Pg["pos_embed"].grad[0, 0, 0]).abs().max().item() < 1e-3
     if hw == 224:
         assert (dpos.cpu() - Pg["pos_embed"].grad[0, 0, 1:]).abs().max().item() < 2e-3
     if max_ch == 10:
