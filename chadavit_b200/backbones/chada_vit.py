@@ -218,7 +218,8 @@ class ChAdaViT(nn.Module):
             h, sv = self._block_fwd(i, h, lay, save)
             blocks.append(sv)
         idx = lay.non_cls_rows() if self.return_all_tokens else lay.cu[:-1]
-        out, mean, rstd = ops.layernorm_fwd(h, a.v32("norm.weight"), a.v32("norm.bias"), self.norm.eps, in_idx=idx, out_f32=True, save_stats=save)
+        _, out, mean, rstd = ops.layernorm_fwd(h, a.v32("norm.weight"), a.v32("norm.bias"), self.norm.eps, in_idx=idx, out_bf16=False,
+                                               out_f32=True, save_stats=save)
         if not save:
             return out, None
         s = _Saved()
@@ -226,17 +227,21 @@ class ChAdaViT(nn.Module):
         return out, s
 
     def _block_fwd(self, i: int, x: torch.Tensor, lay: ops.PackedLayout, save: bool):
+        """x fp32 [T,D] -> x' fp32 [T,D].  The residual stream and every LayerNorm input stay fp32; bf16 is used only for
+        tensor-core operands (u, qkv, att, y, hid)."""
         a, pre = self.arena, f"blocks.{i}."
         eps = self.blocks[i].norm1.eps
         g1, b1 = a.v32(pre + "norm1.weight"), a.v32(pre + "norm1.bias")
-        u, m1a, r1a = ops.layernorm_fwd(x, g1, b1, eps, save_stats=save)
+        R = ops.EPI_RESIDUAL_F32 | ops.EPI_OUT_F32
+        u, _, m1a, r1a = ops.layernorm_fwd(x, g1, b1, eps, save_stats=save)
         qkv = ops.gemm(u, a.v16(pre + "self_attn.in_proj_weight"), bias=a.v32(pre + "self_attn.in_proj_bias"))
         att, lse = ops.attn_fwd(qkv, lay, self.num_heads, need_lse=save)
-        z1 = ops.gemm(att, a.v16(pre + "self_attn.out_proj.weight"), bias=a.v32(pre + "self_attn.out_proj.bias"), aux=x, flags=ops.EPI_RESIDUAL)
-        y, m1b, r1b = ops.layernorm_fwd(z1, g1, b1, eps, save_stats=save)
+        z1 = ops.gemm(att, a.v16(pre + "self_attn.out_proj.weight"), bias=a.v32(pre + "self_attn.out_proj.bias"), aux=x, flags=R)
+        y, y32, m1b, r1b = ops.layernorm_fwd(z1, g1, b1, eps, out_f32=True, save_stats=save)
         hid = ops.gemm(y, a.v16(pre + "linear1.weight"), bias=a.v32(pre + "linear1.bias"), flags=ops.EPI_RELU)
-        z2 = ops.gemm(hid, a.v16(pre + "linear2.weight"), bias=a.v32(pre + "linear2.bias"), aux=y, flags=ops.EPI_RESIDUAL)
-        out, m2, r2 = ops.layernorm_fwd(z2, a.v32(pre + "norm2.weight"), a.v32(pre + "norm2.bias"), self.blocks[i].norm2.eps, save_stats=save)
+        z2 = ops.gemm(hid, a.v16(pre + "linear2.weight"), bias=a.v32(pre + "linear2.bias"), aux=y32, flags=R)
+        _, out, m2, r2 = ops.layernorm_fwd(z2, a.v32(pre + "norm2.weight"), a.v32(pre + "norm2.bias"), self.blocks[i].norm2.eps,
+                                           out_bf16=False, out_f32=True, save_stats=save)
         if not save:
             return out, None
         return out, (x, u, m1a, r1a, qkv, att, lse, z1, m1b, r1b, y, hid, z2, m2, r2)
@@ -249,21 +254,23 @@ class ChAdaViT(nn.Module):
         D, P = self.embed_dim, self.token_learner.patch_size
         lay = s.lay
         # final norm (+ CLS / all-token gather): rows not selected get zero gradient
-        dx = ops.layernorm_bwd(dout, s.x_last, a.v32("norm.weight"), s.fin_mean, s.fin_rstd, dgamma=g("norm.weight"),
-                               dbeta=g("norm.bias"), idx=s.fin_idx)
+        dx, _ = ops.layernorm_bwd(dout, s.x_last, a.v32("norm.weight"), s.fin_mean, s.fin_rstd, dgamma=g("norm.weight"),
+                                  dbeta=g("norm.bias"), idx=s.fin_idx)
+        dx16 = None
         for i in reversed(range(self.depth)):
-            dx = self._block_bwd(i, s.blocks[i], dx, lay, gflat)
+            dx, dx16 = self._block_bwd(i, s.blocks[i], dx, lay, gflat, last=(i == 0))
             s.blocks[i] = None
         N0 = self.pos_embed.shape[2] - 1
         dpos = g("pos_embed").view(N0 + 1, D)
-        dpos_patch = dpos[1:] if s.interp is None else torch.zeros(lay.npatch, D, device=dx.device, dtype=torch.float32)
+        dpos_patch = dpos[1:] if s.interp is None else torch.zeros(lay.npatch, D, device=dx16.device, dtype=torch.float32)
         dchan = g("channel_token").view(self.max_channels, D) if self.max_channels == PAD_CHANNELS else None
-        ops.tokenize_bwd(dx, s.patches, lay, dw_pe=g("token_learner.proj.weight").view(D, P * P), db_pe=g("token_learner.proj.bias"),
+        ops.tokenize_bwd(dx16, s.patches, lay, dw_pe=g("token_learner.proj.weight").view(D, P * P), db_pe=g("token_learner.proj.bias"),
                          dpos_patch=dpos_patch, dpos0=dpos[0], dcls_tok=g("cls_token").view(D), dchan_tok=dchan)
         if s.interp is not None:  # pos_embed receives gradient through the bicubic resize (SURVEY.md §8c probe)
             ops.small_matmul_f32(s.interp, dpos_patch, trans_a=True, out=dpos[1:], accumulate=True)
 
-    def _block_bwd(self, i: int, sv, dxo: torch.Tensor, lay: ops.PackedLayout, gflat: torch.Tensor) -> torch.Tensor:
+    def _block_bwd(self, i: int, sv, dxo: torch.Tensor, lay: ops.PackedLayout, gflat: torch.Tensor, last: bool):
+        """dxo fp32 [T,D] -> (dx fp32, dx bf16 if last).  Gradient residual stream fp32; bf16 only for MMA operands."""
         a, pre = self.arena, f"blocks.{i}."
         g = lambda n: a.g32(pre + n, gflat)  # noqa: E731
         x, u, m1a, r1a, qkv, att, lse, z1, m1b, r1b, y, hid, z2, m2, r2 = sv
@@ -272,24 +279,25 @@ class ChAdaViT(nn.Module):
         sk = lambda tiles: ops.splitk_for(T, tiles)  # noqa: E731
         mt = lambda n: (n + 127) // 128  # noqa: E731
         # x' = LN2(z2), z2 = y + relu(y W1^T + b1) W2^T + b2
-        dz2 = ops.layernorm_bwd(dxo, z2, a.v32(pre + "norm2.weight"), m2, r2, dgamma=g("norm2.weight"), dbeta=g("norm2.bias"),
-                                dcolsum=g("linear2.bias"))
-        ops.gemm(dz2, hid, a_mn=True, b_mn=True, flags=A, out=g("linear2.weight"), k_splits=sk(mt(D) * (FFN_DIM // 256)))
-        dh = ops.gemm(dz2, a.v16(pre + "linear2.weight"), b_mn=True, aux=hid, flags=ops.EPI_RELU_MASK)
+        dz2, dz2h = ops.layernorm_bwd(dxo, z2, a.v32(pre + "norm2.weight"), m2, r2, dgamma=g("norm2.weight"), dbeta=g("norm2.bias"),
+                                      dcolsum=g("linear2.bias"), want_bf16=True)
+        ops.gemm(dz2h, hid, a_mn=True, b_mn=True, flags=A, out=g("linear2.weight"), k_splits=sk(mt(D) * (FFN_DIM // 256)))
+        dh = ops.gemm(dz2h, a.v16(pre + "linear2.weight"), b_mn=True, aux=hid, flags=ops.EPI_RELU_MASK)
         ops.colsum(dh, g("linear1.bias"))
         ops.gemm(dh, y, a_mn=True, b_mn=True, flags=A, out=g("linear1.weight"), k_splits=sk(mt(FFN_DIM) * mt(D)))
-        dy = ops.gemm(dh, a.v16(pre + "linear1.weight"), b_mn=True, aux=dz2, flags=ops.EPI_RESIDUAL)
+        dy = ops.gemm(dh, a.v16(pre + "linear1.weight"), b_mn=True, aux=dz2, flags=ops.EPI_RESIDUAL_F32 | ops.EPI_OUT_F32)
         # y = LN1(z1), z1 = x + att Wo^T + bo      (second use of norm1: gradients accumulate)
-        dz1 = ops.layernorm_bwd(dy, z1, a.v32(pre + "norm1.weight"), m1b, r1b, dgamma=g("norm1.weight"), dbeta=g("norm1.bias"),
-                                dcolsum=g("self_attn.out_proj.bias"))
-        ops.gemm(dz1, att, a_mn=True, b_mn=True, flags=A, out=g("self_attn.out_proj.weight"), k_splits=sk(mt(D) * mt(D)))
-        datt = ops.gemm(dz1, a.v16(pre + "self_attn.out_proj.weight"), b_mn=True)
+        dz1, dz1h = ops.layernorm_bwd(dy, z1, a.v32(pre + "norm1.weight"), m1b, r1b, dgamma=g("norm1.weight"), dbeta=g("norm1.bias"),
+                                      dcolsum=g("self_attn.out_proj.bias"), want_bf16=True)
+        ops.gemm(dz1h, att, a_mn=True, b_mn=True, flags=A, out=g("self_attn.out_proj.weight"), k_splits=sk(mt(D) * mt(D)))
+        datt = ops.gemm(dz1h, a.v16(pre + "self_attn.out_proj.weight"), b_mn=True)
         dqkv = ops.attn_bwd(datt, qkv, att, lse, lay, self.num_heads)
         ops.colsum(dqkv, g("self_attn.in_proj_bias"))
         ops.gemm(dqkv, u, a_mn=True, b_mn=True, flags=A, out=g("self_attn.in_proj_weight"), k_splits=sk(mt(3 * D) * mt(D)))
-        du = ops.gemm(dqkv, a.v16(pre + "self_attn.in_proj_weight"), b_mn=True)
+        du = ops.gemm(dqkv, a.v16(pre + "self_attn.in_proj_weight"), b_mn=True, flags=ops.EPI_OUT_F32)
         # u = LN1(x) (first use) ; dx = dLN1(du) + dz1 (residual into z1)
-        return ops.layernorm_bwd(du, x, a.v32(pre + "norm1.weight"), m1a, r1a, dgamma=g("norm1.weight"), dbeta=g("norm1.bias"), dres=dz1)
+        return ops.layernorm_bwd(du, x, a.v32(pre + "norm1.weight"), m1a, r1a, dgamma=g("norm1.weight"), dbeta=g("norm1.bias"), dres=dz1,
+                                 want_f32=not last, want_bf16=last)
 
 
 def chada_vit(**kwargs):

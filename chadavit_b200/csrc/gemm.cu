@@ -178,6 +178,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
           }
+          if (g.flags & CB_EPI_RESIDUAL_F32) {
+            const float* rp = reinterpret_cast<const float*>(g.aux) + (long)row * g.ld_aux + n;
+            const float4 r0 = __ldg(reinterpret_cast<const float4*>(rp)), r1 = __ldg(reinterpret_cast<const float4*>(rp + 4));
+            v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w; v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+          }
           if (g.flags & (CB_EPI_RESIDUAL | CB_EPI_RELU_MASK)) {
             const uint4 a = __ldg(reinterpret_cast<const uint4*>(g.aux + (long)row * g.ld_aux + n));
             const uint32_t au[4] = {a.x, a.y, a.z, a.w};
@@ -292,6 +297,6 @@ extern "C" int cb_gemm_bf16(const void* A, int lda, int a_mn, const void* B, int
   g.M = M; g.N = N; g.K = K; g.k_splits = k_splits; g.C = C; g.ldc = ldc; g.bias = bias;
   g.aux = reinterpret_cast<const __nv_bfloat16*>(aux); g.ld_aux = ld_aux; g.flags = flags; g.alpha = alpha;
   CB_CHECK(!(flags & CB_EPI_TOKENIZE), "cb_gemm_bf16: use cb_tokenize_fwd for the tokenizer epilogue");
-  CB_CHECK(!(flags & (CB_EPI_RESIDUAL | CB_EPI_RELU_MASK)) || aux, "cb_gemm_bf16: aux pointer required by flags");
+  CB_CHECK(!(flags & (CB_EPI_RESIDUAL | CB_EPI_RELU_MASK | CB_EPI_RESIDUAL_F32)) || aux, "cb_gemm_bf16: aux pointer required by flags");
   return cb::gemm_run(A, lda, a_mn, B, ldb, b_mn, g, reinterpret_cast<cudaStream_t>(stream));
 }

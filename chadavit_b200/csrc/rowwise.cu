@@ -27,11 +27,24 @@ __global__ void im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __rest
 }
 
 // ------------------------------------------------------------------------------------------------ LayerNorm
-// LN_MAX_CHUNKS (template): 16-byte chunks per lane; D <= 32 lanes * chunks * 8  (1 -> D<=256, 2 -> 512, 4 -> 1024)
+// The residual stream / LayerNorm inputs are kept in fp32 (only GEMM operands are rounded to bf16), so the LN kernels
+// read fp32 rows and can emit bf16 (next GEMM operand) and/or fp32 (next residual) outputs in one pass.
+// LN_MAX_CHUNKS (template): 8-element chunks per lane; D <= 32 lanes * chunks * 8  (1 -> D<=256, 2 -> 512, 4 -> 1024)
+__device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void st8(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void st8_bf16(__nv_bfloat16* p, const float (&v)[8]) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+}
 
-// y[o] = LN(x[i]) * gamma + beta;  i = in_idx ? in_idx[r] : r;  o = r.   mean/rstd saved per output row r.
+// y[r] = LN(x[i]) * gamma + beta;  i = in_idx ? in_idx[r] : r.   mean/rstd saved per output row r.
 template <int LN_MAX_CHUNKS>
-__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict__ in_idx,
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x, const int* __restrict__ in_idx,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             __nv_bfloat16* __restrict__ y, float* __restrict__ y32,
                                                             float* __restrict__ mean_out, float* __restrict__ rstd_out,
@@ -47,10 +60,9 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const __nv_bfloat16*
     for (int k = 0; k < LN_MAX_CHUNKS; ++k) {
       const int c = lane + k * 32;
       if (c < nchunk) {
-        const uint4 u = *reinterpret_cast<const uint4*>(x + src * D + c * 8);
-        const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+        ld8(x + src * D + c * 8, v[k]);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { const float2 f = unpack_bf16(uu[j]); v[k][2 * j] = f.x; v[k][2 * j + 1] = f.y; s += f.x + f.y; }
+        for (int j = 0; j < 8; ++j) s += v[k][j];
       }
     }
     const float mean = warp_sum(s) / D;
@@ -67,32 +79,25 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const __nv_bfloat16*
     for (int k = 0; k < LN_MAX_CHUNKS; ++k) {
       const int c = lane + k * 32;
       if (c < nchunk) {
-        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c * 8 + 4));
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c * 8)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c * 8 + 4));
-        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-        float o[8];
+        float gg[8], bb[8], o[8];
+        ld8(gamma + c * 8, gg); ld8(beta + c * 8, bb);
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = (v[k][j] - mean) * rstd * gg[j] + bb[j];
-        if (y) *reinterpret_cast<uint4*>(y + (long)r * D + c * 8) =
-            make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
-        if (y32) {
-          *reinterpret_cast<float4*>(y32 + (long)r * D + c * 8) = make_float4(o[0], o[1], o[2], o[3]);
-          *reinterpret_cast<float4*>(y32 + (long)r * D + c * 8 + 4) = make_float4(o[4], o[5], o[6], o[7]);
-        }
+        if (y) st8_bf16(y + (long)r * D + c * 8, o);
+        if (y32) st8(y32 + (long)r * D + c * 8, o);
       }
     }
   }
 }
 
 // dx[i] = LNbwd(dy[r], x[i]) (+ dres[i]);  i = idx ? idx[r] : r.  dgamma/dbeta/dcolsum are ACCUMULATED (fp32 atomics,
-// one per block per column).  dy is bf16 (dy) or fp32 (dy32).
+// one per block per column).  dy, x, dres fp32; dx written as fp32 (dx32) and/or bf16 (dx16).
 template <int LN_MAX_CHUNKS>
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ dy32,
-                                                            const __nv_bfloat16* __restrict__ x, const int* __restrict__ idx,
-                                                            const float* __restrict__ gamma, const float* __restrict__ mean_in,
-                                                            const float* __restrict__ rstd_in, const __nv_bfloat16* __restrict__ dres,
-                                                            __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma,
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                            const int* __restrict__ idx, const float* __restrict__ gamma,
+                                                            const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                                                            const float* __restrict__ dres, float* __restrict__ dx32,
+                                                            __nv_bfloat16* __restrict__ dx16, float* __restrict__ dgamma,
                                                             float* __restrict__ dbeta, float* __restrict__ dcolsum, int rows, int D) {
   extern __shared__ float red[];  // [3][D]
   const int lane = threadIdx.x & 31;
@@ -100,19 +105,12 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
   const int nchunk = D / 8;
   for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) red[i] = 0.f;
   __syncthreads();
-  float ag[LN_MAX_CHUNKS][8], ab[LN_MAX_CHUNKS][8], ac[LN_MAX_CHUNKS][8];
-#pragma unroll
-  for (int k = 0; k < LN_MAX_CHUNKS; ++k)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { ag[k][j] = 0.f; ab[k][j] = 0.f; ac[k][j] = 0.f; }
-  float gam[LN_MAX_CHUNKS][8];
+  float ag[LN_MAX_CHUNKS][8], ab[LN_MAX_CHUNKS][8], ac[LN_MAX_CHUNKS][8], gam[LN_MAX_CHUNKS][8];
 #pragma unroll
   for (int k = 0; k < LN_MAX_CHUNKS; ++k) {
-    const int c = lane + k * 32;
-    if (c < nchunk) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) gam[k][j] = __ldg(gamma + c * 8 + j);
-    }
+    for (int j = 0; j < 8; ++j) { ag[k][j] = 0.f; ab[k][j] = 0.f; ac[k][j] = 0.f; gam[k][j] = 0.f; }
+    if (lane + k * 32 < nchunk) ld8(gamma + (lane + k * 32) * 8, gam[k]);
   }
   for (int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += warps_per_grid) {
     const long xi = idx ? idx[r] : r;
@@ -123,25 +121,12 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
     for (int k = 0; k < LN_MAX_CHUNKS; ++k) {
       const int c = lane + k * 32;
       if (c < nchunk) {
-        const uint4 ux = *reinterpret_cast<const uint4*>(x + xi * D + c * 8);
-        const uint32_t uxx[4] = {ux.x, ux.y, ux.z, ux.w};
         float d[8];
-        if (dy32) {
-          const float4 d0 = *reinterpret_cast<const float4*>(dy32 + (long)r * D + c * 8), d1 = *reinterpret_cast<const float4*>(dy32 + (long)r * D + c * 8 + 4);
-          d[0] = d0.x; d[1] = d0.y; d[2] = d0.z; d[3] = d0.w; d[4] = d1.x; d[5] = d1.y; d[6] = d1.z; d[7] = d1.w;
-        } else {
-          const uint4 ud = *reinterpret_cast<const uint4*>(dy + (long)r * D + c * 8);
-          const uint32_t udd[4] = {ud.x, ud.y, ud.z, ud.w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) { const float2 fd = unpack_bf16(udd[j]); d[2 * j] = fd.x; d[2 * j + 1] = fd.y; }
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 fx = unpack_bf16(uxx[j]);
-          xh[k][2 * j] = (fx.x - mean) * rstd; xh[k][2 * j + 1] = (fx.y - mean) * rstd;
-        }
+        ld8(dy + (long)r * D + c * 8, d);
+        ld8(x + xi * D + c * 8, xh[k]);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
+          xh[k][j] = (xh[k][j] - mean) * rstd;
           ag[k][j] += d[j] * xh[k][j]; ab[k][j] += d[j];
           g[k][j] = d[j] * gam[k][j];
           s1 += g[k][j]; s2 += g[k][j] * xh[k][j];
@@ -157,13 +142,13 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
 #pragma unroll
         for (int j = 0; j < 8; ++j) { o[j] = rstd * (g[k][j] - s1 - xh[k][j] * s2); ac[k][j] += o[j]; }
         if (dres) {
-          const uint4 u = *reinterpret_cast<const uint4*>(dres + xi * D + c * 8);
-          const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+          float e[8];
+          ld8(dres + xi * D + c * 8, e);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) { const float2 f = unpack_bf16(uu[j]); o[2 * j] += f.x; o[2 * j + 1] += f.y; }
+          for (int j = 0; j < 8; ++j) o[j] += e[j];
         }
-        *reinterpret_cast<uint4*>(dx + xi * D + c * 8) =
-            make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+        if (dx32) st8(dx32 + xi * D + c * 8, o);
+        if (dx16) st8_bf16(dx16 + xi * D + c * 8, o);
       }
     }
   }
@@ -252,26 +237,26 @@ extern "C" int cb_im2col_bf16(const float* x, void* patches, int G, int H, int W
   return 0;
 }
 
-extern "C" int cb_layernorm_fwd(const void* x, const int* in_idx, const float* gamma, const float* beta, void* y, float* y_f32,
+extern "C" int cb_layernorm_fwd(const float* x, const int* in_idx, const float* gamma, const float* beta, void* y, float* y_f32,
                                 float* mean, float* rstd, int rows, int D, float eps, void* stream) {
   CB_CHECK(rows > 0 && D % 8 == 0 && D <= 1024, "layernorm_fwd: rows=%d D=%d (D must be a multiple of 8, <= 1024)", rows, D);
   int blocks = (rows + 7) / 8;
   if (blocks > num_sms() * 8) blocks = num_sms() * 8;
-  if (D <= 256) layernorm_fwd_kernel<1><<<blocks, 256, 0, STREAM>>>(BF(x), in_idx, gamma, beta, BFM(y), y_f32, mean, rstd, rows, D, eps);
-  else if (D <= 512) layernorm_fwd_kernel<2><<<blocks, 256, 0, STREAM>>>(BF(x), in_idx, gamma, beta, BFM(y), y_f32, mean, rstd, rows, D, eps);
-  else layernorm_fwd_kernel<4><<<blocks, 256, 0, STREAM>>>(BF(x), in_idx, gamma, beta, BFM(y), y_f32, mean, rstd, rows, D, eps);
+#define LNF(N) layernorm_fwd_kernel<N><<<blocks, 256, 0, STREAM>>>(x, in_idx, gamma, beta, BFM(y), y_f32, mean, rstd, rows, D, eps)
+  if (D <= 256) LNF(1); else if (D <= 512) LNF(2); else LNF(4);
+#undef LNF
   CB_CUDA(cudaGetLastError());
   return 0;
 }
 
-extern "C" int cb_layernorm_bwd(const void* dy, const float* dy_f32, const void* x, const int* idx, const float* gamma,
-                                const float* mean, const float* rstd, const void* dres, void* dx, float* dgamma, float* dbeta,
+extern "C" int cb_layernorm_bwd(const float* dy, const float* x, const int* idx, const float* gamma, const float* mean,
+                                const float* rstd, const float* dres, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta,
                                 float* dcolsum, int rows, int D, void* stream) {
   CB_CHECK(rows > 0 && D % 8 == 0 && D <= 1024, "layernorm_bwd: rows=%d D=%d", rows, D);
-  CB_CHECK((dy != nullptr) != (dy_f32 != nullptr), "layernorm_bwd: exactly one of dy / dy_f32");
+  CB_CHECK(dx_f32 || dx_bf16, "layernorm_bwd: at least one of dx_f32 / dx_bf16");
   int blocks = (rows + 7) / 8;
   if (blocks > num_sms() * 4) blocks = num_sms() * 4;
-#define LNB(N) layernorm_bwd_kernel<N><<<blocks, 256, 3 * D * sizeof(float), STREAM>>>(BF(dy), dy_f32, BF(x), idx, gamma, mean, rstd, BF(dres), BFM(dx), dgamma, dbeta, dcolsum, rows, D)
+#define LNB(N) layernorm_bwd_kernel<N><<<blocks, 256, 3 * D * sizeof(float), STREAM>>>(dy, x, idx, gamma, mean, rstd, dres, dx_f32, BFM(dx_bf16), dgamma, dbeta, dcolsum, rows, D)
   if (D <= 256) LNB(1); else if (D <= 512) LNB(2); else LNB(4);
 #undef LNB
   CB_CUDA(cudaGetLastError());

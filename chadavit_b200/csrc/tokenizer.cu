@@ -96,7 +96,7 @@ extern "C" int cb_tokenize_fwd(const float* x, int G, int H, int W, int patch, c
   im2col_packed_kernel<<<(int)blocks, 256, 0, STREAM>>>(x, reinterpret_cast<__nv_bfloat16*>(patches_ws), chan_img, cu_seqlens, G, B, H, W, patch);
   CB_CUDA(cudaGetLastError());
   GemmArgs g{};
-  g.M = T; g.N = D; g.K = PP; g.k_splits = 1; g.C = tokens; g.ldc = D; g.bias = b_pe; g.flags = CB_EPI_TOKENIZE; g.alpha = 1.f;
+  g.M = T; g.N = D; g.K = PP; g.k_splits = 1; g.C = tokens; g.ldc = D; g.bias = b_pe; g.flags = CB_EPI_TOKENIZE | CB_EPI_OUT_F32; g.alpha = 1.f;
   g.cu = cu_seqlens; g.nseq = B; g.pos = pos_patch; g.chan_tok = chan_tok; g.cls_tok = cls_tok; g.pos0 = pos0; g.npatch = npatch;
   return gemm_run(patches_ws, PP, 0, w_pe, PP, 0, g, STREAM);
 }

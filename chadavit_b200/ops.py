@@ -12,7 +12,7 @@ import torch
 
 from . import _lib
 
-EPI_RELU, EPI_RESIDUAL, EPI_RELU_MASK, EPI_OUT_F32, EPI_ATOMIC = 1, 2, 4, 8, 16
+EPI_RELU, EPI_RESIDUAL, EPI_RELU_MASK, EPI_OUT_F32, EPI_ATOMIC, EPI_RESIDUAL_F32 = 1, 2, 4, 8, 16, 64
 bf16 = torch.bfloat16
 
 
@@ -64,28 +64,33 @@ def splitk_for(K: int, tiles: int, target_ctas: int = 148) -> int:
 
 # ------------------------------------------------------------------------------------------------ LayerNorm
 def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, *, in_idx: Optional[torch.Tensor] = None,
-                  out_f32: bool = False, save_stats: bool = True):
+                  out_bf16: bool = True, out_f32: bool = False, save_stats: bool = True):
+    """x fp32 [*, D] -> (y bf16 | None, y fp32 | None, mean, rstd)."""
+    assert x.dtype == torch.float32
     D = x.shape[-1]
     rows = in_idx.numel() if in_idx is not None else x.shape[0]
-    y = None if out_f32 else torch.empty(rows, D, device=x.device, dtype=bf16)
+    y = torch.empty(rows, D, device=x.device, dtype=bf16) if out_bf16 else None
     y32 = torch.empty(rows, D, device=x.device, dtype=torch.float32) if out_f32 else None
     mean = torch.empty(rows, device=x.device, dtype=torch.float32) if save_stats else None
     rstd = torch.empty(rows, device=x.device, dtype=torch.float32) if save_stats else None
     _call("cb_layernorm_fwd", _p(x), _p(in_idx), _p(gamma), _p(beta), _p(y), _p(y32), _p(mean), _p(rstd), rows, D, float(eps), _stream())
-    return (y32 if out_f32 else y), mean, rstd
+    return y, y32, mean, rstd
 
 
 def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor, *,
                   dgamma: torch.Tensor, dbeta: torch.Tensor, dcolsum: Optional[torch.Tensor] = None,
-                  dres: Optional[torch.Tensor] = None, idx: Optional[torch.Tensor] = None, dx: Optional[torch.Tensor] = None):
+                  dres: Optional[torch.Tensor] = None, idx: Optional[torch.Tensor] = None, want_f32: bool = True,
+                  want_bf16: bool = False):
+    """dy, x, dres fp32.  Returns (dx fp32 | None, dx bf16 | None); with idx the untouched rows are zero."""
+    assert dy.dtype == torch.float32 and x.dtype == torch.float32
     D = x.shape[-1]
     rows = dy.shape[0]
-    if dx is None:
-        dx = torch.empty_like(x) if idx is None else torch.zeros_like(x)
-    is32 = dy.dtype == torch.float32
-    _call("cb_layernorm_bwd", None if is32 else _p(dy), _p(dy) if is32 else None, _p(x), _p(idx), _p(gamma), _p(mean), _p(rstd),
-          _p(dres), _p(dx), _p(dgamma), _p(dbeta), _p(dcolsum), rows, D, _stream())
-    return dx
+    mk = torch.zeros if idx is not None else torch.empty
+    dx32 = mk(x.shape, device=x.device, dtype=torch.float32) if want_f32 else None
+    dx16 = mk(x.shape, device=x.device, dtype=bf16) if want_bf16 else None
+    _call("cb_layernorm_bwd", _p(dy), _p(x), _p(idx), _p(gamma), _p(mean), _p(rstd), _p(dres), _p(dx32), _p(dx16), _p(dgamma),
+          _p(dbeta), _p(dcolsum), rows, D, _stream())
+    return dx32, dx16
 
 
 def colsum(x: torch.Tensor, out: torch.Tensor) -> None:
@@ -170,7 +175,7 @@ def tokenize_fwd(x: torch.Tensor, lay: PackedLayout, patch: int, w_pe_bf16: torc
         x = x.contiguous()
     D = w_pe_bf16.shape[0]
     patches = torch.empty(lay.T, patch * patch, device=x.device, dtype=bf16)
-    tokens = torch.empty(lay.T, D, device=x.device, dtype=bf16)
+    tokens = torch.empty(lay.T, D, device=x.device, dtype=torch.float32)
     _call("cb_tokenize_fwd", _p(x), G, H, W, patch, _p(lay.cu), _p(lay.chan_img), lay.B, _p(w_pe_bf16), _p(b_pe), _p(pos_patch),
           _p(pos0), _p(cls_tok), _p(chan_tok), _p(patches), _p(tokens), lay.T, D, _stream())
     return tokens, patches

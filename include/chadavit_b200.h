@@ -34,6 +34,7 @@ extern "C" {
 #define CB_EPI_OUT_F32 8    /* store fp32 instead of bf16                                                             */
 #define CB_EPI_ATOMIC 16    /* fp32 atomic accumulate into C (split-K weight gradients)                               */
 #define CB_EPI_TOKENIZE 32  /* internal: tokenizer scatter epilogue (use cb_tokenize_fwd)                             */
+#define CB_EPI_RESIDUAL_F32 64 /* C += aux where aux is fp32 [M,N] (fp32 residual stream)                               */
 
 const char* cb_last_error(void);
 int cb_version(void);
@@ -60,7 +61,7 @@ int cb_gemm_bf16(const void* A, int lda, int a_mn, const void* B, int ldb, int b
  *   pos_patch fp32 [N, D] (pos_embed[0,0,1:], bicubic-resized by the caller when N != 196, chada_vit.py:201-217)
  *   pos0 fp32 [D] = pos_embed[0,0,0], cls_tok fp32 [D] = cls_token (CLS row = cls_tok + pos0, chada_vit.py:259-262)
  *   chan_tok fp32 [max_ch, D] or NULL (chada_vit.py:248)
- *   patches_ws  bf16 [T, patch*patch] workspace (kept for cb_tokenize_bwd);  tokens bf16 [T, D] output
+ *   patches_ws  bf16 [T, patch*patch] workspace (kept for cb_tokenize_bwd);  tokens fp32 [T, D] output
  */
 int cb_tokenize_fwd(const float* x, int G, int H, int W, int patch, const int* cu_seqlens, const int* chan_img, int B,
                     const void* w_pe, const float* b_pe, const float* pos_patch, const float* pos0,
@@ -75,15 +76,17 @@ int cb_tokenize_bwd(const void* dtokens, const void* patches_ws, const int* cu_s
 int cb_im2col_bf16(const float* x, void* patches, int G, int H, int W, int patch, void* stream);
 
 /*
- * nn.LayerNorm over the last dim (norm1 / norm2 / final norm, chada_vit.py:96,99,100,281).  x bf16 [*, D];
+ * nn.LayerNorm over the last dim (norm1 / norm2 / final norm, chada_vit.py:96,99,100,281).  x fp32 [*, D] (the
+ * residual stream stays fp32; only GEMM operands are rounded to bf16);
  * row r of the output normalises input row in_idx[r] (or r when in_idx is NULL: the CLS gather of chada_vit.py:289
  * is in_idx = cu_seqlens).  Either output may be NULL: y bf16 [rows,D], y_f32 fp32 [rows,D].  mean/rstd fp32 [rows].
  */
-int cb_layernorm_fwd(const void* x, const int* in_idx, const float* gamma, const float* beta, void* y, float* y_f32,
+int cb_layernorm_fwd(const float* x, const int* in_idx, const float* gamma, const float* beta, void* y, float* y_f32,
                      float* mean, float* rstd, int rows, int D, float eps, void* stream);
-/* dx[idx[r]] = dLN(dy[r]) (+ dres[idx[r]]);  dgamma/dbeta/dcolsum (= column sum of dLN) fp32 [D], ACCUMULATED. */
-int cb_layernorm_bwd(const void* dy, const float* dy_f32, const void* x, const int* idx, const float* gamma,
-                     const float* mean, const float* rstd, const void* dres, void* dx, float* dgamma, float* dbeta,
+/* dx[idx[r]] = dLN(dy[r]) (+ dres[idx[r]]), written as fp32 (dx_f32) and/or bf16 (dx_bf16); dy, x, dres fp32;
+ * dgamma/dbeta/dcolsum (= column sum of dLN, i.e. the bias gradient of the preceding linear) fp32 [D], ACCUMULATED. */
+int cb_layernorm_bwd(const float* dy, const float* x, const int* idx, const float* gamma, const float* mean,
+                     const float* rstd, const float* dres, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta,
                      float* dcolsum, int rows, int D, void* stream);
 /* out[n] += sum_t x[t,n]  (bias gradients);  x bf16 [T,N] with row stride ld */
 int cb_colsum_bf16(const void* x, int ld, float* out, int T, int N, void* stream);

@@ -40,10 +40,11 @@ def name_seed(name: str, salt: int = 0) -> int:
     return (zlib.crc32(name.encode()) + 7919 * salt) & 0xFFFFFFFF
 
 
-def param_scale(name: str) -> tuple[float, float]:
-    """(scale, offset) used for a state-dict entry, chosen so attention is not flat and LN is not identity."""
+def param_scale(name: str, shape=()) -> tuple[float, float]:
+    """(scale, offset) used for a state-dict entry, chosen so attention is neither flat nor one-hot (attention scores
+    have a standard deviation of about 1.5 for LayerNorm-ed inputs, like a trained model) and LN is not the identity."""
     if name.endswith("in_proj_weight"):
-        return 0.30, 0.0
+        return float((4.5 / shape[1]) ** 0.5), 0.0
     if name.endswith("weight_g"):
         return 0.0, 1.0  # reference pins weight_g to 1 (src/methods/dino.py:81)
     if name.endswith("weight_v"):
@@ -65,7 +66,7 @@ def det_state_dict(shapes: dict, salt: int = 0) -> dict:
     """name -> float32 ndarray for every (name, shape) in ``shapes`` (insertion order kept)."""
     out = {}
     for name, shape in shapes.items():
-        sc, off = param_scale(name)
+        sc, off = param_scale(name, tuple(shape))
         out[name] = det_uniform(tuple(shape), name_seed(name, salt), sc, off)
     return out
 
