@@ -1,0 +1,292 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: one ChAda-ViT-moyen/16 DINO pre-training step (BASELINE.json configs[2]).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+A step = student forward on 2 global (224^2) + 6 local (96^2) crops of 64 images per GPU with a ragged 1..10 channel
+mix, teacher forward on the global crops, DINO head + fused loss, backward, gradient all-reduce (N > 1), fused AdamW,
+teacher EMA and centre update — the reference's wiring (local crops go through the student backbone only).
+Prints ONE JSON line (rank 0).  `value` = images/s with inputs resident in HBM; `e2e` = the same step through the public
+API from pinned HOST buffers (H2D of every crop + D2H of the loss inside the timed region).  `roofline` = the dominant
+kernel class timed live with CUDA events; `cpu_baseline` = the oracle port on the host cores on a bounded sample.
+`--impl reference` times that CPU port as its own arm (the reference is pure Python/PyTorch; /root/reference does not
+exist on the GPU box, so the arm runs oracle/chada_oracle.py, which is pinned to the reference by tests/golden).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+D_MODEL, N_PROTO, BATCH, N_GLOBAL, N_LOCAL = 192, 4096, 64, 2, 6
+METRIC = "DINO pretrain imgs/s at 1/2/4/8 B200; varlen attn TFLOPS vs BF16 peak"
+
+
+def channel_counts(batch: int, seed: int = 1234):
+    """C_b ~ U{1..10} (HOW_TO_USE.ipynb cell 16), fixed seed, identical on every rank -> ranks are token-balanced."""
+    return np.random.RandomState(seed).randint(1, 11, size=batch).tolist()
+
+
+def make_crops(counts, seed, device, pin=False):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    G = sum(counts)
+    crops = []
+    for i in range(N_GLOBAL + N_LOCAL):
+        hw = 224 if i < N_GLOBAL else 96
+        x = torch.randn(G, 1, hw, hw, generator=g)
+        crops.append(x.pin_memory() if pin else x.to(device))
+    return crops
+
+
+def dino_cfg(multicrop=False):
+    return {"method": "dino", "backbone": {"kwargs": {"patch_size": 16, "embed_dim": D_MODEL, "return_all_tokens": False}},
+            "data": {"max_img_channels": 10, "num_large_crops": N_GLOBAL, "num_small_crops": N_LOCAL},
+            "method_kwargs": {"num_prototypes": N_PROTO, "multicrop_loss": multicrop}, "max_epochs": 100, "max_steps": 100000,
+            "optimizer": {"lr": 5e-4, "weight_decay": 1e-4}, "momentum": {"base_tau": 0.9995, "final_tau": 1.0}}
+
+
+# ---------------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.stop = index, [], threading.Event()
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([s.strip() for s in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.1)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.t.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no_samples"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons, "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------- CPU arm (oracle port)
+def cpu_port_step(n_images: int, threads: int, reps: int, warmup: int = 1):
+    """The reference's algorithm (oracle port, fp32, padded + key-padding mask) for the same step on `n_images` images."""
+    from oracle import chada_oracle as O
+    from oracle import det
+    torch.set_num_threads(threads)
+    counts = channel_counts(BATCH)[:n_images]
+    stu = {k: torch.from_numpy(v).requires_grad_() for k, v in det.det_state_dict(O.backbone_shapes(D_MODEL), 1).items()}
+    tea = {k: torch.from_numpy(v) for k, v in det.det_state_dict(O.backbone_shapes(D_MODEL), 2).items()}
+    sh = {k: torch.from_numpy(v).requires_grad_() for k, v in det.det_state_dict(O.head_shapes(D_MODEL, N_PROTO), 3).items()}
+    th = {k: torch.from_numpy(v) for k, v in det.det_state_dict(O.head_shapes(D_MODEL, N_PROTO), 4).items()}
+    sh["last_layer.weight_g"].requires_grad_(False)
+    params = [p for p in list(stu.values()) + list(sh.values()) if p.requires_grad]
+    opt = torch.optim.AdamW(params, lr=5e-4, weight_decay=1e-4)
+    crops = make_crops(counts, 99, "cpu")
+    center = torch.zeros(1, N_PROTO)
+    times = []
+    for it in range(warmup + reps):
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        loss, center = O.dino_step(crops, [counts] * (N_GLOBAL + N_LOCAL), stu, sh, tea, th, center, nhead=2, final_eps=1e-6,
+                                   num_large_crops=N_GLOBAL, run_local_crops=True)
+        loss.backward()
+        opt.step()
+        with torch.no_grad():
+            for d_on, d_mo in ((stu, tea), (sh, th)):
+                for k in d_on:
+                    d_mo[k].mul_(0.9995).add_(d_on[k].detach(), alpha=0.0005)
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    return n_images / float(np.median(times)), float(np.median(times))
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_img = 2
+    t0 = time.perf_counter()
+    ips, sec = cpu_port_step(n_img, cores, reps=max(1, args.steps), warmup=min(1, args.warmup))
+    line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": "imgs/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"ChAda-ViT-moyen/16 DINO pretraining step (2x224^2 + 6x96^2 crops, ragged 1-10 channels), "
+                                   f"CPU sample of {n_img} images per step", "global_batch": n_img},
+            "cpu_baseline": {"value": ips, "unit": "imgs/s", "cores": cores, "kind": "port",
+                             "sample": f"{n_img} images x 8 crops per step, oracle port of the reference modules (fp32, padded+masked), "
+                                       f"fwd+bwd+AdamW+EMA, median of {max(1, args.steps)} steps"},
+            "e2e": {"value": ips, "unit": "imgs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "wall_s": time.perf_counter() - t0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--multicrop", action="store_true", help="true multi-crop loss (V=8) instead of the reference wiring")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch.distributed as dist
+    from chadavit_b200 import _lib, ops
+    from chadavit_b200.methods import DINO
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+
+    torch.manual_seed(0)                      # identical random init on every rank (DDP replicas)
+    model = DINO(dino_cfg(args.multicrop)).to(dev)
+    counts = channel_counts(BATCH)            # same multiset on every rank -> token-balanced
+    lnc = [counts] * (N_GLOBAL + N_LOCAL)
+    crops = make_crops(counts, 1234 + rank, dev)
+    batch = (crops, None, lnc)
+    tokens_g = sum(1 + c * 196 for c in counts)
+    tokens_l = sum(1 + c * 36 for c in counts)
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        loss = model.fused_train_step(batch)
+    sync()
+    # ---- timed region 1: inputs resident in HBM, with per-kernel-class event timing
+    ops.PROFILE = {"cb_attn_varlen_fwd": [0, 0.0, []], "cb_attn_varlen_bwd": [0, 0.0, []], "cb_gemm_bf16": [0, 0.0, []]}
+    launches0 = _lib.launch_count
+    with ClockSampler(local_rank) as clk:
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            loss = model.fused_train_step(batch)
+        e1.record()
+        sync()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count - launches0
+    prof = {}
+    for name, (n, work, evs) in ops.PROFILE.items():
+        t = sum(a.elapsed_time(b) for a, b in evs)
+        prof[name] = {"launches": n, "ms_total": t, "work": work}
+    ops.PROFILE = None
+    loss_val = float(loss.item())
+
+    # ---- timed region 2: end to end through the public API from pinned host buffers
+    host_crops = make_crops(counts, 1234 + rank, dev, pin=True)
+    h2d = sum(c.numel() * 4 for c in host_crops)
+    for _ in range(2):
+        model.fused_train_step(([c.to(dev, non_blocking=True) for c in host_crops], None, lnc)).item()
+    sync()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(args.steps):
+        l = model.fused_train_step(([c.to(dev, non_blocking=True) for c in host_crops], None, lnc))
+        _ = l.item()                           # D2H read of the step's loss
+    e3.record()
+    sync()
+    ms_e2e = e2.elapsed_time(e3)
+
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)   # kernels timed inside a long step -> sustained figure
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s (B200_PROFILING.md)"
+    top = max(prof, key=lambda k: prof[k]["ms_total"])
+    roof = {}
+    for name, p in prof.items():
+        ach = p["work"] / (p["ms_total"] * 1e-3) / 1e12 if p["ms_total"] > 0 else 0.0
+        roof[name] = {"launches_per_step": p["launches"] / args.steps, "ms_per_step": p["ms_total"] / args.steps,
+                      "share_of_step": p["ms_total"] / ms, "achieved_tflops": ach, "frac": ach / tf_peak}
+    tp = prof[top]
+    roofline = {"kernel": top, "bound": "tensor", "achieved": roof[top]["achieved_tflops"], "peak": tf_peak, "unit": "TFLOP/s",
+                "frac": roof[top]["frac"], "traffic": None, "peak_source": peak_src,
+                "algorithmic_flops_per_launch": tp["work"] / max(1, tp["launches"]),
+                "avg_launch_ms": tp["ms_total"] / max(1, tp["launches"]), "all": roof}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        n_img = 2
+        ips, sec = cpu_port_step(n_img, cores, reps=1, warmup=0)
+        cpu = {"value": ips, "unit": "imgs/s", "cores": cores, "kind": "port",
+               "sample": f"{n_img} images x 8 crops, one step (fwd+bwd+AdamW+EMA) of the oracle port of the reference modules, fp32, {sec:.1f} s"}
+
+    imgs = BATCH * world
+    line = {
+        "metric": METRIC, "value": imgs * args.steps / (ms * 1e-3), "unit": "imgs/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "ChAda-ViT-moyen/16 (D=192, 12 blocks, 2 heads, FFN 2048) DINO pretraining step: 2x224^2 global + "
+                               "6x96^2 local crops, batch 64/GPU, ragged U{1..10} channels, K=4096 prototypes, AdamW + teacher EMA; "
+                               + ("true multi-crop loss (V=8)" if args.multicrop else "reference wiring (local crops: student backbone only, SURVEY Q11)"),
+                   "global_batch": imgs, "per_gpu_batch": BATCH, "sum_channels_per_gpu": int(sum(counts)),
+                   "tokens_per_gpu_global_crop": tokens_g, "tokens_per_gpu_local_crop": tokens_l,
+                   "parallelism": f"dp{world}", "ranks_token_balanced": True,
+                   "l2_policy": "working set per step (~10 GB of activations) >> 126 MB L2; no explicit flush"},
+        "clocks": clk.summary(),
+        "e2e": {"value": imgs * args.steps / (ms_e2e * 1e-3), "unit": "imgs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "loss": loss_val,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -30,6 +30,17 @@ SIGNATURES = {
     "cb_gather_rows_f32": [_vp, _vp, _vp, _i, _i, _vp],
     "cb_attn_varlen_fwd": [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _f, _vp],
     "cb_attn_varlen_bwd": [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _f, _vp],
+    "cb_gelu_fwd": [_vp, _vp, _l, _vp],
+    "cb_gelu_bwd": [_vp, _vp, _vp, _l, _vp],
+    "cb_l2norm_fwd": [_vp, _vp, _vp, _i, _i, _f, _vp],
+    "cb_l2norm_bwd": [_vp, _vp, _vp, _vp, _i, _i, _vp],
+    "cb_weightnorm_fwd": [_vp, _vp, _vp, _vp, _i, _i, _vp],
+    "cb_weightnorm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
+    "cb_dino_loss_fwd_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _vp],
+    "cb_colsum_f32": [_vp, _vp, _i, _i, _vp],
+    "cb_dino_center_ema": [_vp, _vp, _f, _f, _i, _vp],
+    "cb_ema_update": [_vp, _vp, _vp, _f, _l, _vp],
+    "cb_adamw_step": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _l, _f, _f, _f, _f, _f, _i, _f, _f, _vp],
 }
 
 _lib = None

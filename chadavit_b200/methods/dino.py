@@ -1,0 +1,372 @@
+"""DINOHead and the DINO training-step engine behind the reference's interfaces (src/methods/dino.py, the crop
+loops of src/methods/base.py:668-733,1186-1276).
+
+* ``DINOHead`` keeps the reference's constructor, ``.mlp`` / ``.last_layer`` attributes and state-dict keys
+  (``mlp.{0,2,4}.{weight,bias}``, ``last_layer.weight_g``, ``last_layer.weight_v``); its forward/backward run on the
+  tcgen05 GEMM + the small fused kernels in csrc/dino.cu.
+* ``DINO`` reproduces the reference wiring of one training step: the student head and the loss see
+  only the large crops, small crops go through the student backbone and are discarded, the teacher sees the large crops,
+  the loss uses the old centre, the EMA follows the optimizer step.  ``training_step`` is the autograd-compatible
+  drop-in (returns a loss tensor for ``loss.backward()``); ``fused_train_step`` is the engine path used for throughput:
+  no autograd graph, gradients accumulated straight into flat arenas, ONE fused AdamW+EMA+bf16-refresh launch per network.
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from .. import ops
+from ..arena import ParamArena
+from ..backbones.chada_vit import ChAdaViT, trunc_normal_, vit_channels
+from ..losses.dino import DINOLoss
+from ..utils.momentum import MomentumUpdater, initialize_momentum_params
+
+
+class _HeadSaved:
+    __slots__ = ("ins", "pres", "z", "inv", "zn16", "wn16", "winv")
+
+
+class _HeadFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, module: "DINOHead", x: torch.Tensor, *params):
+        out, saved = module._forward_impl(x, save=True)
+        ctx.module, ctx.saved = module, saved
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        m: DINOHead = ctx.module
+        gflat = torch.zeros_like(m.arena.fp32)
+        dx = m._backward_impl(ctx.saved, dout.contiguous(), gflat)
+        ctx.saved = None
+        grads = tuple(m.arena.g32(n, gflat) if p.requires_grad else None for n, p in zip(m.arena.names, m.arena.params))
+        return (None, dx) + grads
+
+
+class DINOHead(nn.Module):
+    """3-layer MLP -> L2 normalise -> weight-normed prototypes (src/methods/dino.py:32-111)."""
+    mlp: Any
+    last_layer: Any
+
+    def __init__(self, in_dim: int, num_prototypes: int, use_bn: bool = True, norm_last_layer: bool = True, num_layers: int = 3,
+                 hidden_dim: int = 2048, bottleneck_dim: int = 256):
+        super().__init__()
+        if use_bn:
+            raise NotImplementedError("chadavit_b200.DINOHead: use_bn=True (BatchNorm1d in the projector) is not supported; the "
+                                      "reference's DINO config default is use_bn_in_head=False (src/methods/dino.py:207-209)")
+        num_layers = max(num_layers, 1)
+        if num_layers == 1:
+            self.mlp = nn.Linear(in_dim, bottleneck_dim)
+        else:
+            layers: List[Any] = [nn.Linear(in_dim, hidden_dim), nn.GELU()]
+            for _ in range(num_layers - 2):
+                layers += [nn.Linear(hidden_dim, hidden_dim), nn.GELU()]
+            layers.append(nn.Linear(hidden_dim, bottleneck_dim))
+            self.mlp = nn.Sequential(*layers)
+        self.apply(self._init_weights)
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            self.last_layer = nn.utils.weight_norm(nn.Linear(bottleneck_dim, num_prototypes, bias=False))
+        self.last_layer.weight_g.data.fill_(1)
+        if norm_last_layer:
+            self.last_layer.weight_g.requires_grad = False
+        self.in_dim, self.bottleneck_dim, self.num_prototypes = in_dim, bottleneck_dim, num_prototypes
+        self._arena: Optional[ParamArena] = None
+
+    @staticmethod
+    def _init_weights(m: nn.Module):
+        if isinstance(m, nn.Linear):
+            trunc_normal_(m.weight, std=0.02)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+
+    @property
+    def arena(self) -> ParamArena:
+        if self._arena is None:
+            self._arena = ParamArena(self)
+        return self._arena
+
+    def _linear_names(self) -> List[str]:
+        if isinstance(self.mlp, nn.Linear):
+            return ["mlp"]
+        return [f"mlp.{i}" for i, l in enumerate(self.mlp) if isinstance(l, nn.Linear)]
+
+    def _ready(self) -> ParamArena:
+        a = self.arena
+        a.ensure()
+        if a.fp32.device.type != "cuda":
+            raise RuntimeError("chadavit_b200.DINOHead runs on CUDA (sm_100a) only; there is no CPU fallback")
+        a.refresh_bf16()
+        return a
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if not x.is_cuda:
+            raise RuntimeError("chadavit_b200.DINOHead needs CUDA inputs (no CPU fallback)")
+        self._ready()
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.arena.params)):
+            return _HeadFn.apply(self, x, *self.arena.params)
+        return self._forward_impl(x, save=False)[0]
+
+    # ------------------------------------------------------------------ kernels
+    def _forward_impl(self, x: torch.Tensor, save: bool):
+        a = self.arena
+        names = self._linear_names()
+        h16 = ops.cast_bf16(x.detach().contiguous().float())
+        ins, pres = [], []
+        pre = None
+        for li, n in enumerate(names):
+            pre = ops.gemm(h16, a.v16(n + ".weight"), bias=a.v32(n + ".bias"), flags=ops.EPI_OUT_F32)
+            ins.append(h16)
+            if li < len(names) - 1:
+                pres.append(pre)
+                h16 = ops.gelu_fwd(pre)
+        zn16, inv = ops.l2norm_fwd(pre, 1e-12)
+        wn16, winv = ops.weightnorm_fwd(a.v32("last_layer.weight_v"), a.v32("last_layer.weight_g").view(-1))
+        logits = ops.gemm(zn16, wn16, flags=ops.EPI_OUT_F32)
+        if not save:
+            return logits, None
+        s = _HeadSaved()
+        s.ins, s.pres, s.z, s.inv, s.zn16, s.wn16, s.winv = ins, pres, pre, inv, zn16, wn16, winv
+        return logits, s
+
+    def _backward_impl(self, s: _HeadSaved, dlogits: torch.Tensor, gflat: torch.Tensor) -> torch.Tensor:
+        """Accumulates parameter gradients into ``gflat`` (arena-shaped fp32) and returns d(input) fp32."""
+        a = self.arena
+        g = lambda n: a.g32(n, gflat)  # noqa: E731
+        names = self._linear_names()
+        d16 = dlogits if dlogits.dtype == torch.bfloat16 else ops.cast_bf16(dlogits.float().contiguous())
+        dzn = ops.gemm(d16, s.wn16, b_mn=True, flags=ops.EPI_OUT_F32)
+        dwn = ops.gemm(d16, s.zn16, a_mn=True, b_mn=True, flags=ops.EPI_OUT_F32)
+        wg = self.last_layer.weight_g
+        ops.weightnorm_bwd(dwn, a.v32("last_layer.weight_v"), a.v32("last_layer.weight_g").view(-1), s.winv, g("last_layer.weight_v"),
+                           g("last_layer.weight_g").view(-1) if wg.requires_grad else None)
+        dcur = ops.l2norm_bwd(dzn, s.z, s.inv)
+        dx = None
+        for li in reversed(range(len(names))):
+            n = names[li]
+            ops.gemm(dcur, s.ins[li], a_mn=True, b_mn=True, flags=ops.EPI_ATOMIC, out=g(n + ".weight"))
+            ops.colsum(dcur, g(n + ".bias"))
+            dact = ops.gemm(dcur, a.v16(n + ".weight"), b_mn=True, flags=ops.EPI_OUT_F32)
+            if li > 0:
+                dcur = ops.gelu_bwd(dact, s.pres[li - 1])
+            else:
+                dx = dact
+        return dx
+
+
+# ------------------------------------------------------------------------------------------------ DINO engine
+def _cfg(cfg, path: str, default=None):
+    cur = cfg
+    for k in path.split("."):
+        if cur is None:
+            return default
+        cur = cur.get(k, None) if isinstance(cur, dict) else getattr(cur, k, None)
+    return default if cur is None else cur
+
+
+class DINO(nn.Module):
+    """DINO method without the Lightning shell: same sub-module names as the reference LightningModule
+    (``backbone``, ``momentum_backbone``, ``head``, ``momentum_head``, ``dino_loss_func``, ``momentum_updater``) so
+    checkpoints' ``state_dict`` keys line up, same ``cfg`` fields (dict / namespace / DictConfig)."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        kwargs = dict(_cfg(cfg, "backbone.kwargs", {}) or {})
+        kwargs.setdefault("patch_size", 16)
+        kwargs.setdefault("embed_dim", 192)
+        kwargs.setdefault("return_all_tokens", False)
+        kwargs["max_number_channels"] = _cfg(cfg, "data.max_img_channels", 10)          # base.py:166-167
+        if kwargs["return_all_tokens"]:
+            raise NotImplementedError("DINO pre-training uses the CLS embedding (return_all_tokens=False)")
+        method = _cfg(cfg, "method", "dino")
+        self.backbone: ChAdaViT = vit_channels(method, **kwargs)
+        self.momentum_backbone: ChAdaViT = vit_channels(method, **kwargs)                # base.py:1005-1031
+        initialize_momentum_params(self.backbone, self.momentum_backbone)
+        self.features_dim = self.backbone.num_features
+        mk = lambda: DINOHead(in_dim=self.features_dim, hidden_dim=_cfg(cfg, "method_kwargs.proj_hidden_dim", 2048),  # noqa: E731
+                              use_bn=_cfg(cfg, "method_kwargs.use_bn_in_head", False),
+                              bottleneck_dim=_cfg(cfg, "method_kwargs.proj_output_dim", 256),
+                              num_prototypes=_cfg(cfg, "method_kwargs.num_prototypes", 4096),
+                              norm_last_layer=_cfg(cfg, "method_kwargs.norm_last_layer", True))
+        self.head, self.momentum_head = mk(), mk()
+        initialize_momentum_params(self.head, self.momentum_head)
+        self.max_epochs = _cfg(cfg, "max_epochs", 100)
+        self.num_large_crops = _cfg(cfg, "data.num_large_crops", 2)
+        self.num_small_crops = _cfg(cfg, "data.num_small_crops", 0)
+        self.num_crops = self.num_large_crops + self.num_small_crops
+        # reference wiring: DINOLoss is built with its default num_large_crops=2 (Q11); multicrop_loss=True is the
+        # "true multi-crop" variant (all V views through head and loss), labelled separately in bench.py
+        self.multicrop_loss = bool(_cfg(cfg, "method_kwargs.multicrop_loss", False))
+        self.dino_loss_func = DINOLoss(
+            num_prototypes=_cfg(cfg, "method_kwargs.num_prototypes", 4096),
+            student_temp=_cfg(cfg, "method_kwargs.student_temperature", 0.1),
+            warmup_teacher_temp=_cfg(cfg, "method_kwargs.warmup_teacher_temperature", 0.04),
+            teacher_temp=_cfg(cfg, "method_kwargs.teacher_temperature", 0.07),
+            warmup_teacher_temp_epochs=_cfg(cfg, "method_kwargs.warmup_teacher_temperature_epochs", 0),
+            num_epochs=self.max_epochs,
+            num_large_crops=self.num_crops if self.multicrop_loss else 2,
+        )
+        self.clip_grad = _cfg(cfg, "method_kwargs.clip_grad", 0)
+        self.freeze_last_layer = _cfg(cfg, "method_kwargs.freeze_last_layer", 1)
+        self.momentum_updater = MomentumUpdater(_cfg(cfg, "momentum.base_tau", 0.9995), _cfg(cfg, "momentum.final_tau", 1.0))
+        self.lr = _cfg(cfg, "optimizer.lr", 5e-4)
+        self.weight_decay = _cfg(cfg, "optimizer.weight_decay", 1e-4)
+        self.betas = tuple(_cfg(cfg, "optimizer.kwargs.betas", (0.9, 0.999)))
+        self.adam_eps = _cfg(cfg, "optimizer.kwargs.eps", 1e-8)
+        self.exclude_bias_n_norm_wd = bool(_cfg(cfg, "optimizer.exclude_bias_n_norm_wd", False))
+        self.current_epoch = 0
+        self.global_step = 0
+        self.max_steps = _cfg(cfg, "max_steps", 100000)
+        self.list_num_channels: List[List[int]] = []
+        self._opt: Dict[str, Dict[str, torch.Tensor]] = {}
+        if self.clip_grad:
+            raise NotImplementedError("clip_grad > 0 (per-parameter clipping, dino.py:249-261) is not implemented in this round")
+
+    # ------------------------------------------------------------------ reference-shaped pieces
+    @property
+    def momentum_pairs(self) -> List[Tuple[nn.Module, nn.Module]]:
+        return [(self.backbone, self.momentum_backbone), (self.head, self.momentum_head)]
+
+    @property
+    def learnable_params(self) -> List[dict]:
+        return [{"name": "backbone", "params": self.backbone.parameters()}, {"name": "head", "params": self.head.parameters()}]
+
+    def on_train_epoch_start(self):
+        self.dino_loss_func.epoch = self.current_epoch
+
+    def forward(self, X: torch.Tensor, index: int) -> Dict[str, Any]:
+        feats = self.backbone(X, index, self.list_num_channels)
+        return {"feats": feats, "z": self.head(feats)}
+
+    @torch.no_grad()
+    def momentum_forward(self, X: torch.Tensor, index: int) -> Dict[str, Any]:
+        feats = self.momentum_backbone(X, index, self.list_num_channels)
+        return {"feats": feats, "z": self.momentum_head(feats)}
+
+    def training_step(self, batch: Sequence[Any], batch_idx: int = 0) -> torch.Tensor:
+        """Autograd drop-in of DINO.training_step (dino.py:300-325 + base.py:668-733,1186-1248): returns the loss tensor."""
+        X, _targets, list_num_channels = batch
+        self.list_num_channels = list_num_channels
+        X = [X] if isinstance(X, torch.Tensor) else X
+        assert len(X) == self.num_crops                                              # base.py:693
+        nl = self.num_large_crops
+        z = [self(x, i)["z"] for i, x in enumerate(X[:nl])]
+        for i, x in enumerate(X[nl:]):                                               # base.py:701-707 (index restarts at 0, Q12)
+            feats = self.backbone(x, i, list_num_channels)
+            if self.multicrop_loss:
+                z.append(self.head(feats))
+        mz = [self.momentum_forward(x, i)["z"] for i, x in enumerate(X[:nl])]
+        return self.dino_loss_func(torch.cat(z), torch.cat(mz))
+
+    def on_after_backward(self):
+        if self.current_epoch < self.freeze_last_layer:                              # dino.py:374-376
+            for p in self.head.last_layer.parameters():
+                p.grad = None
+
+    @torch.no_grad()
+    def on_train_batch_end(self):
+        """EMA of (backbone, head) into their momentum copies, then the cosine tau update (base.py:1250-1276)."""
+        for on, mo in self.momentum_pairs:
+            self.momentum_updater.update(on, mo)
+        self.global_step += 1
+        self.momentum_updater.update_tau(cur_step=self.global_step, max_steps=self.max_steps)
+
+    def configure_optimizers(self):
+        params = [{"params": list(self.backbone.parameters())}, {"params": list(self.head.parameters())}]
+        return torch.optim.AdamW(params, lr=self.lr, weight_decay=self.weight_decay, betas=self.betas, eps=self.adam_eps)
+
+    # ------------------------------------------------------------------ engine path
+    def _opt_state(self, name: str, arena: ParamArena) -> Dict[str, torch.Tensor]:
+        st = self._opt.get(name)
+        if st is None or st["m"].device != arena.fp32.device or st["m"].numel() != arena.numel:
+            flags = torch.zeros(arena.numel, dtype=torch.uint8)
+            for n, p in zip(arena.names, arena.params):
+                off, cnt, _ = arena.offsets[n]
+                decay = not (self.exclude_bias_n_norm_wd and (p.dim() <= 1 or "norm" in n))
+                flags[off:off + cnt] = (1 if decay else 0) | (0 if p.requires_grad else 2)
+            # alignment padding between parameters: frozen
+            used = torch.zeros(arena.numel, dtype=torch.bool)
+            for n in arena.names:
+                off, cnt, _ = arena.offsets[n]
+                used[off:off + cnt] = True
+            flags[~used] = 2
+            st = {"m": torch.zeros_like(arena.fp32), "v": torch.zeros_like(arena.fp32), "flags": flags.to(arena.fp32.device),
+                  "flags_frozen_last": None}
+            if name == "head":
+                fl = flags.clone()
+                for n in arena.names:
+                    if n.startswith("last_layer."):
+                        off, cnt, _ = arena.offsets[n]
+                        fl[off:off + cnt] = 2
+                st["flags_frozen_last"] = fl.to(arena.fp32.device)
+            self._opt[name] = st
+        return st
+
+    @torch.no_grad()
+    def fused_train_step(self, batch: Sequence[Any], lr: Optional[float] = None) -> torch.Tensor:
+        """One complete DINO step (forward, loss, backward, gradient all-reduce, AdamW, teacher EMA, tau update) without an
+        autograd graph.  Semantics identical to training_step + on_after_backward + AdamW.step + on_train_batch_end."""
+        X, _targets, list_num_channels = batch
+        X = [X] if isinstance(X, torch.Tensor) else X
+        assert len(X) == self.num_crops
+        nl = self.num_large_crops
+        bb, tb, hd, th = self.backbone, self.momentum_backbone, self.head, self.momentum_head
+        for m in (bb, tb, hd, th):
+            m._ready()
+        gb, gh = bb.arena.ensure_grad(), hd.arena.ensure_grad()
+        gb.zero_()
+        gh.zero_()
+        # student: large crops (saved for backward), small crops (reference: forward only, output discarded)
+        saved, feats = [], []
+        for i, x in enumerate(X[:nl]):
+            f, s = bb._forward_impl(x, list_num_channels[i], save=True)
+            saved.append(s)
+            feats.append(f)
+        for i, x in enumerate(X[nl:]):
+            f, s = bb._forward_impl(x, list_num_channels[i], save=self.multicrop_loss)
+            if self.multicrop_loss:
+                saved.append(s)
+                feats.append(f)
+        rows = [f.shape[0] for f in feats]
+        logits, hs = hd._forward_impl(torch.cat(feats), save=True)
+        # teacher: large crops only
+        tfeats = [tb._forward_impl(x, list_num_channels[i], save=False)[0] for i, x in enumerate(X[:nl])]
+        tlogits, _ = th._forward_impl(torch.cat(tfeats), save=False)
+        # loss + d(loss)/d(student logits) in one pass, then the centre update (old centre used by the loss, Q13)
+        L = self.dino_loss_func
+        temp = float(L.teacher_temp_schedule[L.epoch])
+        loss, _, d16 = ops.dino_loss_fwd_bwd(logits, tlogits, L.center.view(-1), L.num_large_crops, L.student_temp, temp)
+        L.update_center(tlogits)
+        # backward: head, then each saved backbone call
+        dfe = hd._backward_impl(hs, d16, gh)
+        o = 0
+        for s, r in zip(saved, rows):
+            bb._backward_impl(s, dfe[o:o + r].contiguous(), gb)
+            o += r
+        # data-parallel replicas: average gradients (C1) — flat arenas, one NCCL all-reduce each
+        world = 1
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            world = dist.get_world_size()
+            dist.all_reduce(gb)
+            dist.all_reduce(gh)
+        # AdamW + teacher EMA + bf16 refresh of student and teacher, one launch per network
+        self.global_step += 1
+        lr = self.lr if lr is None else lr
+        tau = self.momentum_updater.cur_tau
+        for name, on, mo, g in (("backbone", bb, tb, gb), ("head", hd, th, gh)):
+            st = self._opt_state(name, on.arena)
+            flags = st["flags"]
+            if name == "head" and self.current_epoch < self.freeze_last_layer:
+                flags = st["flags_frozen_last"]
+            ops.adamw_step(on.arena.fp32, g, st["m"], st["v"], lr=lr, beta1=self.betas[0], beta2=self.betas[1], eps=self.adam_eps,
+                           weight_decay=self.weight_decay, step=self.global_step, flags=flags, p_bf16=on.arena.bf16,
+                           teacher=mo.arena.fp32, teacher_bf16=mo.arena.bf16, grad_scale=1.0 / world, tau=tau)
+            for ar in (on.arena, mo.arena):
+                ar.mark_dirty()
+                ar._bf16_key = (ar.manual_version, sum(p._version for p in ar.params))   # shadows were refreshed by the kernel
+        self.momentum_updater.update_tau(cur_step=self.global_step, max_steps=self.max_steps)
+        return loss[0]

@@ -28,9 +28,26 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
-def _call(name: str, *args) -> None:
+# kernels launched per C-ABI call (for bench.py's gpu_launches claim; memsets are not counted)
+_KERNELS_PER_CALL = {"cb_tokenize_fwd": 2, "cb_tokenize_bwd": 2, "cb_attn_varlen_bwd": 3, "cb_sync_check": 0}
+
+# Optional per-kernel-class device timing (bench.py): PROFILE[name] = [n_launches, work, [(start_evt, end_evt), ...]]
+PROFILE = None
+
+
+def _call(name: str, *args, work: float = 0.0) -> None:
     lib = _lib.load()
-    _lib.launch_count += 1
+    _lib.launch_count += _KERNELS_PER_CALL.get(name, 1)
+    if PROFILE is not None and name in PROFILE:
+        rec = PROFILE[name]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(getattr(lib, name)(*args), name)
+        e1.record()
+        rec[0] += 1
+        rec[1] += work
+        rec[2].append((e0, e1))
+        return
     _lib.check(getattr(lib, name)(*args), name)
 
 
@@ -52,7 +69,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
         out = torch.empty(M, N, device=A.device, dtype=torch.float32 if flags & (EPI_OUT_F32 | EPI_ATOMIC) else bf16)
     assert out.shape == (M, N) and out.stride(1) == 1
     _call("cb_gemm_bf16", _p(A), A.stride(0), int(a_mn), _p(B), B.stride(0), int(b_mn), _p(out), out.stride(0), M, N, K,
-          _p(bias), _p(aux), aux.stride(0) if aux is not None else 0, flags, float(alpha), k_splits, _stream())
+          _p(bias), _p(aux), aux.stride(0) if aux is not None else 0, flags, float(alpha), k_splits, _stream(), work=2.0 * M * N * K)
     return out
 
 
@@ -128,6 +145,7 @@ class PackedLayout:
         self.cu_host = cu
         self.T = int(cu[-1])
         self.max_seqlen = int(lens.max())
+        self.sum_sq = float((lens.astype(np.float64) ** 2).sum())   # sum_b S_b^2: attention work
         chan_img = np.repeat(np.arange(self.B, dtype=np.int32), counts)
         chan_idx = np.concatenate([np.arange(c, dtype=np.int32) for c in counts])
         self.chan_img_host, self.chan_idx_host = chan_img, chan_idx
@@ -196,7 +214,8 @@ def attn_fwd(qkv: torch.Tensor, lay: PackedLayout, nheads: int, *, need_lse: boo
     work = lay.attn_work(nheads)
     out = torch.empty(T, D, device=qkv.device, dtype=bf16)
     lse = torch.empty(nheads, T, device=qkv.device, dtype=torch.float32) if need_lse else None
-    _call("cb_attn_varlen_fwd", _p(qkv), _p(work), work.shape[0], _p(out), _p(lse), T, D, nheads, float(d) ** -0.5, _stream())
+    _call("cb_attn_varlen_fwd", _p(qkv), _p(work), work.shape[0], _p(out), _p(lse), T, D, nheads, float(d) ** -0.5, _stream(),
+          work=4.0 * D * lay.sum_sq)
     return out, lse
 
 
@@ -210,7 +229,7 @@ def attn_bwd(dout: torch.Tensor, qkv: torch.Tensor, out: torch.Tensor, lse: torc
     dq_acc = torch.empty(T, D, device=qkv.device, dtype=torch.float32)
     dqkv = torch.empty(T, D3, device=qkv.device, dtype=bf16)
     _call("cb_attn_varlen_bwd", _p(dout), _p(qkv), _p(out), _p(lse), _p(work), work.shape[0], _p(delta), _p(dq_acc), _p(dqkv), T, D,
-          nheads, float(d) ** -0.5, _stream())
+          nheads, float(d) ** -0.5, _stream(), work=10.0 * D * lay.sum_sq)
     return dqkv
 
 
@@ -224,3 +243,81 @@ def small_matmul_f32(A: torch.Tensor, B: torch.Tensor, *, trans_a: bool = False,
         out = torch.empty(M, N, device=A.device, dtype=torch.float32)
     _call("cb_small_matmul_f32", _p(A), _p(B), _p(out), M, N, K, int(trans_a), int(accumulate), _stream())
     return out
+
+
+# ------------------------------------------------------------------------------------------------ DINO head / loss / EMA / optimizer
+def gelu_fwd(pre: torch.Tensor) -> torch.Tensor:
+    out = torch.empty(pre.shape, device=pre.device, dtype=bf16)
+    _call("cb_gelu_fwd", _p(pre), _p(out), pre.numel(), _stream())
+    return out
+
+
+def gelu_bwd(dact: torch.Tensor, pre: torch.Tensor) -> torch.Tensor:
+    out = torch.empty(pre.shape, device=pre.device, dtype=bf16)
+    _call("cb_gelu_bwd", _p(dact), _p(pre), _p(out), pre.numel(), _stream())
+    return out
+
+
+def l2norm_fwd(x: torch.Tensor, eps: float = 1e-12):
+    rows, C = x.shape
+    out = torch.empty(rows, C, device=x.device, dtype=bf16)
+    inv = torch.empty(rows, device=x.device, dtype=torch.float32)
+    _call("cb_l2norm_fwd", _p(x), _p(out), _p(inv), rows, C, float(eps), _stream())
+    return out, inv
+
+
+def l2norm_bwd(dy: torch.Tensor, x: torch.Tensor, inv: torch.Tensor) -> torch.Tensor:
+    rows, C = x.shape
+    dx = torch.empty(rows, C, device=x.device, dtype=bf16)
+    _call("cb_l2norm_bwd", _p(dy), _p(x), _p(inv), _p(dx), rows, C, _stream())
+    return dx
+
+
+def weightnorm_fwd(v: torch.Tensor, g: torch.Tensor):
+    K, C = v.shape
+    w = torch.empty(K, C, device=v.device, dtype=bf16)
+    inv = torch.empty(K, device=v.device, dtype=torch.float32)
+    _call("cb_weightnorm_fwd", _p(v), _p(g), _p(w), _p(inv), K, C, _stream())
+    return w, inv
+
+
+def weightnorm_bwd(dw: torch.Tensor, v: torch.Tensor, g: torch.Tensor, inv: torch.Tensor, dv: torch.Tensor, dg: Optional[torch.Tensor]) -> None:
+    K, C = v.shape
+    _call("cb_weightnorm_bwd", _p(dw), _p(v), _p(g), _p(inv), _p(dv), _p(dg), K, C, _stream())
+
+
+def dino_loss_fwd_bwd(student: torch.Tensor, teacher: torch.Tensor, center: torch.Tensor, V: int, student_temp: float, teacher_temp: float,
+                      *, want_f32: bool = False, want_bf16: bool = True):
+    """Returns (loss[1] fp32, dstudent fp32 | None, dstudent bf16 | None).  student (V*B,K), teacher (2*B,K) fp32."""
+    assert student.dtype == torch.float32 and teacher.dtype == torch.float32 and student.is_contiguous() and teacher.is_contiguous()
+    K = student.shape[1]
+    B = teacher.shape[0] // 2
+    if student.shape[0] != V * B or teacher.shape[0] != 2 * B or teacher.shape[1] != K:
+        raise ValueError(f"DINOLoss: student {tuple(student.shape)} / teacher {tuple(teacher.shape)} do not match {V} student views of 2 teacher views")
+    loss = torch.empty(1, device=student.device, dtype=torch.float32)
+    d32 = torch.empty_like(student) if want_f32 else None
+    d16 = torch.empty(student.shape, device=student.device, dtype=bf16) if want_bf16 else None
+    _call("cb_dino_loss_fwd_bwd", _p(student), _p(teacher), _p(center), _p(loss), _p(d32), _p(d16), B, K, V, float(student_temp),
+          float(teacher_temp), _stream())
+    return loss, d32, d16
+
+
+def colsum_f32(x: torch.Tensor) -> torch.Tensor:
+    out = torch.empty(x.shape[1], device=x.device, dtype=torch.float32)
+    _call("cb_colsum_f32", _p(x), _p(out), x.shape[0], x.shape[1], _stream())
+    return out
+
+
+def center_ema(center: torch.Tensor, batch_sum: torch.Tensor, scale: float, momentum: float) -> None:
+    _call("cb_dino_center_ema", _p(center), _p(batch_sum), float(scale), float(momentum), center.numel(), _stream())
+
+
+def ema_update(momentum_flat: torch.Tensor, online_flat: torch.Tensor, tau: float, momentum_bf16: Optional[torch.Tensor] = None) -> None:
+    assert momentum_flat.numel() == online_flat.numel()
+    _call("cb_ema_update", _p(momentum_flat), _p(online_flat), _p(momentum_bf16), float(tau), momentum_flat.numel(), _stream())
+
+
+def adamw_step(p, g, m, v, *, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, step=1, flags=None, p_bf16=None, teacher=None,
+               teacher_bf16=None, grad_scale=1.0, tau=1.0) -> None:
+    _call("cb_adamw_step", _p(p), _p(g), _p(m), _p(v), _p(flags), _p(p_bf16), _p(teacher), _p(teacher_bf16), p.numel(), float(lr),
+          float(beta1), float(beta2), float(eps), float(weight_decay), int(step), float(grad_scale), float(tau), _stream())

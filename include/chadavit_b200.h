@@ -113,6 +113,41 @@ int cb_attn_varlen_fwd(const void* qkv, const int* work, int n_work, void* out, 
 int cb_attn_varlen_bwd(const void* dout, const void* qkv, const void* out, const float* lse, const int* work, int n_work,
                        float* delta_ws, float* dq_acc_ws, void* dqkv, int T, int D, int H, float softmax_scale, void* stream);
 
+/* ---------------- DINOHead pieces (src/methods/dino.py:61-111); the Linear layers themselves are cb_gemm_bf16 ---------------- */
+/* nn.GELU (exact erf): out bf16 = gelu(pre fp32);  backward: dpre bf16 = dact fp32 * gelu'(pre) */
+int cb_gelu_fwd(const float* pre, void* out, long n, void* stream);
+int cb_gelu_bwd(const float* dact, const float* pre, void* dpre, long n, void* stream);
+/* F.normalize(x, dim=-1, eps): out bf16 [rows,C], inv fp32 [rows] = 1/max(||x||,eps);  backward -> dx bf16 */
+int cb_l2norm_fwd(const float* x, void* out, float* inv, int rows, int C, float eps, void* stream);
+int cb_l2norm_bwd(const float* dy, const float* x, const float* inv, void* dx, int rows, int C, void* stream);
+/* nn.utils.weight_norm(Linear(C,K,bias=False)): w bf16 [K,C] = g[k] * v[k,:]/||v[k,:]||;  backward ACCUMULATES dv (and dg
+ * unless NULL = weight_g frozen by norm_last_layer, dino.py:83-84) from dw fp32 [K,C] */
+int cb_weightnorm_fwd(const float* v, const float* g, void* w, float* inv_norm, int K, int C, void* stream);
+int cb_weightnorm_bwd(const float* dw, const float* v, const float* g, const float* inv_norm, float* dv, float* dg, int K,
+                      int C, void* stream);
+
+/*
+ * DINOLoss.forward (src/losses/dino.py:81-99) fused with its gradient, one pass per batch row:
+ *   student fp32 [V*B,K] (view v = rows v*B..v*B+B), teacher fp32 [2*B,K], center fp32 [K] (the OLD center, Q13)
+ *   loss fp32 [1] (overwritten);  d(loss)/d(student) as fp32 [V*B,K] and/or bf16 [V*B,K] (either may be NULL)
+ */
+int cb_dino_loss_fwd_bwd(const float* student, const float* teacher, const float* center, float* loss, float* dstudent_f32,
+                         void* dstudent_bf16, int B, int K, int V, float student_temp, float teacher_temp, void* stream);
+/* update_center (src/losses/dino.py:103-118): out[k] = sum_r x[r,k]; then (after the caller's all-reduce)
+ * center = center*momentum + batch_sum*scale*(1-momentum), scale = 1/(world_size * rows) */
+int cb_colsum_f32(const float* x, float* out, int R, int K, void* stream);
+int cb_dino_center_ema(float* center, const float* batch_sum, float scale, float momentum, int K, void* stream);
+
+/* MomentumUpdater.update over a flat parameter arena (src/utils/momentum.py:73-74): mp = tau*mp + (1-tau)*op, one launch;
+ * optionally refreshes the teacher's bf16 shadow in the same pass.  12 B/param of algorithmic HBM traffic. */
+int cb_ema_update(float* momentum, const float* online, void* momentum_bf16, float tau, long n, void* stream);
+/* torch.optim.AdamW step over a flat arena, optionally fused with the teacher EMA and the bf16 shadow
+ * refresh of both networks.  flags[i]: bit0 = weight decay applies, bit1 = frozen (e.g. head.last_layer while
+ * current_epoch < freeze_last_layer, dino.py:374-376); NULL = decay everything. */
+int cb_adamw_step(float* p, const float* g, float* m, float* v, const unsigned char* flags, void* p_bf16, float* teacher,
+                  void* teacher_bf16, long n, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                  float grad_scale, float tau, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

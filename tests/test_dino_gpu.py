@@ -1,0 +1,180 @@
+"""GPU parity of DINOHead, DINOLoss, EMA/AdamW kernels and one full DINO step against the golden reference outputs / oracle."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import chada_oracle as O
+from oracle import det
+from tests.helpers import cases, det_params, golden, rel_err
+
+pytestmark = pytest.mark.gpu
+G = golden()
+
+
+@pytest.mark.parametrize("tag,ind", [("h32", 32), ("h192", 192)])
+def test_head_forward_backward(tag, ind):
+    from chadavit_b200.methods import DINOHead
+    K = 4096
+    P = det_params(O.head_shapes(ind, K), 11)
+    head = DINOHead(in_dim=ind, num_prototypes=K, use_bn=False)
+    assert list(head.state_dict().keys()) == list(P.keys())
+    head.load_state_dict(P)
+    head = head.cuda()
+    f = torch.from_numpy(det.det_uniform((6, ind), 21, 1.5)).cuda().requires_grad_()
+    z = head(f)
+    assert (z.detach().cpu()[:, ::16] - torch.from_numpy(G[f"head.{tag}.out_sub"])).abs().max().item() < 5e-3   # cosine logits in [-1,1]
+    wgt = torch.from_numpy(det.det_uniform(tuple(z.shape), 98, 1.0)).cuda()
+    (z * wgt).sum().backward()
+    torch.cuda.synchronize()
+    e_in = rel_err(f.grad.cpu(), torch.from_numpy(G[f"head.{tag}.grad_in"]))
+    print(f"head {tag}: grad_in rel err {e_in:.3e}")
+    assert e_in < 3e-2
+    assert head.last_layer.weight_g.grad is None                  # frozen by norm_last_layer (dino.py:83-84)
+    for k, p in head.named_parameters():
+        if p.grad is None:
+            continue
+        e = rel_err(p.grad.cpu().reshape(-1)[::997], torch.from_numpy(G[f"head.{tag}.grad.{k}.sub"]))
+        print(f"  grad {k}: rel err {e:.3e}")
+        assert e < 4e-2, k
+
+
+@pytest.mark.parametrize("V", [2, 8])
+def test_dino_loss_and_center(V):
+    from chadavit_b200.losses import DINOLoss
+    B, K = 5, 4096
+    L = DINOLoss(num_prototypes=K, warmup_teacher_temp=0.04, teacher_temp=0.07, warmup_teacher_temp_epochs=3, num_epochs=10,
+                 num_large_crops=V).cuda()
+    L.epoch = 1
+    for call in range(2):
+        s = torch.from_numpy(det.det_uniform((V * B, K), 31 + call, 1.0)).cuda().requires_grad_()
+        t = torch.from_numpy(det.det_uniform((2 * B, K), 41 + call, 1.0)).cuda()
+        loss = L(s, t)
+        loss.backward()
+        torch.cuda.synchronize()
+        ref = float(G[f"loss.V{V}.call{call}.loss"])
+        print(f"V={V} call {call}: loss {loss.item():.6f} ref {ref:.6f}")
+        assert abs(loss.item() - ref) <= 1e-3                      # north_star: <= 1e-3 absolute on the loss (fp32 here: ~1e-5)
+        assert abs(loss.item() - ref) <= 5e-5
+        assert (L.center[0, ::8].cpu() - torch.from_numpy(G[f"loss.V{V}.call{call}.center_sub"])).abs().max().item() < 1e-6
+        assert (s.grad[:, ::64].cpu() - torch.from_numpy(G[f"loss.V{V}.call{call}.grad_sub"])).abs().max().item() < 1e-6
+
+
+def test_ema_and_adamw_kernels():
+    from chadavit_b200 import ops
+    from chadavit_b200.utils.momentum import MomentumUpdater, initialize_momentum_params
+    upd = MomentumUpdater(0.99, 1.0)
+    a, b = torch.nn.Linear(7, 5), torch.nn.Linear(7, 5)
+    with torch.no_grad():
+        a.weight.copy_(torch.from_numpy(det.det_uniform((5, 7), 51))); a.bias.copy_(torch.from_numpy(det.det_uniform((5,), 52)))
+        b.weight.copy_(torch.from_numpy(det.det_uniform((5, 7), 53))); b.bias.copy_(torch.from_numpy(det.det_uniform((5,), 54)))
+    a, b = a.cuda(), b.cuda()
+    upd.update_tau(30, 100)
+    assert abs(upd.cur_tau - float(G["ema.tau_30_100"])) < 1e-12
+    upd.update(a, b)
+    torch.cuda.synchronize()
+    assert np.allclose(b.weight.detach().cpu().numpy(), G["ema.weight"], atol=1e-7)
+    assert np.allclose(b.bias.detach().cpu().numpy(), G["ema.bias"], atol=1e-7)
+    initialize_momentum_params(a, b)
+    assert torch.equal(a.weight, b.weight) and not b.weight.requires_grad
+    # fused AdamW (+EMA) against torch.optim.AdamW over 3 steps
+    n = 4096 + 512
+    g = torch.Generator().manual_seed(0)
+    p0 = torch.randn(n, generator=g)
+    ref = p0.clone().cuda().requires_grad_()
+    opt = torch.optim.AdamW([ref], lr=1e-3, weight_decay=0.05, betas=(0.9, 0.95), eps=1e-8)
+    p = p0.clone().cuda(); m = torch.zeros_like(p); v = torch.zeros_like(p)
+    teacher = p0.clone().cuda(); tref = p0.clone().cuda()
+    p16 = torch.empty(n, device="cuda", dtype=torch.bfloat16)
+    for step in range(1, 4):
+        grad = torch.randn(n, generator=g).cuda()
+        ref.grad = grad.clone()
+        opt.step()
+        tref = 0.99 * tref + 0.01 * ref.detach()
+        ops.adamw_step(p, grad * 4.0, m, v, lr=1e-3, beta1=0.9, beta2=0.95, eps=1e-8, weight_decay=0.05, step=step, p_bf16=p16,
+                       teacher=teacher, grad_scale=0.25, tau=0.99)
+    torch.cuda.synchronize()
+    assert (p - ref.detach()).abs().max().item() < 2e-6
+    assert (teacher - tref).abs().max().item() < 2e-6
+    assert torch.equal(p16, p.to(torch.bfloat16))
+
+
+def _make_dino(K, multicrop=False, small=2):
+    from chadavit_b200.methods import DINO
+    cfg = {"method": "dino", "backbone": {"kwargs": {"patch_size": 16, "embed_dim": 32, "return_all_tokens": False}},
+           "data": {"max_img_channels": 10, "num_large_crops": 2, "num_small_crops": small},
+           "method_kwargs": {"num_prototypes": K, "multicrop_loss": multicrop, "teacher_temperature": 0.07,
+                             "warmup_teacher_temperature_epochs": 0},
+           "max_epochs": 10, "optimizer": {"lr": 1e-3, "weight_decay": 0.01}}
+    return DINO(cfg)
+
+
+def test_dino_step_matches_reference_and_fused_path():
+    """Loss / centre of one reference-wired step vs the golden values of the reference modules; parameter gradients vs the
+    oracle with bf16 operand rounding; and the engine path (fused_train_step) == autograd path + torch AdamW + EMA."""
+    st = cases()["step"]
+    counts, K, sd = st["counts"], st["K"], st["seeds"]
+    model = _make_dino(K)
+    stu, tea = det_params(O.backbone_shapes(32), sd["stu"]), det_params(O.backbone_shapes(32), sd["tea"])
+    sh, th = det_params(O.head_shapes(32, K), sd["sh"]), det_params(O.head_shapes(32, K), sd["th"])
+    model.backbone.load_state_dict(stu); model.momentum_backbone.load_state_dict(tea)
+    model.head.load_state_dict(sh); model.momentum_head.load_state_dict(th)
+    model = model.cuda()
+    model.current_epoch = 1          # past freeze_last_layer so that last_layer gets updated too
+    model.on_train_epoch_start()
+    crops = [torch.from_numpy(det.det_pixels(sum(counts), 224, 224, s)).cuda() for s in sd["g"]] + \
+            [torch.from_numpy(det.det_pixels(sum(counts), 96, 96, s)).cuda() for s in sd["l"]]
+    batch = (crops, None, [counts] * 4)
+    fused = copy.deepcopy(model)
+    # ---- autograd drop-in path
+    loss = model.training_step(batch)
+    loss.backward()
+    torch.cuda.synchronize()
+    ref = float(G["step.loss"])
+    print(f"step loss {loss.item():.6f} vs reference {ref:.6f}")
+    assert abs(loss.item() - ref) <= 1e-3                                    # north_star loss tolerance
+    assert (model.dino_loss_func.center[0, ::8].cpu() - torch.from_numpy(G["step.center_sub"])).abs().max().item() < 2e-4
+    # gradients vs oracle with the same bf16 operand rounding
+    for d in (stu, sh):
+        for v in d.values():
+            v.requires_grad_()
+    with O.operand_rounding(torch.bfloat16):
+        lo, _ = O.dino_step([c.cpu() for c in crops], [counts] * 4, stu, sh, tea, th, torch.zeros(1, K), nhead=2, final_eps=1e-6,
+                            teacher_temp=0.07, run_local_crops=False)
+    lo.backward()
+    worst = 0.0
+    for tag, mod, d in (("bb", model.backbone, stu), ("head", model.head, sh)):
+        for k, p in mod.named_parameters():
+            if d[k].grad is None:
+                assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+                continue
+            e = rel_err(p.grad.cpu(), d[k].grad)
+            worst = max(worst, e)
+            assert e < 0.12, (k, e)
+    print(f"worst parameter-gradient rel err vs bf16-operand oracle: {worst:.3e}")
+    # ---- engine path == autograd path + AdamW + EMA
+    opt = model.configure_optimizers()
+    model.on_after_backward()
+    opt.step()
+    model.on_train_batch_end()
+    fused.current_epoch = 1
+    fused.on_train_epoch_start()
+    loss_f = fused.fused_train_step(batch)
+    torch.cuda.synchronize()
+    assert abs(loss_f.item() - loss.item()) < 1e-5
+    for (k, p), (_, q) in zip(model.named_parameters(), fused.named_parameters()):
+        d = (p.detach() - q.detach()).abs().max().item()
+        assert d <= 2e-3 * max(1.0, p.detach().abs().max().item()), (k, d)      # Adam normalises the update: |dp| <= lr per step
+    assert (model.dino_loss_func.center - fused.dino_loss_func.center).abs().max().item() < 1e-6
+    assert abs(model.momentum_updater.cur_tau - fused.momentum_updater.cur_tau) < 1e-12
+
+
+def test_multicrop_loss_variant_runs():
+    model = _make_dino(4096, multicrop=True).cuda()
+    counts = [1, 2]
+    crops = [torch.randn(3, 1, 224, 224, device="cuda") for _ in range(2)] + [torch.randn(3, 1, 96, 96, device="cuda") for _ in range(2)]
+    l1 = model.fused_train_step((crops, None, [counts] * 4))
+    l2 = model.fused_train_step((crops, None, [counts] * 4))
+    torch.cuda.synchronize()
+    assert torch.isfinite(l1) and torch.isfinite(l2) and l1.item() > 0
