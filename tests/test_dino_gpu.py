@@ -115,18 +115,22 @@ def test_dino_step_matches_reference_and_fused_path():
     oracle with bf16 operand rounding; and the engine path (fused_train_step) == autograd path + torch AdamW + EMA."""
     st = cases()["step"]
     counts, K, sd = st["counts"], st["K"], st["seeds"]
-    model = _make_dino(K)
     stu, tea = det_params(O.backbone_shapes(32), sd["stu"]), det_params(O.backbone_shapes(32), sd["tea"])
     sh, th = det_params(O.head_shapes(32, K), sd["sh"]), det_params(O.head_shapes(32, K), sd["th"])
-    model.backbone.load_state_dict(stu); model.momentum_backbone.load_state_dict(tea)
-    model.head.load_state_dict(sh); model.momentum_head.load_state_dict(th)
-    model = model.cuda()
-    model.current_epoch = 1          # past freeze_last_layer so that last_layer gets updated too
-    model.on_train_epoch_start()
+
+    def build():
+        m = _make_dino(K)
+        m.backbone.load_state_dict(stu); m.momentum_backbone.load_state_dict(tea)
+        m.head.load_state_dict(sh); m.momentum_head.load_state_dict(th)
+        m = m.cuda()
+        m.current_epoch = 1          # past freeze_last_layer so that last_layer gets updated too
+        m.on_train_epoch_start()
+        return m
+
+    model, fused = build(), build()
     crops = [torch.from_numpy(det.det_pixels(sum(counts), 224, 224, s)).cuda() for s in sd["g"]] + \
             [torch.from_numpy(det.det_pixels(sum(counts), 96, 96, s)).cuda() for s in sd["l"]]
     batch = (crops, None, [counts] * 4)
-    fused = copy.deepcopy(model)
     # ---- autograd drop-in path
     loss = model.training_step(batch)
     loss.backward()
@@ -158,8 +162,6 @@ def test_dino_step_matches_reference_and_fused_path():
     model.on_after_backward()
     opt.step()
     model.on_train_batch_end()
-    fused.current_epoch = 1
-    fused.on_train_epoch_start()
     loss_f = fused.fused_train_step(batch)
     torch.cuda.synchronize()
     assert abs(loss_f.item() - loss.item()) < 1e-5
