@@ -1,29 +1,32 @@
 // Persistent, warp-specialised tcgen05 GEMM for sm_100a:  C[M,N] (+)= op(A)[M,K] * op(B)[N,K]^T
 //   * operands bf16, accumulate fp32 in TMEM (double-buffered accumulators: epilogue of tile i overlaps MMA of tile i+1)
 //   * TMA (cp.async.bulk.tensor) loads into 128B/64B-swizzled smem stages, mbarrier full/empty ring
-//   * warp 0 = TMA producer, warp 1 = MMA issuer (single thread), warps 2..5 = epilogue (TMEM -> regs -> global)
+//   * warp 0 = TMA producer, warp 1 = MMA issuer (single thread), warps 2..5 = epilogue
 //   * either operand may be K-major ([rows,K] row-major) or MN-major ([K,rows] row-major); the latter is what the
 //     weight-gradient (dW = dY^T X) and input-gradient (dX = dY W) products of the encoder need without transposes
-//   * epilogue: bias, ReLU, residual add, ReLU-mask, fp32 / bf16 store, split-K fp32 atomics, tokenizer scatter
+//   * epilogue: TMEM -> registers (bias, ReLU, residual add, ReLU-mask, tokenizer embeddings) -> 128B-swizzled smem
+//     slab -> TMA store (bf16 / fp32) or TMA reduce-add (fp32 split-K weight gradients): every global write is a
+//     coalesced bulk store, issued per warp (32 rows x 128 B) and double-buffered so it overlaps the next slab
 #include "common.cuh"
 #include "chadavit_b200.h"
 #include "internal.h"
 
 namespace cb {
 
-
 constexpr int BM = 128;
 constexpr int BK = 64;
+constexpr int EPI_SLAB_BYTES = 32 * 128;            // one warp's slab: 32 rows x 128 B
+constexpr int EPI_BYTES = 4 * 2 * EPI_SLAB_BYTES;   // 4 warps x 2 buffers
 
 template <int BN>
 struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN <= 128) ? 6 : (BN <= 192 ? 5 : 4);
+  static constexpr int STAGES = (BN <= 128) ? 5 : 4;
   static constexpr int ACC_STRIDE = (BN <= 128) ? 128 : 256;  // TMEM columns between the two accumulators
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 // MODE: 0 = K-major (128B swizzle, 64-element K rows), 1 = MN-major 64-element blocks (128B swizzle),
@@ -44,13 +47,15 @@ __device__ __forceinline__ void operand_load(void* smem, const CUtensorMap* tm, 
 
 template <int BN, int AMODE, int BMODE>
 __global__ void __launch_bounds__(192, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
+            const GemmArgs g) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + Cfg::STAGES * Cfg::A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint8_t* sEpi = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + EPI_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + Cfg::STAGES;
   uint64_t* acc_full = bars + 2 * Cfg::STAGES;
@@ -66,6 +71,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
     for (int i = 0; i < Cfg::STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
     fence_barrier_init();
@@ -119,19 +125,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   } else {
     // ---------------- epilogue: warp w owns TMEM lanes 32*(w&3) .. +31  == rows of the tile
     const int q = warp & 3;
+    const bool out_f32 = (g.flags & (CB_EPI_OUT_F32 | CB_EPI_ATOMIC)) != 0;
+    uint8_t* my_slab = sEpi + q * 2 * EPI_SLAB_BYTES;
+    uint32_t slab_i = 0;  // running slab counter of this warp (double buffer)
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int split = tile / (num_m * num_n), mn = tile % (num_m * num_n);
       const int m0 = (mn / num_n) * BM, n0 = (mn % num_n) * BN;
-      const int kb0 = split * kb_per, kb1 = min(kb0 + kb_per, kb_total);
       const int buf = it & 1; const uint32_t aph = (it >> 1) & 1;
       mbar_wait(&acc_full[buf], aph);
       tc_fence_after();
       const int row = m0 + q * 32 + lane;
-      const bool row_ok = row < g.M && kb1 > kb0;
+      const bool row_ok = row < g.M;
       const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + buf * Cfg::ACC_STRIDE;
-      const long out_row = row;
-      const float* pos_row = nullptr; const float* chan_row = nullptr; bool is_cls = false;  // for CLS rows: pos_row = pos0, chan_row = cls_tok
+      const float* pos_row = nullptr; const float* chan_row = nullptr; bool is_cls = false;  // CLS rows: pos_row = pos0, chan_row = cls_tok
       if ((g.flags & CB_EPI_TOKENIZE) && row_ok) {
         int lo = 0, hi = g.nseq;  // largest b with cu[b] <= row
         while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (__ldg(g.cu + mid) <= row) lo = mid; else hi = mid; }
@@ -143,75 +150,97 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (g.chan_tok) chan_row = g.chan_tok + (long)c * g.N;
         }
       }
+      const int n_lim = min(BN, g.N - n0);  // valid columns of this tile (multiple of 8)
 #pragma unroll 1
       for (int c = 0; c < BN; c += 32) {
+        if (c >= n_lim) break;   // warp-uniform
         uint32_t r[32];
         tmem_ld32(t_addr + c, r);
         tmem_ld_wait();
-        if (!row_ok) continue;
+        if (c + 32 >= n_lim) {   // last TMEM read of this tile: release the accumulator buffer early
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        }
+        // ---- slab bookkeeping: bf16 output packs two 32-column chunks into one 128-byte row, fp32 output one chunk
+        const bool new_slab = out_f32 || ((c & 32) == 0);
+        if (new_slab) {
+          if (lane == 0) tma_store_wait_read<1>();   // the buffer we are about to overwrite (2 slabs ago) has been read
+          __syncwarp();
+        }
+        uint8_t* slab = my_slab + (slab_i & 1) * EPI_SLAB_BYTES;
+        uint8_t* srow = slab + lane * 128;
 #pragma unroll
         for (int j8 = 0; j8 < 4; ++j8) {
           const int n = n0 + c + j8 * 8;
-          if (n >= g.N) break;
           float v[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[j] = is_cls ? 0.f : __uint_as_float(r[j8 * 8 + j]) * g.alpha;
-          if (g.bias && split == 0 && !is_cls) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(g.bias + n));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(g.bias + n + 4));
-            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-          }
-          if (pos_row) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(pos_row + n));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(pos_row + n + 4));
-            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-          }
-          if (chan_row) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(chan_row + n));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(chan_row + n + 4));
-            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-          }
-          if (g.flags & CB_EPI_RELU) {
+          if (row_ok && n < g.N) {
+            if (g.bias && split == 0 && !is_cls) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(g.bias + n));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(g.bias + n + 4));
+              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+            }
+            if (pos_row) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(pos_row + n));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(pos_row + n + 4));
+              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+            }
+            if (chan_row) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(chan_row + n));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(chan_row + n + 4));
+              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+            }
+            if (g.flags & CB_EPI_RELU) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
-          }
-          if (g.flags & CB_EPI_RESIDUAL_F32) {
-            const float* rp = reinterpret_cast<const float*>(g.aux) + (long)row * g.ld_aux + n;
-            const float4 r0 = __ldg(reinterpret_cast<const float4*>(rp)), r1 = __ldg(reinterpret_cast<const float4*>(rp + 4));
-            v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w; v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
-          }
-          if (g.flags & (CB_EPI_RESIDUAL | CB_EPI_RELU_MASK)) {
-            const uint4 a = __ldg(reinterpret_cast<const uint4*>(g.aux + (long)row * g.ld_aux + n));
-            const uint32_t au[4] = {a.x, a.y, a.z, a.w};
+              for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            if (g.flags & CB_EPI_RESIDUAL_F32) {
+              const float* rp = reinterpret_cast<const float*>(g.aux) + (long)row * g.ld_aux + n;
+              const float4 r0 = __ldg(reinterpret_cast<const float4*>(rp)), r1 = __ldg(reinterpret_cast<const float4*>(rp + 4));
+              v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w; v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+            }
+            if (g.flags & (CB_EPI_RESIDUAL | CB_EPI_RELU_MASK)) {
+              const uint4 a = __ldg(reinterpret_cast<const uint4*>(g.aux + (long)row * g.ld_aux + n));
+              const uint32_t au[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 f = unpack_bf16(au[j]);
-              if (g.flags & CB_EPI_RESIDUAL) { v[2 * j] += f.x; v[2 * j + 1] += f.y; }
-              else { v[2 * j] = f.x > 0.f ? v[2 * j] : 0.f; v[2 * j + 1] = f.y > 0.f ? v[2 * j + 1] : 0.f; }
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = unpack_bf16(au[j]);
+                if (g.flags & CB_EPI_RESIDUAL) { v[2 * j] += f.x; v[2 * j + 1] += f.y; }
+                else { v[2 * j] = f.x > 0.f ? v[2 * j] : 0.f; v[2 * j + 1] = f.y > 0.f ? v[2 * j + 1] : 0.f; }
+              }
             }
           }
-          if (g.flags & CB_EPI_ATOMIC) {
-            float* dst = reinterpret_cast<float*>(g.C) + out_row * g.ldc + n;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) atomicAdd(dst + j, v[j]);
-          } else if (g.flags & CB_EPI_OUT_F32) {
-            float* dst = reinterpret_cast<float*>(g.C) + out_row * g.ldc + n;
-            *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-            *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+          // ---- stage into the swizzled slab (16-byte chunk index XOR (row & 7): conflict-free, matches SWIZZLE_128B)
+          if (out_f32) {
+            const int k0 = j8 * 2;
+            *reinterpret_cast<float4*>(srow + (((k0) ^ (lane & 7)) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(srow + (((k0 + 1) ^ (lane & 7)) << 4)) = make_float4(v[4], v[5], v[6], v[7]);
           } else {
-            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(g.C) + out_row * g.ldc + n;
-            *reinterpret_cast<uint4*>(dst) =
+            const int k0 = ((c & 32) ? 4 : 0) + j8;
+            *reinterpret_cast<uint4*>(srow + ((k0 ^ (lane & 7)) << 4)) =
                 make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
           }
         }
+        const bool slab_done = out_f32 || (c & 32) || (c + 32 >= n_lim);
+        if (slab_done) {
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            const int col0 = n0 + (out_f32 ? c : (c & ~63));
+            if (g.flags & CB_EPI_ATOMIC) tma_reduce_add_2d(&tmC, slab, col0, m0 + q * 32);
+            else tma_store_2d(&tmC, slab, col0, m0 + q * 32);
+            tma_store_commit();
+          }
+          ++slab_i;
+        }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[buf]);
     }
+    if (lane == 0) tma_store_wait_all<0>();
   }
   tc_fence_before();
   __syncthreads();
@@ -234,7 +263,7 @@ static int encode_operand(CUtensorMap* tm, const void* base, int rows, int K, in
 }
 
 template <int BN, int AMODE, int BMODE>
-static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, cudaStream_t stream) {
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmArgs& g, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -243,28 +272,29 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs
   }
   const int num_tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN) * g.k_splits;
   const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-  gemm_kernel<BN, AMODE, BMODE><<<grid, 192, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, g);
+  gemm_kernel<BN, AMODE, BMODE><<<grid, 192, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, g);
   CB_CUDA(cudaGetLastError());
   return 0;
 }
 
 template <int BN>
-static int dispatch_modes(int am, int bm, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, cudaStream_t s) {
+static int dispatch_modes(int am, int bm, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmArgs& g,
+                          cudaStream_t s) {
   switch (am * 3 + bm) {
-    case 0: return launch<BN, 0, 0>(tmA, tmB, g, s);
-    case 1: return launch<BN, 0, 1>(tmA, tmB, g, s);
-    case 2: return launch<BN, 0, 2>(tmA, tmB, g, s);
-    case 4: return launch<BN, 1, 1>(tmA, tmB, g, s);
-    case 5: return launch<BN, 1, 2>(tmA, tmB, g, s);
-    case 7: return launch<BN, 2, 1>(tmA, tmB, g, s);
-    case 8: return launch<BN, 2, 2>(tmA, tmB, g, s);
+    case 0: return launch<BN, 0, 0>(tmA, tmB, tmC, g, s);
+    case 1: return launch<BN, 0, 1>(tmA, tmB, tmC, g, s);
+    case 2: return launch<BN, 0, 2>(tmA, tmB, tmC, g, s);
+    case 4: return launch<BN, 1, 1>(tmA, tmB, tmC, g, s);
+    case 5: return launch<BN, 1, 2>(tmA, tmB, tmC, g, s);
+    case 7: return launch<BN, 2, 1>(tmA, tmB, tmC, g, s);
+    case 8: return launch<BN, 2, 2>(tmA, tmB, tmC, g, s);
     default: set_error("gemm: unsupported operand layout combination a=%d b=%d", am, bm); return 1;
   }
 }
 
 int gemm_run(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, GemmArgs g, cudaStream_t stream) {
   CB_CHECK(g.M > 0 && g.N > 0 && g.K > 0, "gemm: empty problem M=%d N=%d K=%d", g.M, g.N, g.K);
-  CB_CHECK(g.N % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && g.ldc % 4 == 0, "gemm: N, lda, ldb must be multiples of 8 (N=%d lda=%d ldb=%d)", g.N, lda, ldb);
+  CB_CHECK(g.N % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && g.ldc % 8 == 0, "gemm: N, lda, ldb, ldc must be multiples of 8 (N=%d lda=%d ldb=%d ldc=%d)", g.N, lda, ldb, g.ldc);
   CB_CHECK((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.C) & 15) == 0,
            "gemm: operands must be 16-byte aligned");
   int am = 0, bm = 0;
@@ -275,17 +305,24 @@ int gemm_run(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn,
   const int kb_total = (g.K + BK - 1) / BK;
   if (g.k_splits > kb_total) g.k_splits = kb_total;
   if (g.k_splits > 1) {
-    // every split must own at least one k-block, otherwise its tile would store garbage
+    // every split must own at least one k-block, otherwise its tile would add garbage
     const int kb_per = (kb_total + g.k_splits - 1) / g.k_splits;
     g.k_splits = (kb_total + kb_per - 1) / kb_per;
     CB_CHECK(g.flags & CB_EPI_ATOMIC, "gemm: split-K requires the atomic epilogue");
   }
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmC;
   if (encode_operand(&tmA, A, g.M, g.K, lda, am, BM)) return 1;
   if (encode_operand(&tmB, B, g.N, g.K, ldb, bm, BN)) return 1;
-  if (BN == 192) return dispatch_modes<192>(am, bm, tmA, tmB, g, stream);
-  if (BN == 256) return dispatch_modes<256>(am, bm, tmA, tmB, g, stream);
-  return dispatch_modes<128>(am, bm, tmA, tmB, g, stream);
+  {
+    const bool f32 = (g.flags & (CB_EPI_OUT_F32 | CB_EPI_ATOMIC)) != 0;
+    uint64_t dims[2] = {(uint64_t)g.N, (uint64_t)g.M};
+    uint64_t strides[1] = {(uint64_t)g.ldc * (f32 ? 4 : 2)};
+    uint32_t box[2] = {f32 ? 32u : 64u, 32u};
+    if (make_tmap(&tmC, g.C, 2, dims, strides, box, 3, f32 ? 4 : 2)) return 1;
+  }
+  if (BN == 192) return dispatch_modes<192>(am, bm, tmA, tmB, tmC, g, stream);
+  if (BN == 256) return dispatch_modes<256>(am, bm, tmA, tmB, tmC, g, stream);
+  return dispatch_modes<128>(am, bm, tmA, tmB, tmC, g, stream);
 }
 
 }  // namespace cb
