@@ -1,12 +1,12 @@
 // Persistent, warp-specialised tcgen05 GEMM for sm_100a:  C[M,N] (+)= op(A)[M,K] * op(B)[N,K]^T
 //   * operands bf16, accumulate fp32 in TMEM (double-buffered accumulators: epilogue of tile i overlaps MMA of tile i+1)
 //   * TMA (cp.async.bulk.tensor) loads into 128B/64B-swizzled smem stages, mbarrier full/empty ring
-//   * warp 0 = TMA producer, warp 1 = MMA issuer (single thread), warps 2..5 = epilogue
+//   * warp 0 = TMA producer, warp 1 = MMA issuer (single thread), warps 2..9 = epilogue
 //   * either operand may be K-major ([rows,K] row-major) or MN-major ([K,rows] row-major); the latter is what the
 //     weight-gradient (dW = dY^T X) and input-gradient (dX = dY W) products of the encoder need without transposes
-//   * epilogue: TMEM -> registers (bias, ReLU, residual add, ReLU-mask, tokenizer embeddings) -> 128B-swizzled smem
-//     slab -> TMA store (bf16 / fp32) or TMA reduce-add (fp32 split-K weight gradients): every global write is a
-//     coalesced bulk store, issued per warp (32 rows x 128 B) and double-buffered so it overlaps the next slab
+//   * epilogue (8 warps): TMEM -> registers (bias, ReLU, residual add, ReLU-mask, tokenizer embeddings) -> 128B-swizzled
+//     per-warp smem slab (32 rows x 128 B) -> read back row-wise so every global store / fp32 atomic is a full coalesced
+//     128-byte line (a thread owns a ROW of the accumulator in TMEM, so direct stores would scatter 32 rows per instruction)
 #include "common.cuh"
 #include "chadavit_b200.h"
 #include "internal.h"
@@ -16,7 +16,7 @@ namespace cb {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int EPI_SLAB_BYTES = 32 * 128;            // one warp's slab: 32 rows x 128 B
-constexpr int EPI_BYTES = 4 * 2 * EPI_SLAB_BYTES;   // 4 warps x 2 buffers
+constexpr int EPI_BYTES = 8 * EPI_SLAB_BYTES;       // one staging slab per epilogue warp
 
 template <int BN>
 struct GemmCfg {
@@ -45,10 +45,59 @@ __device__ __forceinline__ void operand_load(void* smem, const CUtensorMap* tm, 
   else tma_load_3d(smem, tm, bar, 0, k0, r0 / 32);
 }
 
+// Per-row epilogue state + the math applied to 8 consecutive output columns of that row.
+struct EpiRow {
+  long row; bool ok, is_cls, add_bias;
+  const float* pos_row; const float* chan_row;
+  __device__ __forceinline__ void init(const GemmArgs& g, int r, bool row_ok, int split) {
+    row = r; ok = row_ok; is_cls = false; pos_row = nullptr; chan_row = nullptr;
+    add_bias = g.bias != nullptr && split == 0;
+    if ((g.flags & CB_EPI_TOKENIZE) && row_ok) {
+      int lo = 0, hi = g.nseq;  // largest b with cu[b] <= row
+      while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (__ldg(g.cu + mid) <= r) lo = mid; else hi = mid; }
+      const int off = r - __ldg(g.cu + lo);
+      if (off == 0) { is_cls = true; add_bias = false; pos_row = g.pos0; chan_row = g.cls_tok; }   // CLS = cls_token + pos_embed[0]
+      else {
+        const int c = (off - 1) / g.npatch, p = (off - 1) - c * g.npatch;
+        pos_row = g.pos + (long)p * g.N;
+        if (g.chan_tok) chan_row = g.chan_tok + (long)c * g.N;
+      }
+    }
+  }
+  __device__ __forceinline__ static void add8(float (&v)[8], const float* p) {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p)), b1 = __ldg(reinterpret_cast<const float4*>(p + 4));
+    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+  }
+  __device__ __forceinline__ void apply(const GemmArgs& g, float (&v)[8], int n) const {
+    if (!ok || n >= g.N) return;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = is_cls ? 0.f : v[j] * g.alpha;
+    if (add_bias) add8(v, g.bias + n);
+    if (pos_row) add8(v, pos_row + n);
+    if (chan_row) add8(v, chan_row + n);
+    if (g.flags & CB_EPI_RELU) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    if (g.flags & CB_EPI_RESIDUAL_F32) add8(v, reinterpret_cast<const float*>(g.aux) + row * g.ld_aux + n);
+    if (g.flags & (CB_EPI_RESIDUAL | CB_EPI_RELU_MASK)) {
+      const uint4 a = __ldg(reinterpret_cast<const uint4*>(g.aux + row * g.ld_aux + n));
+      const uint32_t au[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16(au[j]);
+        if (g.flags & CB_EPI_RESIDUAL) { v[2 * j] += f.x; v[2 * j + 1] += f.y; }
+        else { v[2 * j] = f.x > 0.f ? v[2 * j] : 0.f; v[2 * j + 1] = f.y > 0.f ? v[2 * j + 1] : 0.f; }
+      }
+    }
+  }
+};
+
+constexpr int GEMM_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+
 template <int BN, int AMODE, int BMODE>
-__global__ void __launch_bounds__(192, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
-            const GemmArgs g) {
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -71,9 +120,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    tma_prefetch_desc(&tmC);
     for (int i = 0; i < Cfg::STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -123,11 +171,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     }
   } else {
-    // ---------------- epilogue: warp w owns TMEM lanes 32*(w&3) .. +31  == rows of the tile
+    // ---------------- epilogue: 8 warps; warp w owns TMEM lanes 32*(w&3) .. +31 (rows) and every other column slab
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;           // 0/1: which of the two warps of this lane quarter
     const bool out_f32 = (g.flags & (CB_EPI_OUT_F32 | CB_EPI_ATOMIC)) != 0;
-    uint8_t* my_slab = sEpi + q * 2 * EPI_SLAB_BYTES;
-    uint32_t slab_i = 0;  // running slab counter of this warp (double buffer)
+    const int slab_cols = out_f32 ? 32 : 64;    // one slab = 32 rows x 128 B
+    uint8_t* slab = sEpi + (warp - 2) * EPI_SLAB_BYTES;
+    uint8_t* srow = slab + lane * 128;
+    const int rb_row = lane >> 3, rb_chunk = lane & 7;   // read-back mapping: 8 lanes cover one 128-byte row
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int split = tile / (num_m * num_n), mn = tile % (num_m * num_n);
@@ -138,109 +189,73 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int row = m0 + q * 32 + lane;
       const bool row_ok = row < g.M;
       const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + buf * Cfg::ACC_STRIDE;
-      const float* pos_row = nullptr; const float* chan_row = nullptr; bool is_cls = false;  // CLS rows: pos_row = pos0, chan_row = cls_tok
-      if ((g.flags & CB_EPI_TOKENIZE) && row_ok) {
-        int lo = 0, hi = g.nseq;  // largest b with cu[b] <= row
-        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (__ldg(g.cu + mid) <= row) lo = mid; else hi = mid; }
-        const int off = row - __ldg(g.cu + lo);
-        if (off == 0) { is_cls = true; pos_row = g.pos0; chan_row = g.cls_tok; }
-        else {
-          const int c = (off - 1) / g.npatch, p = (off - 1) - c * g.npatch;
-          pos_row = g.pos + (long)p * g.N;
-          if (g.chan_tok) chan_row = g.chan_tok + (long)c * g.N;
-        }
-      }
+      EpiRow er;
+      er.init(g, row, row_ok, split);
       const int n_lim = min(BN, g.N - n0);  // valid columns of this tile (multiple of 8)
+      const int n_slabs = (n_lim + slab_cols - 1) / slab_cols;
+      const int last_slab = ((n_slabs - 1 - half) >= 0) ? (n_slabs - 1 - ((n_slabs - 1 - half) & 1)) : -1;  // last slab of this warp
+      if (last_slab < 0) {   // nothing to do for this warp in this tile: still release the accumulator
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        continue;
+      }
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        if (c >= n_lim) break;   // warp-uniform
-        uint32_t r[32];
-        tmem_ld32(t_addr + c, r);
-        tmem_ld_wait();
-        if (c + 32 >= n_lim) {   // last TMEM read of this tile: release the accumulator buffer early
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty[buf]);
-        }
-        // ---- slab bookkeeping: bf16 output packs two 32-column chunks into one 128-byte row, fp32 output one chunk
-        const bool new_slab = out_f32 || ((c & 32) == 0);
-        if (new_slab) {
-          if (lane == 0) tma_store_wait_read<1>();   // the buffer we are about to overwrite (2 slabs ago) has been read
-          __syncwarp();
-        }
-        uint8_t* slab = my_slab + (slab_i & 1) * EPI_SLAB_BYTES;
-        uint8_t* srow = slab + lane * 128;
+      for (int sl = half; sl < n_slabs; sl += 2) {
+        const int c = sl * slab_cols;
+        if (out_f32) {
+          uint32_t r[32];
+          tmem_ld32(t_addr + c, r);
+          tmem_ld_wait();
+          if (sl == last_slab) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&acc_empty[buf]); }
 #pragma unroll
-        for (int j8 = 0; j8 < 4; ++j8) {
-          const int n = n0 + c + j8 * 8;
-          float v[8];
+          for (int j8 = 0; j8 < 4; ++j8) {
+            float v[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = is_cls ? 0.f : __uint_as_float(r[j8 * 8 + j]) * g.alpha;
-          if (row_ok && n < g.N) {
-            if (g.bias && split == 0 && !is_cls) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(g.bias + n));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(g.bias + n + 4));
-              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-            }
-            if (pos_row) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(pos_row + n));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(pos_row + n + 4));
-              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-            }
-            if (chan_row) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(chan_row + n));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(chan_row + n + 4));
-              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-            }
-            if (g.flags & CB_EPI_RELU) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
-            }
-            if (g.flags & CB_EPI_RESIDUAL_F32) {
-              const float* rp = reinterpret_cast<const float*>(g.aux) + (long)row * g.ld_aux + n;
-              const float4 r0 = __ldg(reinterpret_cast<const float4*>(rp)), r1 = __ldg(reinterpret_cast<const float4*>(rp + 4));
-              v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w; v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
-            }
-            if (g.flags & (CB_EPI_RESIDUAL | CB_EPI_RELU_MASK)) {
-              const uint4 a = __ldg(reinterpret_cast<const uint4*>(g.aux + (long)row * g.ld_aux + n));
-              const uint32_t au[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 f = unpack_bf16(au[j]);
-                if (g.flags & CB_EPI_RESIDUAL) { v[2 * j] += f.x; v[2 * j + 1] += f.y; }
-                else { v[2 * j] = f.x > 0.f ? v[2 * j] : 0.f; v[2 * j + 1] = f.y > 0.f ? v[2 * j + 1] : 0.f; }
-              }
-            }
+            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j8 * 8 + j]);
+            er.apply(g, v, n0 + c + j8 * 8);
+            *reinterpret_cast<float4*>(srow + (((j8 * 2) ^ (lane & 7)) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(srow + (((j8 * 2 + 1) ^ (lane & 7)) << 4)) = make_float4(v[4], v[5], v[6], v[7]);
           }
-          // ---- stage into the swizzled slab (16-byte chunk index XOR (row & 7): conflict-free, matches SWIZZLE_128B)
-          if (out_f32) {
-            const int k0 = j8 * 2;
-            *reinterpret_cast<float4*>(srow + (((k0) ^ (lane & 7)) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
-            *reinterpret_cast<float4*>(srow + (((k0 + 1) ^ (lane & 7)) << 4)) = make_float4(v[4], v[5], v[6], v[7]);
-          } else {
-            const int k0 = ((c & 32) ? 4 : 0) + j8;
-            *reinterpret_cast<uint4*>(srow + ((k0 ^ (lane & 7)) << 4)) =
+        } else {
+          uint32_t r0[32], r1[32];
+          tmem_ld32(t_addr + c, r0);
+          if (c + 32 < n_lim) tmem_ld32(t_addr + c + 32, r1);
+          tmem_ld_wait();
+          if (sl == last_slab) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&acc_empty[buf]); }
+#pragma unroll
+          for (int j8 = 0; j8 < 8; ++j8) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(j8 < 4 ? r0[j8 * 8 + j] : r1[(j8 - 4) * 8 + j]);
+            er.apply(g, v, n0 + c + j8 * 8);
+            *reinterpret_cast<uint4*>(srow + ((j8 ^ (lane & 7)) << 4)) =
                 make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
           }
         }
-        const bool slab_done = out_f32 || (c & 32) || (c + 32 >= n_lim);
-        if (slab_done) {
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) {
-            const int col0 = n0 + (out_f32 ? c : (c & ~63));
-            if (g.flags & CB_EPI_ATOMIC) tma_reduce_add_2d(&tmC, slab, col0, m0 + q * 32);
-            else tma_store_2d(&tmC, slab, col0, m0 + q * 32);
-            tma_store_commit();
+        __syncwarp();
+        // ---- coalesced read-back: each instruction moves 4 full 128-byte rows
+        const int gcol = n0 + c + rb_chunk * (out_f32 ? 4 : 8);
+        const bool col_ok = gcol < g.N;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rl = i * 4 + rb_row;
+          const long grow = (long)m0 + q * 32 + rl;
+          const uint4 val = *reinterpret_cast<const uint4*>(slab + rl * 128 + ((rb_chunk ^ (rl & 7)) << 4));
+          if (grow < g.M && col_ok) {
+            if (g.flags & CB_EPI_ATOMIC) {
+              atomicAdd(reinterpret_cast<float4*>(reinterpret_cast<float*>(g.C) + grow * g.ldc + gcol),
+                        make_float4(__uint_as_float(val.x), __uint_as_float(val.y), __uint_as_float(val.z), __uint_as_float(val.w)));
+            } else if (out_f32) {
+              *reinterpret_cast<uint4*>(reinterpret_cast<float*>(g.C) + grow * g.ldc + gcol) = val;
+            } else {
+              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(g.C) + grow * g.ldc + gcol) = val;
+            }
           }
-          ++slab_i;
         }
+        __syncwarp();
       }
     }
-    if (lane == 0) tma_store_wait_all<0>();
   }
   tc_fence_before();
   __syncthreads();
@@ -263,7 +278,7 @@ static int encode_operand(CUtensorMap* tm, const void* base, int rows, int K, in
 }
 
 template <int BN, int AMODE, int BMODE>
-static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmArgs& g, cudaStream_t stream) {
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -272,22 +287,21 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
   }
   const int num_tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN) * g.k_splits;
   const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-  gemm_kernel<BN, AMODE, BMODE><<<grid, 192, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, g);
+  gemm_kernel<BN, AMODE, BMODE><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, g);
   CB_CUDA(cudaGetLastError());
   return 0;
 }
 
 template <int BN>
-static int dispatch_modes(int am, int bm, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmArgs& g,
-                          cudaStream_t s) {
+static int dispatch_modes(int am, int bm, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, cudaStream_t s) {
   switch (am * 3 + bm) {
-    case 0: return launch<BN, 0, 0>(tmA, tmB, tmC, g, s);
-    case 1: return launch<BN, 0, 1>(tmA, tmB, tmC, g, s);
-    case 2: return launch<BN, 0, 2>(tmA, tmB, tmC, g, s);
-    case 4: return launch<BN, 1, 1>(tmA, tmB, tmC, g, s);
-    case 5: return launch<BN, 1, 2>(tmA, tmB, tmC, g, s);
-    case 7: return launch<BN, 2, 1>(tmA, tmB, tmC, g, s);
-    case 8: return launch<BN, 2, 2>(tmA, tmB, tmC, g, s);
+    case 0: return launch<BN, 0, 0>(tmA, tmB, g, s);
+    case 1: return launch<BN, 0, 1>(tmA, tmB, g, s);
+    case 2: return launch<BN, 0, 2>(tmA, tmB, g, s);
+    case 4: return launch<BN, 1, 1>(tmA, tmB, g, s);
+    case 5: return launch<BN, 1, 2>(tmA, tmB, g, s);
+    case 7: return launch<BN, 2, 1>(tmA, tmB, g, s);
+    case 8: return launch<BN, 2, 2>(tmA, tmB, g, s);
     default: set_error("gemm: unsupported operand layout combination a=%d b=%d", am, bm); return 1;
   }
 }
@@ -310,19 +324,12 @@ int gemm_run(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn,
     g.k_splits = (kb_total + kb_per - 1) / kb_per;
     CB_CHECK(g.flags & CB_EPI_ATOMIC, "gemm: split-K requires the atomic epilogue");
   }
-  CUtensorMap tmA, tmB, tmC;
+  CUtensorMap tmA, tmB;
   if (encode_operand(&tmA, A, g.M, g.K, lda, am, BM)) return 1;
   if (encode_operand(&tmB, B, g.N, g.K, ldb, bm, BN)) return 1;
-  {
-    const bool f32 = (g.flags & (CB_EPI_OUT_F32 | CB_EPI_ATOMIC)) != 0;
-    uint64_t dims[2] = {(uint64_t)g.N, (uint64_t)g.M};
-    uint64_t strides[1] = {(uint64_t)g.ldc * (f32 ? 4 : 2)};
-    uint32_t box[2] = {f32 ? 32u : 64u, 32u};
-    if (make_tmap(&tmC, g.C, 2, dims, strides, box, 3, f32 ? 4 : 2)) return 1;
-  }
-  if (BN == 192) return dispatch_modes<192>(am, bm, tmA, tmB, tmC, g, stream);
-  if (BN == 256) return dispatch_modes<256>(am, bm, tmA, tmB, tmC, g, stream);
-  return dispatch_modes<128>(am, bm, tmA, tmB, tmC, g, stream);
+  if (BN == 192) return dispatch_modes<192>(am, bm, tmA, tmB, g, stream);
+  if (BN == 256) return dispatch_modes<256>(am, bm, tmA, tmB, g, stream);
+  return dispatch_modes<128>(am, bm, tmA, tmB, g, stream);
 }
 
 }  // namespace cb

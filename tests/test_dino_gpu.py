@@ -128,8 +128,8 @@ def test_dino_step_matches_reference_and_fused_path():
         return m
 
     model, fused = build(), build()
-    crops = [torch.from_numpy(det.det_pixels(sum(counts), 224, 224, s)).cuda() for s in sd["g"]] + \
-            [torch.from_numpy(det.det_pixels(sum(counts), 96, 96, s)).cuda() for s in sd["l"]]
+    crops = [torch.from_numpy(det.det_pixels(sum(counts), 224, 224, s_)).cuda() for s_ in sd["g"]] + \
+            [torch.from_numpy(det.det_pixels(sum(counts), 96, 96, s_)).cuda() for s_ in sd["l"]]
     batch = (crops, None, [counts] * 4)
     # ---- autograd drop-in path
     loss = model.training_step(batch)

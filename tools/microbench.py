@@ -1,0 +1,108 @@
+#!/usr/bin/env python
+"""Per-kernel microbenchmarks at the shapes of one moyen/16 global-crop pass (T ~ 68.7k tokens, D=192, F=2048).
+
+    python tools/microbench.py [--tokens 68664]
+
+Each op is timed alone with CUDA events (10 warm-ups, 30 reps, buffers >> L2 are rotated for HBM-bound ops);
+prints us, TFLOP/s and algorithmic GB/s so the GEMM/attention/row-wise kernels can be compared with the roofline."""
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from chadavit_b200 import ops  # noqa: E402
+
+bf16 = torch.bfloat16
+
+
+def timeit(fn, reps=30, warm=10):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e3  # us
+
+
+def report(name, us, flops=0.0, bytes_=0.0):
+    print(f"{name:46s} {us:9.1f} us  {flops / us / 1e6:8.1f} TFLOP/s  {bytes_ / us / 1e3:8.1f} GB/s")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--tokens", type=int, default=68664)
+    a = ap.parse_args()
+    T, D, F = a.tokens, 192, 2048
+    dev = "cuda"
+    r = lambda *s: (torch.randn(*s, device=dev) * 0.5).to(bf16)  # noqa: E731
+    x16, w_in, w_o, w1, w2 = r(T, D), r(3 * D, D), r(D, D), r(F, D), r(D, F)
+    hid, qkv = r(T, F), r(T, 3 * D)
+    x32 = torch.randn(T, D, device=dev)
+    b_in, b_o, b1, b2 = (torch.randn(n, device=dev) for n in (3 * D, D, F, D))
+    R = ops.EPI_RESIDUAL_F32 | ops.EPI_OUT_F32
+    print(f"# T={T} D={D} F={F}")
+    # ---- forward GEMMs
+    o = torch.empty(T, 3 * D, device=dev, dtype=bf16)
+    report("qkv   [T,192]x[192,576] +bias -> bf16", timeit(lambda: ops.gemm(x16, w_in, bias=b_in, out=o)), 2.0 * T * D * 3 * D, T * (D + 3 * D) * 2)
+    o = torch.empty(T, D, device=dev)
+    report("proj  [T,192]x[192,192] +bias +res32 -> f32", timeit(lambda: ops.gemm(x16, w_o, bias=b_o, aux=x32, flags=R, out=o)), 2.0 * T * D * D, T * D * (2 + 4 + 4))
+    o = torch.empty(T, F, device=dev, dtype=bf16)
+    report("fc1   [T,192]x[192,2048] +bias relu -> bf16", timeit(lambda: ops.gemm(x16, w1, bias=b1, flags=ops.EPI_RELU, out=o)), 2.0 * T * D * F, T * (D + F) * 2)
+    o = torch.empty(T, D, device=dev)
+    report("fc2   [T,2048]x[2048,192] +bias +res32 -> f32", timeit(lambda: ops.gemm(hid, w2, bias=b2, aux=x32, flags=R, out=o)), 2.0 * T * D * F, T * (F * 2 + D * 8))
+    # ---- backward GEMMs
+    o = torch.empty(T, F, device=dev, dtype=bf16)
+    report("dh    [T,192]x[192,2048] (W2 MN) relu-mask", timeit(lambda: ops.gemm(x16, w2, b_mn=True, aux=hid, flags=ops.EPI_RELU_MASK, out=o)), 2.0 * T * D * F, T * (D + 2 * F) * 2)
+    o = torch.empty(T, D, device=dev)
+    report("dy    [T,2048]x[2048,192] (W1 MN) +res32 -> f32", timeit(lambda: ops.gemm(hid, w1, b_mn=True, aux=x32, flags=R, out=o)), 2.0 * T * D * F, T * (F * 2 + D * 8))
+    o = torch.empty(T, D, device=dev)
+    report("du    [T,576]x[576,192] (Win MN) -> f32", timeit(lambda: ops.gemm(qkv, w_in, b_mn=True, flags=ops.EPI_OUT_F32, out=o)), 2.0 * T * D * 3 * D, T * (3 * D * 2 + D * 4))
+    g = torch.zeros(D, F, device=dev)
+    ks = ops.splitk_for(T, 2 * 8)
+    report(f"dW2   [192,T]x[T,2048] split-K {ks} atomic", timeit(lambda: ops.gemm(x16, hid, a_mn=True, b_mn=True, flags=ops.EPI_ATOMIC, out=g, k_splits=ks)), 2.0 * T * D * F, T * (D + F) * 2)
+    g = torch.zeros(F, D, device=dev)
+    ks = ops.splitk_for(T, 16 * 2)
+    report(f"dW1   [2048,T]x[T,192] split-K {ks} atomic", timeit(lambda: ops.gemm(hid, x16, a_mn=True, b_mn=True, flags=ops.EPI_ATOMIC, out=g, k_splits=ks)), 2.0 * T * D * F, T * (D + F) * 2)
+    g = torch.zeros(3 * D, D, device=dev)
+    ks = ops.splitk_for(T, 5 * 2)
+    report(f"dWin  [576,T]x[T,192] split-K {ks} atomic", timeit(lambda: ops.gemm(qkv, x16, a_mn=True, b_mn=True, flags=ops.EPI_ATOMIC, out=g, k_splits=ks)), 2.0 * T * D * 3 * D, T * 4 * D * 2)
+    # ---- attention (ragged U{1..10} batch of 64 at 224^2 like bench.py)
+    counts = np.random.RandomState(1234).randint(1, 11, size=64).tolist()
+    lay = ops.PackedLayout(counts, 196, dev)
+    qkv2 = r(lay.T, 3 * D)
+    do = r(lay.T, D)
+    out, lse = ops.attn_fwd(qkv2, lay, 2)
+    report(f"attn fwd  T={lay.T} H=2 d=96", timeit(lambda: ops.attn_fwd(qkv2, lay, 2)), 4.0 * D * lay.sum_sq, lay.T * 4 * D * 2)
+    report(f"attn bwd  T={lay.T} H=2 d=96", timeit(lambda: ops.attn_bwd(do, qkv2, out, lse, lay, 2)), 10.0 * D * lay.sum_sq, lay.T * 9 * D * 2)
+    lay10 = ops.PackedLayout([10] * 32, 196, dev)
+    qkv3 = r(lay10.T, 3 * D)
+    do3 = r(lay10.T, D)
+    out3, lse3 = ops.attn_fwd(qkv3, lay10, 2)
+    report(f"attn fwd  32 x 1961 tokens H=2 d=96", timeit(lambda: ops.attn_fwd(qkv3, lay10, 2)), 4.0 * D * lay10.sum_sq)
+    report(f"attn bwd  32 x 1961 tokens H=2 d=96", timeit(lambda: ops.attn_bwd(do3, qkv3, out3, lse3, lay10, 2)), 10.0 * D * lay10.sum_sq)
+    # ---- row-wise
+    gam, bet = torch.ones(D, device=dev), torch.zeros(D, device=dev)
+    report("layernorm fwd f32 -> bf16+f32", timeit(lambda: ops.layernorm_fwd(x32, gam, bet, 1e-5, out_f32=True)), 0, T * D * (4 + 2 + 4))
+    _, _, mean, rstd = ops.layernorm_fwd(x32, gam, bet, 1e-5)
+    dg, db, dc = (torch.zeros(D, device=dev) for _ in range(3))
+    report("layernorm bwd f32 (+dres) -> f32+bf16", timeit(lambda: ops.layernorm_bwd(x32, x32, gam, mean, rstd, dgamma=dg, dbeta=db, dcolsum=dc, dres=x32, want_bf16=True)), 0, T * D * (4 * 3 + 4 + 2))
+    acc = torch.zeros(F, device=dev)
+    report("colsum bf16 [T,2048]", timeit(lambda: ops.colsum(hid, acc)), 0, T * F * 2)
+    acc = torch.zeros(3 * D, device=dev)
+    report("colsum bf16 [T,576]", timeit(lambda: ops.colsum(qkv, acc)), 0, T * 3 * D * 2)
+    n = 17_510_464
+    p, gr, m, v, t = (torch.randn(n, device=dev) for _ in range(5))
+    p16, t16 = torch.empty(n, device=dev, dtype=bf16), torch.empty(n, device=dev, dtype=bf16)
+    report("adamw+ema+bf16 shadows 17.5M params", timeit(lambda: ops.adamw_step(p, gr, m, v, lr=1e-3, step=3, p_bf16=p16, teacher=t, teacher_bf16=t16, tau=0.99)), 0, n * 44.0)
+    report("ema only 17.5M params (12 B/param)", timeit(lambda: ops.ema_update(t, p, 0.99)), 0, n * 12.0)
+
+
+if __name__ == "__main__":
+    main()
