@@ -45,54 +45,6 @@ __device__ __forceinline__ void operand_load(void* smem, const CUtensorMap* tm, 
   else tma_load_3d(smem, tm, bar, 0, k0, r0 / 32);
 }
 
-// Per-row epilogue state + the math applied to 8 consecutive output columns of that row.
-struct EpiRow {
-  long row; bool ok, is_cls, add_bias;
-  const float* pos_row; const float* chan_row;
-  __device__ __forceinline__ void init(const GemmArgs& g, int r, bool row_ok, int split) {
-    row = r; ok = row_ok; is_cls = false; pos_row = nullptr; chan_row = nullptr;
-    add_bias = g.bias != nullptr && split == 0;
-    if ((g.flags & CB_EPI_TOKENIZE) && row_ok) {
-      int lo = 0, hi = g.nseq;  // largest b with cu[b] <= row
-      while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (__ldg(g.cu + mid) <= r) lo = mid; else hi = mid; }
-      const int off = r - __ldg(g.cu + lo);
-      if (off == 0) { is_cls = true; add_bias = false; pos_row = g.pos0; chan_row = g.cls_tok; }   // CLS = cls_token + pos_embed[0]
-      else {
-        const int c = (off - 1) / g.npatch, p = (off - 1) - c * g.npatch;
-        pos_row = g.pos + (long)p * g.N;
-        if (g.chan_tok) chan_row = g.chan_tok + (long)c * g.N;
-      }
-    }
-  }
-  __device__ __forceinline__ static void add8(float (&v)[8], const float* p) {
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p)), b1 = __ldg(reinterpret_cast<const float4*>(p + 4));
-    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-  }
-  __device__ __forceinline__ void apply(const GemmArgs& g, float (&v)[8], int n) const {
-    if (!ok || n >= g.N) return;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = is_cls ? 0.f : v[j] * g.alpha;
-    if (add_bias) add8(v, g.bias + n);
-    if (pos_row) add8(v, pos_row + n);
-    if (chan_row) add8(v, chan_row + n);
-    if (g.flags & CB_EPI_RELU) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
-    }
-    if (g.flags & CB_EPI_RESIDUAL_F32) add8(v, reinterpret_cast<const float*>(g.aux) + row * g.ld_aux + n);
-    if (g.flags & (CB_EPI_RESIDUAL | CB_EPI_RELU_MASK)) {
-      const uint4 a = __ldg(reinterpret_cast<const uint4*>(g.aux + row * g.ld_aux + n));
-      const uint32_t au[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = unpack_bf16(au[j]);
-        if (g.flags & CB_EPI_RESIDUAL) { v[2 * j] += f.x; v[2 * j + 1] += f.y; }
-        else { v[2 * j] = f.x > 0.f ? v[2 * j] : 0.f; v[2 * j + 1] = f.y > 0.f ? v[2 * j + 1] : 0.f; }
-      }
-    }
-  }
-};
-
 constexpr int GEMM_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 
 template <int BN, int AMODE, int BMODE>
@@ -171,29 +123,41 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     }
   } else {
-    // ---------------- epilogue: 8 warps; warp w owns TMEM lanes 32*(w&3) .. +31 (rows) and every other column slab
+    // ---------------- epilogue: 8 warps; warp w owns TMEM lanes 32*(w&3) .. +31 (rows) and every other 32-column slab.
+    // Raw fp32 accumulators are staged in a swizzled smem slab (thread = row), then read back row-wise (8 lanes = one
+    // 128-byte row) where ALL epilogue math happens, so bias / residual / mask reads and every store are coalesced and
+    // the per-column vectors are loaded once per slab (the L1 is ~3 KB next to 225 KB of smem: scalar __ldg's would all
+    // be serialised L2 round trips).
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;           // 0/1: which of the two warps of this lane quarter
+    const int ew = warp - 2;                     // 0..7
+    const int half = ew >> 2;                    // which of the two warps of this lane quarter
     const bool out_f32 = (g.flags & (CB_EPI_OUT_F32 | CB_EPI_ATOMIC)) != 0;
-    const int slab_cols = out_f32 ? 32 : 64;    // one slab = 32 rows x 128 B
-    uint8_t* slab = sEpi + (warp - 2) * EPI_SLAB_BYTES;
+    uint8_t* slab = sEpi + ew * EPI_SLAB_BYTES;
     uint8_t* srow = slab + lane * 128;
-    const int rb_row = lane >> 3, rb_chunk = lane & 7;   // read-back mapping: 8 lanes cover one 128-byte row
+    const int rb_row = lane >> 3, rb_chunk = lane & 7;   // read-back mapping: 8 lanes cover one 128-byte row (4 columns each)
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int split = tile / (num_m * num_n), mn = tile % (num_m * num_n);
       const int m0 = (mn / num_n) * BM, n0 = (mn % num_n) * BN;
       const int buf = it & 1; const uint32_t aph = (it >> 1) & 1;
+      const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + buf * Cfg::ACC_STRIDE;
+      const int n_lim = min(BN, g.N - n0);  // valid columns of this tile (multiple of 8)
+      const int n_slabs = (n_lim + 31) / 32;
+      const int last_slab = ((n_slabs - 1 - half) >= 0) ? (n_slabs - 1 - ((n_slabs - 1 - half) & 1)) : -1;  // last slab of this warp
+      int2 ri = make_int2(-1, -1);   // tokenizer: this lane's row -> {pos row offset, chan row offset}; shuffled in the read-back
+      if (g.flags & CB_EPI_TOKENIZE) {
+        // row t of sequence b: off = t - cu[b]; off == 0 -> CLS row (cls_token + pos_embed[0]), else patch p of channel c
+        const int row = m0 + q * 32 + lane;
+        if (row < g.M) {
+          int lo = 0, hi = g.nseq;  // largest b with cu[b] <= row
+          while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (__ldg(g.cu + mid) <= row) lo = mid; else hi = mid; }
+          const int off = row - __ldg(g.cu + lo);
+          if (off == 0) ri = make_int2(-2, -2);
+          else { const int c = (off - 1) / g.npatch; ri = make_int2(((off - 1) - c * g.npatch) * g.N, g.chan_tok ? c * g.N : -1); }
+        }
+      }
       mbar_wait(&acc_full[buf], aph);
       tc_fence_after();
-      const int row = m0 + q * 32 + lane;
-      const bool row_ok = row < g.M;
-      const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + buf * Cfg::ACC_STRIDE;
-      EpiRow er;
-      er.init(g, row, row_ok, split);
-      const int n_lim = min(BN, g.N - n0);  // valid columns of this tile (multiple of 8)
-      const int n_slabs = (n_lim + slab_cols - 1) / slab_cols;
-      const int last_slab = ((n_slabs - 1 - half) >= 0) ? (n_slabs - 1 - ((n_slabs - 1 - half) & 1)) : -1;  // last slab of this warp
       if (last_slab < 0) {   // nothing to do for this warp in this tile: still release the accumulator
         tc_fence_before();
         __syncwarp();
@@ -202,58 +166,90 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
 #pragma unroll 1
       for (int sl = half; sl < n_slabs; sl += 2) {
-        const int c = sl * slab_cols;
-        if (out_f32) {
+        const int c = sl * 32;
+        {
           uint32_t r[32];
           tmem_ld32(t_addr + c, r);
           tmem_ld_wait();
           if (sl == last_slab) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&acc_empty[buf]); }
 #pragma unroll
-          for (int j8 = 0; j8 < 4; ++j8) {
-            float v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j8 * 8 + j]);
-            er.apply(g, v, n0 + c + j8 * 8);
-            *reinterpret_cast<float4*>(srow + (((j8 * 2) ^ (lane & 7)) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
-            *reinterpret_cast<float4*>(srow + (((j8 * 2 + 1) ^ (lane & 7)) << 4)) = make_float4(v[4], v[5], v[6], v[7]);
-          }
-        } else {
-          uint32_t r0[32], r1[32];
-          tmem_ld32(t_addr + c, r0);
-          if (c + 32 < n_lim) tmem_ld32(t_addr + c + 32, r1);
-          tmem_ld_wait();
-          if (sl == last_slab) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&acc_empty[buf]); }
-#pragma unroll
-          for (int j8 = 0; j8 < 8; ++j8) {
-            float v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(j8 < 4 ? r0[j8 * 8 + j] : r1[(j8 - 4) * 8 + j]);
-            er.apply(g, v, n0 + c + j8 * 8);
-            *reinterpret_cast<uint4*>(srow + ((j8 ^ (lane & 7)) << 4)) =
-                make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-          }
+          for (int k = 0; k < 8; ++k)
+            *reinterpret_cast<uint4*>(srow + ((k ^ (lane & 7)) << 4)) = make_uint4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
         }
         __syncwarp();
-        // ---- coalesced read-back: each instruction moves 4 full 128-byte rows
-        const int gcol = n0 + c + rb_chunk * (out_f32 ? 4 : 8);
+        // ---- read-back + epilogue math: this lane owns columns gcol..gcol+3 of rows rb_row, rb_row+4, ...
+        const int gcol = n0 + c + rb_chunk * 4;
         const bool col_ok = gcol < g.N;
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g.bias && split == 0 && col_ok) bias4 = __ldg(reinterpret_cast<const float4*>(g.bias + gcol));
+        float4 acc[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int rl = i * 4 + rb_row;
-          const long grow = (long)m0 + q * 32 + rl;
-          const uint4 val = *reinterpret_cast<const uint4*>(slab + rl * 128 + ((rb_chunk ^ (rl & 7)) << 4));
-          if (grow < g.M && col_ok) {
-            if (g.flags & CB_EPI_ATOMIC) {
-              atomicAdd(reinterpret_cast<float4*>(reinterpret_cast<float*>(g.C) + grow * g.ldc + gcol),
-                        make_float4(__uint_as_float(val.x), __uint_as_float(val.y), __uint_as_float(val.z), __uint_as_float(val.w)));
-            } else if (out_f32) {
-              *reinterpret_cast<uint4*>(reinterpret_cast<float*>(g.C) + grow * g.ldc + gcol) = val;
-            } else {
-              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(g.C) + grow * g.ldc + gcol) = val;
-            }
+          acc[i] = *reinterpret_cast<const float4*>(slab + rl * 128 + ((rb_chunk ^ (rl & 7)) << 4));
+        }
+        __syncwarp();   // slab may be overwritten by the next iteration from here on
+        int2 rinfo[8];
+        if (g.flags & CB_EPI_TOKENIZE) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            rinfo[i].x = __shfl_sync(0xffffffffu, ri.x, i * 4 + rb_row);
+            rinfo[i].y = __shfl_sync(0xffffffffu, ri.y, i * 4 + rb_row);
           }
         }
-        __syncwarp();
+        if (col_ok) {
+          float4 res[8];
+          uint2 aux16[8];
+          if (g.flags & CB_EPI_RESIDUAL_F32) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const long grow = (long)m0 + q * 32 + i * 4 + rb_row;
+              res[i] = grow < g.M ? __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(g.aux) + grow * g.ld_aux + gcol))
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+          if (g.flags & (CB_EPI_RESIDUAL | CB_EPI_RELU_MASK)) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const long grow = (long)m0 + q * 32 + i * 4 + rb_row;
+              aux16[i] = grow < g.M ? __ldg(reinterpret_cast<const uint2*>(g.aux + grow * g.ld_aux + gcol)) : make_uint2(0u, 0u);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rl = i * 4 + rb_row;
+            const long grow = (long)m0 + q * 32 + rl;
+            if (grow >= g.M) continue;
+            float4 v = acc[i];
+            v.x *= g.alpha; v.y *= g.alpha; v.z *= g.alpha; v.w *= g.alpha;
+            if (g.flags & CB_EPI_TOKENIZE) {
+              const int2 rr = rinfo[i];
+              if (rr.x == -2) {   // CLS row: cls_token + pos_embed[0] (no conv bias)
+                const float4 a4 = __ldg(reinterpret_cast<const float4*>(g.cls_tok + gcol)), b4 = __ldg(reinterpret_cast<const float4*>(g.pos0 + gcol));
+                v = make_float4(a4.x + b4.x, a4.y + b4.y, a4.z + b4.z, a4.w + b4.w);
+              } else {
+                const float4 p4 = __ldg(reinterpret_cast<const float4*>(g.pos + rr.x + gcol));
+                v.x += bias4.x + p4.x; v.y += bias4.y + p4.y; v.z += bias4.z + p4.z; v.w += bias4.w + p4.w;
+                if (rr.y >= 0) {
+                  const float4 c4 = __ldg(reinterpret_cast<const float4*>(g.chan_tok + rr.y + gcol));
+                  v.x += c4.x; v.y += c4.y; v.z += c4.z; v.w += c4.w;
+                }
+              }
+            } else {
+              v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
+            }
+            if (g.flags & CB_EPI_RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+            if (g.flags & CB_EPI_RESIDUAL_F32) { v.x += res[i].x; v.y += res[i].y; v.z += res[i].z; v.w += res[i].w; }
+            if (g.flags & (CB_EPI_RESIDUAL | CB_EPI_RELU_MASK)) {
+              const float2 f0 = unpack_bf16(aux16[i].x), f1 = unpack_bf16(aux16[i].y);
+              if (g.flags & CB_EPI_RESIDUAL) { v.x += f0.x; v.y += f0.y; v.z += f1.x; v.w += f1.y; }
+              else { v.x = f0.x > 0.f ? v.x : 0.f; v.y = f0.y > 0.f ? v.y : 0.f; v.z = f1.x > 0.f ? v.z : 0.f; v.w = f1.y > 0.f ? v.w : 0.f; }
+            }
+            if (g.flags & CB_EPI_ATOMIC) atomicAdd(reinterpret_cast<float4*>(reinterpret_cast<float*>(g.C) + grow * g.ldc + gcol), v);
+            else if (out_f32) *reinterpret_cast<float4*>(reinterpret_cast<float*>(g.C) + grow * g.ldc + gcol) = v;
+            else *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.C) + grow * g.ldc + gcol) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+          }
+        }
       }
     }
   }
