@@ -45,6 +45,8 @@ __device__ __forceinline__ void operand_load(void* smem, const CUtensorMap* tm, 
   else tma_load_3d(smem, tm, bar, 0, k0, r0 / 32);
 }
 
+enum EpiMode { EM_BF16 = 0, EM_BF16_MASK = 1, EM_F32 = 2, EM_ATOMIC = 3, EM_TOKENIZE = 4 };
+
 constexpr int GEMM_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 
 template <int BN, int AMODE, int BMODE>
@@ -131,7 +133,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int q = warp & 3;
     const int ew = warp - 2;                     // 0..7
     const int half = ew >> 2;                    // which of the two warps of this lane quarter
-    const bool out_f32 = (g.flags & (CB_EPI_OUT_F32 | CB_EPI_ATOMIC)) != 0;
+    const int mode = (g.flags & CB_EPI_TOKENIZE) ? EM_TOKENIZE : (g.flags & CB_EPI_ATOMIC) ? EM_ATOMIC : (g.flags & CB_EPI_OUT_F32) ? EM_F32
+                     : (g.flags & CB_EPI_RELU_MASK) ? EM_BF16_MASK : EM_BF16;
     uint8_t* slab = sEpi + ew * EPI_SLAB_BYTES;
     uint8_t* srow = slab + lane * 128;
     const int rb_row = lane >> 3, rb_chunk = lane & 7;   // read-back mapping: 8 lanes cover one 128-byte row (4 columns each)
@@ -178,10 +181,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         __syncwarp();
         // ---- read-back + epilogue math: this lane owns columns gcol..gcol+3 of rows rb_row, rb_row+4, ...
+        // One lean, branch-free loop per epilogue mode (the mode is uniform for the launch).
         const int gcol = n0 + c + rb_chunk * 4;
         const bool col_ok = gcol < g.N;
-        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (g.bias && split == 0 && col_ok) bias4 = __ldg(reinterpret_cast<const float4*>(g.bias + gcol));
         float4 acc[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -189,65 +191,91 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           acc[i] = *reinterpret_cast<const float4*>(slab + rl * 128 + ((rb_chunk ^ (rl & 7)) << 4));
         }
         __syncwarp();   // slab may be overwritten by the next iteration from here on
-        int2 rinfo[8];
-        if (g.flags & CB_EPI_TOKENIZE) {
+        if (g.alpha != 1.f) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            rinfo[i].x = __shfl_sync(0xffffffffu, ri.x, i * 4 + rb_row);
-            rinfo[i].y = __shfl_sync(0xffffffffu, ri.y, i * 4 + rb_row);
-          }
+          for (int i = 0; i < 8; ++i) { acc[i].x *= g.alpha; acc[i].y *= g.alpha; acc[i].z *= g.alpha; acc[i].w *= g.alpha; }
         }
-        if (col_ok) {
-          float4 res[8];
-          uint2 aux16[8];
-          if (g.flags & CB_EPI_RESIDUAL_F32) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const long grow = (long)m0 + q * 32 + i * 4 + rb_row;
-              res[i] = grow < g.M ? __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(g.aux) + grow * g.ld_aux + gcol))
-                                  : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-          }
-          if (g.flags & (CB_EPI_RESIDUAL | CB_EPI_RELU_MASK)) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const long grow = (long)m0 + q * 32 + i * 4 + rb_row;
-              aux16[i] = grow < g.M ? __ldg(reinterpret_cast<const uint2*>(g.aux + grow * g.ld_aux + gcol)) : make_uint2(0u, 0u);
-            }
-          }
+        const long row0 = (long)m0 + q * 32 + rb_row;          // rows row0 + 4*i
+        const int nrows = (int)min((long)8, (g.M - row0 + 3) / 4);   // valid i range (rows are contiguous -> prefix)
+        if (!col_ok || nrows <= 0) continue;
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g.bias && split == 0) bias4 = __ldg(reinterpret_cast<const float4*>(g.bias + gcol));
+        if (mode == EM_BF16) {
+          const float lo = (g.flags & CB_EPI_RELU) ? 0.f : -INFINITY;
+          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(g.C) + row0 * g.ldc + gcol;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const int rl = i * 4 + rb_row;
-            const long grow = (long)m0 + q * 32 + rl;
-            if (grow >= g.M) continue;
-            float4 v = acc[i];
-            v.x *= g.alpha; v.y *= g.alpha; v.z *= g.alpha; v.w *= g.alpha;
-            if (g.flags & CB_EPI_TOKENIZE) {
-              const int2 rr = rinfo[i];
-              if (rr.x == -2) {   // CLS row: cls_token + pos_embed[0] (no conv bias)
+            if (i < nrows) {
+              const float4 v = acc[i];
+              *reinterpret_cast<uint2*>(dst + (long)i * 4 * g.ldc) =
+                  make_uint2(pack_bf16(fmaxf(v.x + bias4.x, lo), fmaxf(v.y + bias4.y, lo)), pack_bf16(fmaxf(v.z + bias4.z, lo), fmaxf(v.w + bias4.w, lo)));
+            }
+          }
+        } else if (mode == EM_BF16_MASK) {
+          const __nv_bfloat16* ap = g.aux + row0 * g.ld_aux + gcol;
+          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(g.C) + row0 * g.ldc + gcol;
+          uint2 m16[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) m16[i] = i < nrows ? __ldg(reinterpret_cast<const uint2*>(ap + (long)i * 4 * g.ld_aux)) : make_uint2(0u, 0u);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (i < nrows) {
+              const float4 v = acc[i];
+              const float2 f0 = unpack_bf16(m16[i].x), f1 = unpack_bf16(m16[i].y);
+              *reinterpret_cast<uint2*>(dst + (long)i * 4 * g.ldc) =
+                  make_uint2(pack_bf16(f0.x > 0.f ? v.x : 0.f, f0.y > 0.f ? v.y : 0.f), pack_bf16(f1.x > 0.f ? v.z : 0.f, f1.y > 0.f ? v.w : 0.f));
+            }
+          }
+        } else if (mode == EM_F32) {
+          float* dst = reinterpret_cast<float*>(g.C) + row0 * g.ldc + gcol;
+          float4 res[8];
+          if (g.flags & CB_EPI_RESIDUAL_F32) {
+            const float* rp = reinterpret_cast<const float*>(g.aux) + row0 * g.ld_aux + gcol;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) res[i] = i < nrows ? __ldg(reinterpret_cast<const float4*>(rp + (long)i * 4 * g.ld_aux)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          const float lo = (g.flags & CB_EPI_RELU) ? 0.f : -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (i < nrows) {
+              const float4 v = acc[i];
+              *reinterpret_cast<float4*>(dst + (long)i * 4 * g.ldc) =
+                  make_float4(fmaxf(v.x + bias4.x, lo) + res[i].x, fmaxf(v.y + bias4.y, lo) + res[i].y, fmaxf(v.z + bias4.z, lo) + res[i].z,
+                              fmaxf(v.w + bias4.w, lo) + res[i].w);
+            }
+          }
+        } else if (mode == EM_ATOMIC) {
+          float* dst = reinterpret_cast<float*>(g.C) + row0 * g.ldc + gcol;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (i < nrows) {
+              const float4 v = acc[i];
+              atomicAdd(reinterpret_cast<float4*>(dst + (long)i * 4 * g.ldc), make_float4(v.x + bias4.x, v.y + bias4.y, v.z + bias4.z, v.w + bias4.w));
+            }
+          }
+        } else {  // EM_TOKENIZE: fp32 tokens = acc + conv bias + pos[p] + channel_token[c]; CLS rows = cls_token + pos_embed[0]
+          float* dst = reinterpret_cast<float*>(g.C) + row0 * g.ldc + gcol;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int px = __shfl_sync(0xffffffffu, ri.x, i * 4 + rb_row), cx = __shfl_sync(0xffffffffu, ri.y, i * 4 + rb_row);
+            if (i < nrows) {
+              float4 v = acc[i];
+              if (px == -2) {
                 const float4 a4 = __ldg(reinterpret_cast<const float4*>(g.cls_tok + gcol)), b4 = __ldg(reinterpret_cast<const float4*>(g.pos0 + gcol));
                 v = make_float4(a4.x + b4.x, a4.y + b4.y, a4.z + b4.z, a4.w + b4.w);
               } else {
-                const float4 p4 = __ldg(reinterpret_cast<const float4*>(g.pos + rr.x + gcol));
+                const float4 p4 = __ldg(reinterpret_cast<const float4*>(g.pos + px + gcol));
                 v.x += bias4.x + p4.x; v.y += bias4.y + p4.y; v.z += bias4.z + p4.z; v.w += bias4.w + p4.w;
-                if (rr.y >= 0) {
-                  const float4 c4 = __ldg(reinterpret_cast<const float4*>(g.chan_tok + rr.y + gcol));
+                if (cx >= 0) {
+                  const float4 c4 = __ldg(reinterpret_cast<const float4*>(g.chan_tok + cx + gcol));
                   v.x += c4.x; v.y += c4.y; v.z += c4.z; v.w += c4.w;
                 }
               }
-            } else {
-              v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
+              *reinterpret_cast<float4*>(dst + (long)i * 4 * g.ldc) = v;
             }
-            if (g.flags & CB_EPI_RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-            if (g.flags & CB_EPI_RESIDUAL_F32) { v.x += res[i].x; v.y += res[i].y; v.z += res[i].z; v.w += res[i].w; }
-            if (g.flags & (CB_EPI_RESIDUAL | CB_EPI_RELU_MASK)) {
-              const float2 f0 = unpack_bf16(aux16[i].x), f1 = unpack_bf16(aux16[i].y);
-              if (g.flags & CB_EPI_RESIDUAL) { v.x += f0.x; v.y += f0.y; v.z += f1.x; v.w += f1.y; }
-              else { v.x = f0.x > 0.f ? v.x : 0.f; v.y = f0.y > 0.f ? v.y : 0.f; v.z = f1.x > 0.f ? v.z : 0.f; v.w = f1.y > 0.f ? v.w : 0.f; }
-            }
-            if (g.flags & CB_EPI_ATOMIC) atomicAdd(reinterpret_cast<float4*>(reinterpret_cast<float*>(g.C) + grow * g.ldc + gcol), v);
-            else if (out_f32) *reinterpret_cast<float4*>(reinterpret_cast<float*>(g.C) + grow * g.ldc + gcol) = v;
-            else *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.C) + grow * g.ldc + gcol) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
           }
         }
       }
@@ -337,6 +365,8 @@ extern "C" int cb_gemm_bf16(const void* A, int lda, int a_mn, const void* B, int
   g.M = M; g.N = N; g.K = K; g.k_splits = k_splits; g.C = C; g.ldc = ldc; g.bias = bias;
   g.aux = reinterpret_cast<const __nv_bfloat16*>(aux); g.ld_aux = ld_aux; g.flags = flags; g.alpha = alpha;
   CB_CHECK(!(flags & CB_EPI_TOKENIZE), "cb_gemm_bf16: use cb_tokenize_fwd for the tokenizer epilogue");
-  CB_CHECK(!(flags & (CB_EPI_RESIDUAL | CB_EPI_RELU_MASK | CB_EPI_RESIDUAL_F32)) || aux, "cb_gemm_bf16: aux pointer required by flags");
+  CB_CHECK(!(flags & CB_EPI_RESIDUAL), "cb_gemm_bf16: bf16 residual epilogue was removed (the residual stream is fp32: use CB_EPI_RESIDUAL_F32)");
+  CB_CHECK(!(flags & CB_EPI_RESIDUAL_F32) || (flags & CB_EPI_OUT_F32), "cb_gemm_bf16: CB_EPI_RESIDUAL_F32 requires CB_EPI_OUT_F32");
+  CB_CHECK(!(flags & (CB_EPI_RELU_MASK | CB_EPI_RESIDUAL_F32)) || aux, "cb_gemm_bf16: aux pointer required by flags");
   return cb::gemm_run(A, lda, a_mn, B, ldb, b_mn, g, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -29,12 +29,12 @@ extern "C" {
 
 /* ---- epilogue flags of cb_gemm_bf16 ---- */
 #define CB_EPI_RELU 1       /* C = max(C, 0)                                  (linear1 + F.relu, chada_vit.py:115)   */
-#define CB_EPI_RESIDUAL 2   /* C += aux                                       (x + attn / x + ff, chada_vit.py:99-100) */
+#define CB_EPI_RESIDUAL 2   /* reserved (bf16 residual; rejected: the residual stream is fp32, see CB_EPI_RESIDUAL_F32)  */
 #define CB_EPI_RELU_MASK 4  /* C = aux > 0 ? C : 0                            (backward of F.relu)                    */
 #define CB_EPI_OUT_F32 8    /* store fp32 instead of bf16                                                             */
 #define CB_EPI_ATOMIC 16    /* fp32 atomic accumulate into C (split-K weight gradients)                               */
 #define CB_EPI_TOKENIZE 32  /* internal: tokenizer scatter epilogue (use cb_tokenize_fwd)                             */
-#define CB_EPI_RESIDUAL_F32 64 /* C += aux where aux is fp32 [M,N] (fp32 residual stream)                               */
+#define CB_EPI_RESIDUAL_F32 64 /* C += aux, aux fp32 [M,N], needs CB_EPI_OUT_F32      (x + attn / x + ff, chada_vit.py:99-100) */
 
 const char* cb_last_error(void);
 int cb_version(void);

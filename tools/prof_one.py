@@ -1,0 +1,36 @@
+#!/usr/bin/env python
+"""Launch ONE kernel class a few times so that `ncu --set full` can capture it in isolation.
+    python tools/prof_one.py fc1|qkv|dh|fc2|attn_fwd|attn_bwd|ln_fwd|ln_bwd"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from chadavit_b200 import ops  # noqa: E402
+
+which = sys.argv[1] if len(sys.argv) > 1 else "fc1"
+T, D, F, dev, bf16 = 68664, 192, 2048, "cuda", torch.bfloat16
+r = lambda *s: (torch.randn(*s, device=dev) * 0.5).to(bf16)  # noqa: E731
+x16, hid, x32 = r(T, D), r(T, F), torch.randn(T, D, device=dev)
+w_in, w1, w2 = r(3 * D, D), r(F, D), r(D, F)
+b1, b2, b_in = torch.randn(F, device=dev), torch.randn(D, device=dev), torch.randn(3 * D, device=dev)
+counts = np.random.RandomState(1234).randint(1, 11, size=64).tolist()
+lay = ops.PackedLayout(counts, 196, dev)
+qkv = r(lay.T, 3 * D)
+do = r(lay.T, D)
+R = ops.EPI_RESIDUAL_F32 | ops.EPI_OUT_F32
+fns = {
+    "fc1": lambda: ops.gemm(x16, w1, bias=b1, flags=ops.EPI_RELU),
+    "qkv": lambda: ops.gemm(x16, w_in, bias=b_in),
+    "dh": lambda: ops.gemm(x16, w2, b_mn=True, aux=hid, flags=ops.EPI_RELU_MASK),
+    "fc2": lambda: ops.gemm(hid, w2, bias=b2, aux=x32, flags=R),
+    "attn_fwd": lambda: ops.attn_fwd(qkv, lay, 2),
+}
+if which == "attn_bwd":
+    out, lse = ops.attn_fwd(qkv, lay, 2)
+    fns["attn_bwd"] = lambda: ops.attn_bwd(do, qkv, out, lse, lay, 2)
+for _ in range(5):
+    fns[which]()
+torch.cuda.synchronize()
