@@ -159,13 +159,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           else { const int c = (off - 1) / g.npatch; ri = make_int2(((off - 1) - c * g.npatch) * g.N, g.chan_tok ? c * g.N : -1); }
         }
       }
-      // bias of this warp's FIRST slab is fetched before the accumulator wait, the next slab's during the current one,
-      // and the TMEM read of slab s+1 is issued before the math/stores of slab s: L2 and TMEM latencies stay off the
-      // critical path (ncu: the first use of the bias and the tcgen05.ld wait were the two hottest stalls).
-      const bool has_bias = g.bias != nullptr && split == 0;
-      float4 bias_next = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (has_bias && last_slab >= 0 && n0 + half * 32 + rb_chunk * 4 < g.N)
-        bias_next = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + half * 32 + rb_chunk * 4));
       mbar_wait(&acc_full[buf], aph);
       tc_fence_after();
       if (last_slab < 0) {   // nothing to do for this warp in this tile: still release the accumulator
@@ -174,43 +167,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (lane == 0) mbar_arrive(&acc_empty[buf]);
         continue;
       }
-      const long row0 = (long)m0 + q * 32 + rb_row;                                // this lane's rows: row0 + 4*i
-      const int nrows = (int)max((long)0, min((long)8, (g.M - row0 + 3) / 4));     // valid i range (prefix)
-      uint32_t r[32];
-      tmem_ld32(t_addr + half * 32, r);
 #pragma unroll 1
       for (int sl = half; sl < n_slabs; sl += 2) {
         const int c = sl * 32;
-        const int gcol = n0 + c + rb_chunk * 4;
-        const bool col_ok = gcol < g.N;
-        const float4 bias4 = bias_next;
-        if (has_bias && sl + 2 < n_slabs && gcol + 64 < g.N) bias_next = __ldg(reinterpret_cast<const float4*>(g.bias + gcol + 64));
-        // operands that do not depend on the accumulator are requested before the TMEM wait
-        float4 pf[8];
-        if (mode == EM_F32 && (g.flags & CB_EPI_RESIDUAL_F32) && col_ok) {
-          const float* rp = reinterpret_cast<const float*>(g.aux) + row0 * g.ld_aux + gcol;
+        {
+          uint32_t r[32];
+          tmem_ld32(t_addr + c, r);
+          tmem_ld_wait();
+          if (sl == last_slab) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&acc_empty[buf]); }
 #pragma unroll
-          for (int i = 0; i < 8; ++i) pf[i] = i < nrows ? __ldg(reinterpret_cast<const float4*>(rp + (long)i * 4 * g.ld_aux)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        } else if (mode == EM_BF16_MASK && col_ok) {
-          const __nv_bfloat16* ap = g.aux + row0 * g.ld_aux + gcol;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const uint2 u = i < nrows ? __ldg(reinterpret_cast<const uint2*>(ap + (long)i * 4 * g.ld_aux)) : make_uint2(0u, 0u);
-            pf[i] = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), 0.f, 0.f);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) pf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int k = 0; k < 8; ++k)
+            *reinterpret_cast<uint4*>(srow + ((k ^ (lane & 7)) << 4)) = make_uint4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
         }
-        tmem_ld_wait();
-        if (sl == last_slab) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&acc_empty[buf]); }
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          *reinterpret_cast<uint4*>(srow + ((k ^ (lane & 7)) << 4)) = make_uint4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
         __syncwarp();
-        if (sl + 2 < n_slabs) tmem_ld32(t_addr + c + 64, r);   // next slab's accumulator: in flight during the math below
         // ---- read-back + epilogue math: this lane owns columns gcol..gcol+3 of rows rb_row, rb_row+4, ...
         // One lean, branch-free loop per epilogue mode (the mode is uniform for the launch).
+        const int gcol = n0 + c + rb_chunk * 4;
+        const bool col_ok = gcol < g.N;
         float4 acc[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -222,7 +195,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
           for (int i = 0; i < 8; ++i) { acc[i].x *= g.alpha; acc[i].y *= g.alpha; acc[i].z *= g.alpha; acc[i].w *= g.alpha; }
         }
+        const long row0 = (long)m0 + q * 32 + rb_row;          // rows row0 + 4*i
+        const int nrows = (int)min((long)8, (g.M - row0 + 3) / 4);   // valid i range (rows are contiguous -> prefix)
         if (!col_ok || nrows <= 0) continue;
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g.bias && split == 0) bias4 = __ldg(reinterpret_cast<const float4*>(g.bias + gcol));
         if (mode == EM_BF16) {
           const float lo = (g.flags & CB_EPI_RELU) ? 0.f : -INFINITY;
           __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(g.C) + row0 * g.ldc + gcol;
@@ -235,26 +212,39 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
           }
         } else if (mode == EM_BF16_MASK) {
+          const __nv_bfloat16* ap = g.aux + row0 * g.ld_aux + gcol;
           __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(g.C) + row0 * g.ldc + gcol;
+          uint2 m16[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) m16[i] = i < nrows ? __ldg(reinterpret_cast<const uint2*>(ap + (long)i * 4 * g.ld_aux)) : make_uint2(0u, 0u);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             if (i < nrows) {
               const float4 v = acc[i];
-              const float2 f0 = unpack_bf16(__float_as_uint(pf[i].x)), f1 = unpack_bf16(__float_as_uint(pf[i].y));
+              const float2 f0 = unpack_bf16(m16[i].x), f1 = unpack_bf16(m16[i].y);
               *reinterpret_cast<uint2*>(dst + (long)i * 4 * g.ldc) =
                   make_uint2(pack_bf16(f0.x > 0.f ? v.x : 0.f, f0.y > 0.f ? v.y : 0.f), pack_bf16(f1.x > 0.f ? v.z : 0.f, f1.y > 0.f ? v.w : 0.f));
             }
           }
         } else if (mode == EM_F32) {
           float* dst = reinterpret_cast<float*>(g.C) + row0 * g.ldc + gcol;
+          float4 res[8];
+          if (g.flags & CB_EPI_RESIDUAL_F32) {
+            const float* rp = reinterpret_cast<const float*>(g.aux) + row0 * g.ld_aux + gcol;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) res[i] = i < nrows ? __ldg(reinterpret_cast<const float4*>(rp + (long)i * 4 * g.ld_aux)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
           const float lo = (g.flags & CB_EPI_RELU) ? 0.f : -INFINITY;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             if (i < nrows) {
-              const float4 v = acc[i];   // pf = fp32 residual requested before the TMEM wait (zeros when the flag is off)
+              const float4 v = acc[i];
               *reinterpret_cast<float4*>(dst + (long)i * 4 * g.ldc) =
-                  make_float4(fmaxf(v.x + bias4.x, lo) + pf[i].x, fmaxf(v.y + bias4.y, lo) + pf[i].y, fmaxf(v.z + bias4.z, lo) + pf[i].z,
-                              fmaxf(v.w + bias4.w, lo) + pf[i].w);
+                  make_float4(fmaxf(v.x + bias4.x, lo) + res[i].x, fmaxf(v.y + bias4.y, lo) + res[i].y, fmaxf(v.z + bias4.z, lo) + res[i].z,
+                              fmaxf(v.w + bias4.w, lo) + res[i].w);
             }
           }
         } else if (mode == EM_ATOMIC) {
