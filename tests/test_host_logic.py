@@ -1,0 +1,151 @@
+"""CPU: host-side bookkeeping (bit-exact index contract), module surface / state-dict parity, schedules, and the
+world_size-2 (gloo) equivalence of the data-parallel reductions."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import chada_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("counts,npatch", [([1, 3, 5, 10], 196), ([2, 10, 1], 36), ([10] * 7, 196), ([1], 4)])
+def test_packed_layout_is_bit_exact(counts, npatch):
+    """cu_seqlens / channel->image maps / row order == the reference's split-pad-stack order at the unmasked positions."""
+    from chadavit_b200.ops import PackedLayout
+    lay = PackedLayout(counts, npatch, "cpu")
+    cu, rows = O.packed_index(counts, npatch)
+    assert lay.cu_host.tolist() == cu and lay.T == len(rows) == len(counts) + sum(counts) * npatch
+    # row cu[b]+1+c*N+p  <->  channel image (off_b + c), patch p
+    off = np.concatenate([[0], np.cumsum(counts)])
+    for b, C in enumerate(counts):
+        for c in (0, C - 1):
+            g = off[b] + c
+            assert lay.chan_img_host[g] == b and lay.chan_idx_host[g] == c
+            assert g * npatch + 0 + b + 1 == cu[b] + 1 + c * npatch      # packed row of patch 0 of channel image g
+    # reference mask: padded rows are exactly the rows NOT in `rows`
+    S_pad = 1 + 10 * npatch
+    masked = np.ones(len(counts) * S_pad, bool)
+    masked[rows] = False
+    for b, C in enumerate(counts):
+        assert masked[b * S_pad:(b + 1) * S_pad].sum() == (10 - C) * npatch   # channel_mask.sum(1) == 1960 - 196*C
+    w = lay.attn_work(2).numpy()
+    assert w.shape[1] == 4 and len(w) == 2 * sum((cu[b + 1] - cu[b] + 127) // 128 for b in range(len(counts)))
+    lens = w[:, 2] - w[:, 1]
+    assert (np.diff(lens) <= 0).all()                                 # longest sequences first
+    nc = lay.non_cls_rows().numpy()
+    assert len(nc) == sum(counts) * npatch and not set(nc) & set(cu[:-1])
+    with pytest.raises(ValueError):
+        PackedLayout([11], npatch, "cpu")
+    with pytest.raises(ValueError):
+        PackedLayout([0, 2], npatch, "cpu")
+
+
+def test_module_surface_matches_reference_contract():
+    from chadavit_b200.backbones import ChAdaViT, chada_vit, vit_channels
+    from chadavit_b200.methods import DINOHead
+    m = vit_channels("dino", patch_size=16, embed_dim=192, return_all_tokens=False, max_number_channels=10, ignored="x")
+    assert isinstance(m, ChAdaViT) and m.num_heads == 2 and m.norm.eps == 1e-6 and len(m.blocks) == 12
+    assert m.num_features == m.embed_dim == 192 and m.token_learner.num_patches == 196 and m.token_learner.patch_size == 16
+    sd = m.state_dict()
+    assert {k: tuple(v.shape) for k, v in sd.items()} == O.backbone_shapes(192)
+    assert list(sd.keys()) == list(O.backbone_shapes(192).keys())
+    assert sum(p.numel() for p in m.parameters()) == 11_341_632
+    bare = ChAdaViT(patch_size=16, embed_dim=192, return_all_tokens=False, max_number_channels=10)
+    assert bare.num_heads == 12 and bare.norm.eps == 1e-5                # Q4 / Q5
+    bare.load_state_dict(sd)                                             # same weights load either way (Q4)
+    h = DINOHead(192, 4096, use_bn=False)
+    assert {k: tuple(v.shape) for k, v in h.state_dict().items()} == O.head_shapes(192, 4096)
+    assert sum(p.numel() for p in h.parameters()) == 6_168_832 and not h.last_layer.weight_g.requires_grad
+    with pytest.raises(NotImplementedError):
+        DINOHead(192, 4096)                                              # use_bn=True (ctor default) is rejected loudly
+    # flat arena keeps parameters as views, survives load_state_dict and is rebuilt after .data is replaced
+    a = m.arena
+    a.ensure()
+    p = m.blocks[3].linear1.weight
+    assert p.data_ptr() == a.fp32.data_ptr() + 4 * a.offsets["blocks.3.linear1.weight"][0]
+    p.data = p.data.clone()
+    a.ensure()
+    assert p.data_ptr() == a.fp32.data_ptr() + 4 * a.offsets["blocks.3.linear1.weight"][0]
+
+
+def test_schedules_match_reference_formulas():
+    from chadavit_b200.losses import DINOLoss
+    from chadavit_b200.utils.momentum import MomentumUpdater
+    L = DINOLoss(64, 0.04, 0.07, 3, 10)
+    assert np.allclose(L.teacher_temp_schedule[:4], [0.04, 0.055, 0.07, 0.07]) and len(L.teacher_temp_schedule) == 10
+    for e in range(10):
+        assert abs(L.teacher_temp_schedule[e] - O.teacher_temp(e, 0.04, 0.07, 3)) < 1e-12
+    u = MomentumUpdater(0.9995, 1.0)
+    for step in (0, 10, 50, 100):
+        u.update_tau(step, 100)
+        assert abs(u.cur_tau - O.cosine_tau(0.9995, 1.0, step, 100)) < 1e-15
+    with pytest.raises(AssertionError):
+        MomentumUpdater(1.0, 0.5)
+
+
+def test_interp_matrix_equals_reference_bicubic():
+    from chadavit_b200.backbones import chada_vit
+    m = chada_vit(patch_size=16, embed_dim=32, return_all_tokens=False, max_number_channels=10)
+    M = m._interp_matrix(6, 6, 96, 96, "cpu")
+    ref = O.interp_pos_embed(m.pos_embed.detach(), 36, 96, 96, 16)[0, 0]
+    assert (M @ m.pos_embed.detach()[0, 0, 1:] - ref).abs().max().item() < 1e-6
+
+
+# ---------------------------------------------------------------------------------------------------- world_size 2 (gloo)
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from oracle import det
+    B, K, V = 3, 64, 2
+    s = torch.from_numpy(det.det_uniform((world, V * B, K), 5))[rank].clone().requires_grad_()
+    t = torch.from_numpy(det.det_uniform((world, 2 * B, K), 6))[rank]
+
+    def allred(x):
+        dist.all_reduce(x)
+        return x
+    loss, center = O.dino_loss(s, t, torch.zeros(1, K), student_temp=0.1, teacher_temp=0.07, world_size=world, all_reduce_sum=allred)
+    loss.backward()
+    g = s.grad.clone()
+    dist.all_reduce(g)                       # DDP: gradient of the mean-over-ranks loss wrt a replicated parameter ~ averaged grads
+    lm = loss.detach().clone()
+    dist.all_reduce(lm)
+    if rank == 0:
+        torch.save({"center": center, "loss_mean": lm / world}, out)
+    dist.destroy_process_group()
+
+
+def test_two_rank_reductions_equal_single_process_on_concatenated_batch(tmp_path):
+    """C2 (centre all-reduce: sum -> /world -> /rows) and the loss mean over ranks reproduce a single-process run on the
+    concatenated batch (SURVEY.md §8e equivalence test), exercised with gloo on CPU."""
+    from oracle import det
+    world = 2
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    out = str(tmp_path / "r0.pt")
+    mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+    got = torch.load(out)
+    B, K, V = 3, 64, 2
+    s = torch.from_numpy(det.det_uniform((world, V * B, K), 5))
+    t = torch.from_numpy(det.det_uniform((world, 2 * B, K), 6))
+    # concatenated batch: view v of the big batch = cat over ranks of view v
+    S = torch.cat([torch.cat([s[r, v * B:(v + 1) * B] for r in range(world)]) for v in range(V)])
+    T = torch.cat([torch.cat([t[r, v * B:(v + 1) * B] for r in range(world)]) for v in range(2)])
+    loss, center = O.dino_loss(S, T, torch.zeros(1, K), student_temp=0.1, teacher_temp=0.07)
+    assert (got["center"] - center).abs().max().item() < 1e-7
+    assert abs(got["loss_mean"].item() - loss.item()) < 1e-6
+
+
+def test_bench_sharding_is_token_balanced():
+    sys.path.insert(0, ROOT)
+    import bench
+    c0, c1 = bench.channel_counts(64), bench.channel_counts(64)
+    assert c0 == c1 and len(c0) == 64 and min(c0) >= 1 and max(c0) <= 10   # identical multiset on every rank
