@@ -49,7 +49,7 @@ enum EpiMode { EM_BF16 = 0, EM_BF16_MASK = 1, EM_F32 = 2, EM_ATOMIC = 3, EM_TOKE
 
 constexpr int GEMM_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 
-template <int BN, int AMODE, int BMODE>
+template <int BN, int AMODE, int BMODE, int EM>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
   using Cfg = GemmCfg<BN>;
@@ -133,8 +133,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int q = warp & 3;
     const int ew = warp - 2;                     // 0..7
     const int half = ew >> 2;                    // which of the two warps of this lane quarter
-    const int mode = (g.flags & CB_EPI_TOKENIZE) ? EM_TOKENIZE : (g.flags & CB_EPI_ATOMIC) ? EM_ATOMIC : (g.flags & CB_EPI_OUT_F32) ? EM_F32
-                     : (g.flags & CB_EPI_RELU_MASK) ? EM_BF16_MASK : EM_BF16;
+    constexpr int mode = EM;   // compile-time epilogue mode: dead branches and their register arrays disappear
     uint8_t* slab = sEpi + ew * EPI_SLAB_BYTES;
     uint8_t* srow = slab + lane * 128;
     const int rb_row = lane >> 3, rb_chunk = lane & 7;   // read-back mapping: 8 lanes cover one 128-byte row (4 columns each)
@@ -159,6 +158,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           else { const int c = (off - 1) / g.npatch; ri = make_int2(((off - 1) - c * g.npatch) * g.N, g.chan_tok ? c * g.N : -1); }
         }
       }
+      // ncu (profiles/r01_ncu_gemm_fc1.txt): the two hottest stalls were the first use of the bias (an L2 round trip per
+      // slab) and the tcgen05.ld wait.  So: the bias of a slab is requested one slab ahead (the first one before the
+      // accumulator wait) and the TMEM read of slab s+1 is issued right after slab s was staged, under its math/stores.
+      const bool has_bias = g.bias != nullptr && split == 0 && mode != EM_BF16_MASK;
+      float4 bias_next = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (has_bias && last_slab >= 0 && n0 + half * 32 + rb_chunk * 4 < g.N)
+        bias_next = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + half * 32 + rb_chunk * 4));
       mbar_wait(&acc_full[buf], aph);
       tc_fence_after();
       if (last_slab < 0) {   // nothing to do for this warp in this tile: still release the accumulator
@@ -167,23 +173,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (lane == 0) mbar_arrive(&acc_empty[buf]);
         continue;
       }
+      uint32_t r[32];
+      tmem_ld32(t_addr + half * 32, r);
 #pragma unroll 1
       for (int sl = half; sl < n_slabs; sl += 2) {
         const int c = sl * 32;
-        {
-          uint32_t r[32];
-          tmem_ld32(t_addr + c, r);
-          tmem_ld_wait();
-          if (sl == last_slab) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&acc_empty[buf]); }
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-            *reinterpret_cast<uint4*>(srow + ((k ^ (lane & 7)) << 4)) = make_uint4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
-        }
-        __syncwarp();
-        // ---- read-back + epilogue math: this lane owns columns gcol..gcol+3 of rows rb_row, rb_row+4, ...
-        // One lean, branch-free loop per epilogue mode (the mode is uniform for the launch).
         const int gcol = n0 + c + rb_chunk * 4;
         const bool col_ok = gcol < g.N;
+        const float4 bias4 = bias_next;
+        if (has_bias && sl + 2 < n_slabs && gcol + 64 < g.N) bias_next = __ldg(reinterpret_cast<const float4*>(g.bias + gcol + 64));
+        tmem_ld_wait();
+        if (sl == last_slab) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&acc_empty[buf]); }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          *reinterpret_cast<uint4*>(srow + ((k ^ (lane & 7)) << 4)) = make_uint4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
+        __syncwarp();
+        if (sl + 2 < n_slabs) tmem_ld32(t_addr + c + 64, r);   // next slab's accumulator, in flight during the math below
+        // ---- read-back + epilogue math: this lane owns columns gcol..gcol+3 of rows rb_row, rb_row+4, ...
+        // One lean, branch-free loop per epilogue mode (compile-time).
         float4 acc[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -198,8 +205,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const long row0 = (long)m0 + q * 32 + rb_row;          // rows row0 + 4*i
         const int nrows = (int)min((long)8, (g.M - row0 + 3) / 4);   // valid i range (rows are contiguous -> prefix)
         if (!col_ok || nrows <= 0) continue;
-        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (g.bias && split == 0) bias4 = __ldg(reinterpret_cast<const float4*>(g.bias + gcol));
         if (mode == EM_BF16) {
           const float lo = (g.flags & CB_EPI_RELU) ? 0.f : -INFINITY;
           __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(g.C) + row0 * g.ldc + gcol;
@@ -301,33 +306,34 @@ static int encode_operand(CUtensorMap* tm, const void* base, int rows, int K, in
   return make_tmap(tm, base, 3, dims, strides, box, mode == 1 ? 3 : 2);
 }
 
-template <int BN, int AMODE, int BMODE>
+template <int BN, int AMODE, int BMODE, int EM>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    CB_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, AMODE, BMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    CB_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, AMODE, BMODE, EM>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
   const int num_tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN) * g.k_splits;
   const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-  gemm_kernel<BN, AMODE, BMODE><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, g);
+  gemm_kernel<BN, AMODE, BMODE, EM><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, g);
   CB_CUDA(cudaGetLastError());
   return 0;
 }
 
+// Instantiated (operand layout, epilogue) pairs: forward products are K-major x K-major; input gradients read the weight
+// MN-major; weight gradients read both operands MN-major and accumulate with fp32 atomics (or store fp32 for the head).
 template <int BN>
-static int dispatch_modes(int am, int bm, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, cudaStream_t s) {
-  switch (am * 3 + bm) {
-    case 0: return launch<BN, 0, 0>(tmA, tmB, g, s);
-    case 1: return launch<BN, 0, 1>(tmA, tmB, g, s);
-    case 2: return launch<BN, 0, 2>(tmA, tmB, g, s);
-    case 4: return launch<BN, 1, 1>(tmA, tmB, g, s);
-    case 5: return launch<BN, 1, 2>(tmA, tmB, g, s);
-    case 7: return launch<BN, 2, 1>(tmA, tmB, g, s);
-    case 8: return launch<BN, 2, 2>(tmA, tmB, g, s);
-    default: set_error("gemm: unsupported operand layout combination a=%d b=%d", am, bm); return 1;
-  }
+static int dispatch_modes(int am, int bm, int em, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, cudaStream_t s) {
+#define CB_CASE(A_, B_, E_) if (am == A_ && bm == B_ && em == E_) return launch<BN, A_, B_, E_>(tmA, tmB, g, s);
+  CB_CASE(0, 0, EM_BF16) CB_CASE(0, 0, EM_F32) CB_CASE(0, 0, EM_TOKENIZE)
+  CB_CASE(0, 1, EM_BF16) CB_CASE(0, 1, EM_BF16_MASK) CB_CASE(0, 1, EM_F32)
+  CB_CASE(0, 2, EM_BF16) CB_CASE(0, 2, EM_BF16_MASK) CB_CASE(0, 2, EM_F32)
+  CB_CASE(1, 1, EM_ATOMIC) CB_CASE(1, 1, EM_F32) CB_CASE(1, 2, EM_ATOMIC) CB_CASE(1, 2, EM_F32)
+  CB_CASE(2, 1, EM_ATOMIC) CB_CASE(2, 1, EM_F32) CB_CASE(2, 2, EM_ATOMIC) CB_CASE(2, 2, EM_F32)
+#undef CB_CASE
+  set_error("gemm: operand layout (a_mn=%d, b_mn=%d) with epilogue mode %d is not instantiated", am, bm, em);
+  return 1;
 }
 
 int gemm_run(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, GemmArgs g, cudaStream_t stream) {
@@ -351,9 +357,11 @@ int gemm_run(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn,
   CUtensorMap tmA, tmB;
   if (encode_operand(&tmA, A, g.M, g.K, lda, am, BM)) return 1;
   if (encode_operand(&tmB, B, g.N, g.K, ldb, bm, BN)) return 1;
-  if (BN == 192) return dispatch_modes<192>(am, bm, tmA, tmB, g, stream);
-  if (BN == 256) return dispatch_modes<256>(am, bm, tmA, tmB, g, stream);
-  return dispatch_modes<128>(am, bm, tmA, tmB, g, stream);
+  const int em = (g.flags & CB_EPI_TOKENIZE) ? EM_TOKENIZE : (g.flags & CB_EPI_ATOMIC) ? EM_ATOMIC : (g.flags & CB_EPI_OUT_F32) ? EM_F32
+                 : (g.flags & CB_EPI_RELU_MASK) ? EM_BF16_MASK : EM_BF16;
+  if (BN == 192) return dispatch_modes<192>(am, bm, em, tmA, tmB, g, stream);
+  if (BN == 256) return dispatch_modes<256>(am, bm, em, tmA, tmB, g, stream);
+  return dispatch_modes<128>(am, bm, em, tmA, tmB, g, stream);
 }
 
 }  // namespace cb
