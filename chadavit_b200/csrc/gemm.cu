@@ -173,6 +173,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (lane == 0) mbar_arrive(&acc_empty[buf]);
         continue;
       }
+      const long row0 = (long)m0 + q * 32 + rb_row;                               // this lane's rows: row0 + 4*i
+      const int nrows = (int)max((long)0, min((long)8, (g.M - row0 + 3) / 4));    // valid i range (a prefix)
       uint32_t r[32];
       tmem_ld32(t_addr + half * 32, r);
 #pragma unroll 1
@@ -182,6 +184,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const bool col_ok = gcol < g.N;
         const float4 bias4 = bias_next;
         if (has_bias && sl + 2 < n_slabs && gcol + 64 < g.N) bias_next = __ldg(reinterpret_cast<const float4*>(g.bias + gcol + 64));
+        // accumulator-independent operands (ReLU mask / fp32 residual) are requested before the TMEM wait
+        uint2 m16[8];
+        float4 res[8];
+        if (mode == EM_BF16_MASK) {
+          const __nv_bfloat16* ap = g.aux + row0 * g.ld_aux + gcol;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) m16[i] = (col_ok && i < nrows) ? __ldg(reinterpret_cast<const uint2*>(ap + (long)i * 4 * g.ld_aux)) : make_uint2(0u, 0u);
+        }
+        if (mode == EM_F32) {
+          if (g.flags & CB_EPI_RESIDUAL_F32) {
+            const float* rp = reinterpret_cast<const float*>(g.aux) + row0 * g.ld_aux + gcol;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) res[i] = (col_ok && i < nrows) ? __ldg(reinterpret_cast<const float4*>(rp + (long)i * 4 * g.ld_aux)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
         tmem_ld_wait();
         if (sl == last_slab) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&acc_empty[buf]); }
 #pragma unroll
@@ -202,8 +222,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
           for (int i = 0; i < 8; ++i) { acc[i].x *= g.alpha; acc[i].y *= g.alpha; acc[i].z *= g.alpha; acc[i].w *= g.alpha; }
         }
-        const long row0 = (long)m0 + q * 32 + rb_row;          // rows row0 + 4*i
-        const int nrows = (int)min((long)8, (g.M - row0 + 3) / 4);   // valid i range (rows are contiguous -> prefix)
         if (!col_ok || nrows <= 0) continue;
         if (mode == EM_BF16) {
           const float lo = (g.flags & CB_EPI_RELU) ? 0.f : -INFINITY;
@@ -217,11 +235,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
           }
         } else if (mode == EM_BF16_MASK) {
-          const __nv_bfloat16* ap = g.aux + row0 * g.ld_aux + gcol;
           __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(g.C) + row0 * g.ldc + gcol;
-          uint2 m16[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) m16[i] = i < nrows ? __ldg(reinterpret_cast<const uint2*>(ap + (long)i * 4 * g.ld_aux)) : make_uint2(0u, 0u);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             if (i < nrows) {
@@ -233,15 +247,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         } else if (mode == EM_F32) {
           float* dst = reinterpret_cast<float*>(g.C) + row0 * g.ldc + gcol;
-          float4 res[8];
-          if (g.flags & CB_EPI_RESIDUAL_F32) {
-            const float* rp = reinterpret_cast<const float*>(g.aux) + row0 * g.ld_aux + gcol;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) res[i] = i < nrows ? __ldg(reinterpret_cast<const float4*>(rp + (long)i * 4 * g.ld_aux)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
           const float lo = (g.flags & CB_EPI_RELU) ? 0.f : -INFINITY;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -326,7 +331,7 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs
 template <int BN>
 static int dispatch_modes(int am, int bm, int em, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, cudaStream_t s) {
 #define CB_CASE(A_, B_, E_) if (am == A_ && bm == B_ && em == E_) return launch<BN, A_, B_, E_>(tmA, tmB, g, s);
-  CB_CASE(0, 0, EM_BF16) CB_CASE(0, 0, EM_F32) CB_CASE(0, 0, EM_TOKENIZE)
+  CB_CASE(0, 0, EM_BF16) CB_CASE(0, 0, EM_F32) CB_CASE(0, 0, EM_TOKENIZE) CB_CASE(0, 0, EM_BF16_MASK)
   CB_CASE(0, 1, EM_BF16) CB_CASE(0, 1, EM_BF16_MASK) CB_CASE(0, 1, EM_F32)
   CB_CASE(0, 2, EM_BF16) CB_CASE(0, 2, EM_BF16_MASK) CB_CASE(0, 2, EM_F32)
   CB_CASE(1, 1, EM_ATOMIC) CB_CASE(1, 1, EM_F32) CB_CASE(1, 2, EM_ATOMIC) CB_CASE(1, 2, EM_F32)
