@@ -331,7 +331,7 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs
 template <int BN>
 static int dispatch_modes(int am, int bm, int em, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, cudaStream_t s) {
 #define CB_CASE(A_, B_, E_) if (am == A_ && bm == B_ && em == E_) return launch<BN, A_, B_, E_>(tmA, tmB, g, s);
-  CB_CASE(0, 0, EM_BF16) CB_CASE(0, 0, EM_F32) CB_CASE(0, 0, EM_TOKENIZE) CB_CASE(0, 0, EM_BF16_MASK)
+  CB_CASE(0, 0, EM_BF16) CB_CASE(0, 0, EM_F32) CB_CASE(0, 0, EM_TOKENIZE) CB_CASE(0, 0, EM_BF16_MASK) CB_CASE(0, 0, EM_ATOMIC)
   CB_CASE(0, 1, EM_BF16) CB_CASE(0, 1, EM_BF16_MASK) CB_CASE(0, 1, EM_F32)
   CB_CASE(0, 2, EM_BF16) CB_CASE(0, 2, EM_BF16_MASK) CB_CASE(0, 2, EM_F32)
   CB_CASE(1, 1, EM_ATOMIC) CB_CASE(1, 1, EM_F32) CB_CASE(1, 2, EM_ATOMIC) CB_CASE(1, 2, EM_F32)
