@@ -48,11 +48,12 @@ def make_crops(counts, seed, device, pin=False):
     return crops
 
 
-def dino_cfg(multicrop=False):
+def dino_cfg(multicrop=False, graph=True):
     return {"method": "dino", "backbone": {"kwargs": {"patch_size": 16, "embed_dim": D_MODEL, "return_all_tokens": False}},
             "data": {"max_img_channels": 10, "num_large_crops": N_GLOBAL, "num_small_crops": N_LOCAL},
             "method_kwargs": {"num_prototypes": N_PROTO, "multicrop_loss": multicrop}, "max_epochs": 100, "max_steps": 100000,
-            "optimizer": {"lr": 5e-4, "weight_decay": 1e-4}, "momentum": {"base_tau": 0.9995, "final_tau": 1.0}}
+            "optimizer": {"lr": 5e-4, "weight_decay": 1e-4}, "momentum": {"base_tau": 0.9995, "final_tau": 1.0},
+            "engine": {"cuda_graph": graph}}
 
 
 # ---------------------------------------------------------------------------------------------------- clocks
@@ -155,6 +156,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--multicrop", action="store_true", help="true multi-crop loss (V=8) instead of the reference wiring")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -174,7 +176,7 @@ def main():
     _lib.load()
 
     torch.manual_seed(0)                      # identical random init on every rank (DDP replicas)
-    model = DINO(dino_cfg(args.multicrop)).to(dev)
+    model = DINO(dino_cfg(args.multicrop, graph=not args.no_graph)).to(dev)
     counts = channel_counts(BATCH)            # same multiset on every rank -> token-balanced
     lnc = [counts] * (N_GLOBAL + N_LOCAL)
     crops = make_crops(counts, 1234 + rank, dev)
@@ -191,9 +193,13 @@ def main():
     for _ in range(args.warmup):
         loss = model.fused_train_step(batch)
     sync()
-    # ---- timed region 1: inputs resident in HBM, with per-kernel-class event timing
-    ops.PROFILE = {"cb_attn_varlen_fwd": [0, 0.0, []], "cb_attn_varlen_bwd": [0, 0.0, []], "cb_gemm_bf16": [0, 0.0, []]}
-    launches0 = _lib.launch_count
+    # ---- timed region 1: inputs resident in HBM
+    launches_eager0 = _lib.launch_count
+    model.use_cuda_graph, keep = False, model.use_cuda_graph
+    model.fused_train_step(batch)             # one eager step only to COUNT the kernels a step launches (graph replays bypass Python)
+    model.use_cuda_graph = keep
+    launches_per_step = _lib.launch_count - launches_eager0
+    sync()
     with ClockSampler(local_rank) as clk:
         sync()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -203,7 +209,18 @@ def main():
         e1.record()
         sync()
     ms = e0.elapsed_time(e1)
-    launches = _lib.launch_count - launches0
+    launches = launches_per_step * args.steps
+    # ---- instrumented eager pass of the same step: CUDA-event duration of every attention / GEMM launch (roofline)
+    model.use_cuda_graph, keep = False, model.use_cuda_graph
+    ops.PROFILE = {"cb_attn_varlen_fwd": [0, 0.0, []], "cb_attn_varlen_bwd": [0, 0.0, []], "cb_gemm_bf16": [0, 0.0, []]}
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        model.fused_train_step(batch)
+    ev1.record()
+    sync()
+    ms_eager = ev0.elapsed_time(ev1)
+    model.use_cuda_graph = keep
     prof = {}
     for name, (n, work, evs) in ops.PROFILE.items():
         t = sum(a.elapsed_time(b) for a, b in evs)
@@ -215,12 +232,12 @@ def main():
     host_crops = make_crops(counts, 1234 + rank, dev, pin=True)
     h2d = sum(c.numel() * 4 for c in host_crops)
     for _ in range(2):
-        model.fused_train_step(([c.to(dev, non_blocking=True) for c in host_crops], None, lnc)).item()
+        model.fused_train_step((host_crops, None, lnc)).item()
     sync()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     for _ in range(args.steps):
-        l = model.fused_train_step(([c.to(dev, non_blocking=True) for c in host_crops], None, lnc))
+        l = model.fused_train_step((host_crops, None, lnc))   # pinned host crops: the H2D copies are part of the step
         _ = l.item()                           # D2H read of the step's loss
     e3.record()
     sync()
@@ -248,12 +265,14 @@ def main():
     for name, p in prof.items():
         ach = p["work"] / (p["ms_total"] * 1e-3) / 1e12 if p["ms_total"] > 0 else 0.0
         roof[name] = {"launches_per_step": p["launches"] / args.steps, "ms_per_step": p["ms_total"] / args.steps,
-                      "share_of_step": p["ms_total"] / ms, "achieved_tflops": ach, "frac": ach / tf_peak}
+                      "share_of_step": p["ms_total"] / ms_eager, "achieved_tflops": ach, "frac": ach / tf_peak}
     tp = prof[top]
     roofline = {"kernel": top, "bound": "tensor", "achieved": roof[top]["achieved_tflops"], "peak": tf_peak, "unit": "TFLOP/s",
                 "frac": roof[top]["frac"], "traffic": None, "peak_source": peak_src,
                 "algorithmic_flops_per_launch": tp["work"] / max(1, tp["launches"]),
-                "avg_launch_ms": tp["ms_total"] / max(1, tp["launches"]), "all": roof}
+                "avg_launch_ms": tp["ms_total"] / max(1, tp["launches"]), "all": roof,
+                "timing": "CUDA events around every launch of the class in an instrumented eager pass of the same step "
+                          f"({ms_eager / args.steps:.1f} ms/step eager vs {ms / args.steps:.1f} ms/step timed)"}
 
     cpu = None
     if not args.no_cpu_baseline:
@@ -273,7 +292,7 @@ def main():
                                + ("true multi-crop loss (V=8)" if args.multicrop else "reference wiring (local crops: student backbone only, SURVEY Q11)"),
                    "global_batch": imgs, "per_gpu_batch": BATCH, "sum_channels_per_gpu": int(sum(counts)),
                    "tokens_per_gpu_global_crop": tokens_g, "tokens_per_gpu_local_crop": tokens_l,
-                   "parallelism": f"dp{world}", "ranks_token_balanced": True,
+                   "parallelism": f"dp{world}", "ranks_token_balanced": True, "cuda_graph": bool(model.use_cuda_graph),
                    "l2_policy": "working set per step (~10 GB of activations) >> 126 MB L2; no explicit flush"},
         "clocks": clk.summary(),
         "e2e": {"value": imgs * args.steps / (ms_e2e * 1e-3), "unit": "imgs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,

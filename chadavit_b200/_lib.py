@@ -40,7 +40,7 @@ SIGNATURES = {
     "cb_colsum_f32": [_vp, _vp, _i, _i, _vp],
     "cb_dino_center_ema": [_vp, _vp, _f, _f, _i, _vp],
     "cb_ema_update": [_vp, _vp, _vp, _f, _l, _vp],
-    "cb_adamw_step": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _l, _f, _f, _f, _f, _f, _i, _f, _f, _vp],
+    "cb_adamw_step": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _l, _f, _f, _f, _f, _f, _i, _f, _f, _vp, _vp],
 }
 
 _lib = None

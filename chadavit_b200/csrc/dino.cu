@@ -196,9 +196,12 @@ struct AdamArgs {
 // flags[i]: bit0 = apply weight decay, bit1 = frozen (no update).  Optional fused teacher EMA and bf16 shadows.
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                              const uint8_t* __restrict__ flags, __nv_bfloat16* __restrict__ p16, float* __restrict__ teacher,
-                             __nv_bfloat16* __restrict__ teacher16, AdamArgs a, long n) {
+                             __nv_bfloat16* __restrict__ teacher16, AdamArgs a, const float* __restrict__ dev_hyper, long n) {
   const long i0 = (blockIdx.x * (long)blockDim.x + threadIdx.x) * 4;
   if (i0 >= n) return;
+  if (dev_hyper) {   // CUDA-graph replay: per-step scalars live in device memory {lr, 1-beta1^t, sqrt(1-beta2^t), tau}
+    a.lr = __ldg(dev_hyper); a.bc1 = __ldg(dev_hyper + 1); a.bc2_sqrt = __ldg(dev_hyper + 2); a.tau = __ldg(dev_hyper + 3);
+  }
   float4 P = *reinterpret_cast<float4*>(p + i0);
   const float4 G = *reinterpret_cast<const float4*>(g + i0);
   float4 M = *reinterpret_cast<float4*>(m + i0), Vv = *reinterpret_cast<float4*>(v + i0);
@@ -303,13 +306,13 @@ extern "C" int cb_ema_update(float* momentum, const float* online, void* momentu
 }
 extern "C" int cb_adamw_step(float* p, const float* g, float* m, float* v, const unsigned char* flags, void* p_bf16, float* teacher,
                              void* teacher_bf16, long n, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
-                             float grad_scale, float tau, void* stream) {
+                             float grad_scale, float tau, const float* dev_hyper, void* stream) {
   CB_CHECK(n > 0 && n % 4 == 0 && step >= 1, "adamw_step: n=%ld step=%d", n, step);
   AdamArgs a;
   a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.wd = weight_decay; a.grad_scale = grad_scale; a.tau = tau;
   a.bc1 = 1.f - powf(beta1, (float)step);
   a.bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
-  adamw_kernel<<<blocks4(n), 256, 0, STREAM>>>(p, g, m, v, flags, BFM(p_bf16), teacher, BFM(teacher_bf16), a, n);
+  adamw_kernel<<<blocks4(n), 256, 0, STREAM>>>(p, g, m, v, flags, BFM(p_bf16), teacher, BFM(teacher_bf16), a, dev_hyper, n);
   CB_CUDA(cudaGetLastError());
   return 0;
 }

@@ -223,6 +223,8 @@ class DINO(nn.Module):
         self.max_steps = _cfg(cfg, "max_steps", 100000)
         self.list_num_channels: List[List[int]] = []
         self._opt: Dict[str, Dict[str, torch.Tensor]] = {}
+        self.use_cuda_graph = bool(_cfg(cfg, "engine.cuda_graph", False))
+        self._graphs: Dict[tuple, dict] = {}
         if self.clip_grad:
             raise NotImplementedError("clip_grad > 0 (per-parameter clipping, dino.py:249-261) is not implemented in this round")
 
@@ -307,16 +309,11 @@ class DINO(nn.Module):
         return st
 
     @torch.no_grad()
-    def fused_train_step(self, batch: Sequence[Any], lr: Optional[float] = None) -> torch.Tensor:
-        """One complete DINO step (forward, loss, backward, gradient all-reduce, AdamW, teacher EMA, tau update) without an
-        autograd graph.  Semantics identical to training_step + on_after_backward + AdamW.step + on_train_batch_end."""
-        X, _targets, list_num_channels = batch
-        X = [X] if isinstance(X, torch.Tensor) else X
-        assert len(X) == self.num_crops
+    def _step_device_work(self, X, list_num_channels, *, lr: float, tau: float, step: int, world: int, dev_hyper=None) -> torch.Tensor:
+        """All device work of one step (zero grads .. fused AdamW+EMA); no host-side state is touched, so the sequence can be
+        captured once into a CUDA graph and replayed (per-step scalars then come from ``dev_hyper``)."""
         nl = self.num_large_crops
         bb, tb, hd, th = self.backbone, self.momentum_backbone, self.head, self.momentum_head
-        for m in (bb, tb, hd, th):
-            m._ready()
         gb, gh = bb.arena.ensure_grad(), hd.arena.ensure_grad()
         gb.zero_()
         gh.zero_()
@@ -348,25 +345,89 @@ class DINO(nn.Module):
             bb._backward_impl(s, dfe[o:o + r].contiguous(), gb)
             o += r
         # data-parallel replicas: average gradients (C1) — flat arenas, one NCCL all-reduce each
-        world = 1
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            world = dist.get_world_size()
+        if world > 1:
             dist.all_reduce(gb)
             dist.all_reduce(gh)
         # AdamW + teacher EMA + bf16 refresh of student and teacher, one launch per network
-        self.global_step += 1
-        lr = self.lr if lr is None else lr
-        tau = self.momentum_updater.cur_tau
         for name, on, mo, g in (("backbone", bb, tb, gb), ("head", hd, th, gh)):
             st = self._opt_state(name, on.arena)
             flags = st["flags"]
             if name == "head" and self.current_epoch < self.freeze_last_layer:
                 flags = st["flags_frozen_last"]
             ops.adamw_step(on.arena.fp32, g, st["m"], st["v"], lr=lr, beta1=self.betas[0], beta2=self.betas[1], eps=self.adam_eps,
-                           weight_decay=self.weight_decay, step=self.global_step, flags=flags, p_bf16=on.arena.bf16,
-                           teacher=mo.arena.fp32, teacher_bf16=mo.arena.bf16, grad_scale=1.0 / world, tau=tau)
-            for ar in (on.arena, mo.arena):
-                ar.mark_dirty()
-                ar._bf16_key = (ar.manual_version, sum(p._version for p in ar.params))   # shadows were refreshed by the kernel
+                           weight_decay=self.weight_decay, step=step, flags=flags, p_bf16=on.arena.bf16,
+                           teacher=mo.arena.fp32, teacher_bf16=mo.arena.bf16, grad_scale=1.0 / world, tau=tau, dev_hyper=dev_hyper)
+        return loss
+
+    @torch.no_grad()
+    def fused_train_step(self, batch: Sequence[Any], lr: Optional[float] = None) -> torch.Tensor:
+        """One complete DINO step (forward, loss, backward, gradient all-reduce, AdamW, teacher EMA, tau update) without an
+        autograd graph.  Semantics identical to training_step + on_after_backward + AdamW.step + on_train_batch_end.
+
+        With ``self.use_cuda_graph`` the device work of a batch *signature* (channel counts per crop + shapes) is captured
+        into a CUDA graph the second time that signature is seen and replayed afterwards (inputs are copied into static
+        buffers; lr / bias corrections / tau are read from device memory), which removes the per-launch host overhead."""
+        X, _targets, list_num_channels = batch
+        X = [X] if isinstance(X, torch.Tensor) else list(X)
+        assert len(X) == self.num_crops
+        bb, tb, hd, th = self.backbone, self.momentum_backbone, self.head, self.momentum_head
+        for m in (bb, tb, hd, th):
+            m._ready()
+        world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        self.global_step += 1
+        lr = self.lr if lr is None else lr
+        tau = self.momentum_updater.cur_tau
+        step = self.global_step
+        loss = None
+        if self.use_cuda_graph:
+            loss = self._graph_step(X, list_num_channels, lr, tau, step, world)
+        if loss is None:
+            dev = bb.arena.fp32.device
+            X = [x if x.is_cuda else x.to(dev, non_blocking=True) for x in X]    # host (pinned) crops are accepted
+            loss = self._step_device_work(X, list_num_channels, lr=lr, tau=tau, step=step, world=world)
+        for ar in (bb.arena, tb.arena, hd.arena, th.arena):
+            ar.mark_dirty()
+            ar._bf16_key = (ar.manual_version, sum(p._version for p in ar.params))   # shadows were refreshed by the kernel
         self.momentum_updater.update_tau(cur_step=self.global_step, max_steps=self.max_steps)
         return loss[0]
+
+    def _graph_step(self, X, list_num_channels, lr, tau, step, world):
+        L = self.dino_loss_func
+        key = (tuple(tuple(int(c) for c in l) for l in list_num_channels[:len(X)]), tuple(tuple(x.shape) for x in X),
+               self.current_epoch < self.freeze_last_layer, float(L.teacher_temp_schedule[L.epoch]), world)
+        ent = self._graphs.get(key)
+        if ent is None:                      # first sighting: run eagerly (also warms up caches / kernel attributes)
+            if len(self._graphs) >= 2:
+                self._graphs.clear()
+            self._graphs[key] = {"seen": 1}
+            return None
+        import math
+        hyper = [lr, 1.0 - self.betas[0] ** step, math.sqrt(1.0 - self.betas[1] ** step), tau]
+        if "graph" not in ent:
+            try:
+                dev = self.backbone.arena.fp32.device
+                ent["x"] = [torch.empty(x.shape, device=dev, dtype=torch.float32) for x in X]
+                ent["hyper_host"] = torch.zeros(4, dtype=torch.float32).pin_memory()
+                ent["hyper"] = torch.zeros(4, dtype=torch.float32, device=dev)
+                for d, x in zip(ent["x"], X):
+                    d.copy_(x, non_blocking=True)
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    ent["loss"] = self._step_device_work(ent["x"], list_num_channels, lr=lr, tau=tau, step=step, world=world,
+                                                         dev_hyper=ent["hyper"])
+                ent["graph"] = g
+            except Exception as e:            # capture unsupported in this configuration: stay eager, loudly
+                import warnings
+                warnings.warn(f"chadavit_b200: CUDA graph capture failed ({e}); continuing without graphs")
+                self.use_cuda_graph = False
+                self._graphs.clear()
+                return None
+        else:
+            for d, x in zip(ent["x"], X):          # H2D (pinned host crops) or D2D into the graph's static input buffers
+                if d.data_ptr() != x.data_ptr():
+                    d.copy_(x, non_blocking=True)
+        ent["hyper_host"].copy_(torch.tensor(hyper, dtype=torch.float32))
+        ent["hyper"].copy_(ent["hyper_host"], non_blocking=True)
+        ent["graph"].replay()
+        return ent["loss"]

@@ -318,6 +318,7 @@ def ema_update(momentum_flat: torch.Tensor, online_flat: torch.Tensor, tau: floa
 
 
 def adamw_step(p, g, m, v, *, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, step=1, flags=None, p_bf16=None, teacher=None,
-               teacher_bf16=None, grad_scale=1.0, tau=1.0) -> None:
+               teacher_bf16=None, grad_scale=1.0, tau=1.0, dev_hyper=None) -> None:
+    """dev_hyper: optional device fp32[4] {lr, 1-beta1^step, sqrt(1-beta2^step), tau} read by the kernel (CUDA-graph replay)."""
     _call("cb_adamw_step", _p(p), _p(g), _p(m), _p(v), _p(flags), _p(p_bf16), _p(teacher), _p(teacher_bf16), p.numel(), float(lr),
-          float(beta1), float(beta2), float(eps), float(weight_decay), int(step), float(grad_scale), float(tau), _stream())
+          float(beta1), float(beta2), float(eps), float(weight_decay), int(step), float(grad_scale), float(tau), _p(dev_hyper), _stream())

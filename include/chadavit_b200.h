@@ -143,10 +143,11 @@ int cb_dino_center_ema(float* center, const float* batch_sum, float scale, float
 int cb_ema_update(float* momentum, const float* online, void* momentum_bf16, float tau, long n, void* stream);
 /* torch.optim.AdamW step over a flat arena, optionally fused with the teacher EMA and the bf16 shadow
  * refresh of both networks.  flags[i]: bit0 = weight decay applies, bit1 = frozen (e.g. head.last_layer while
- * current_epoch < freeze_last_layer, dino.py:374-376); NULL = decay everything. */
+ * current_epoch < freeze_last_layer, dino.py:374-376); NULL = decay everything.  dev_hyper (optional, device fp32[4] =
+ * {lr, 1-beta1^step, sqrt(1-beta2^step), tau}) overrides the per-step scalars so a captured CUDA graph can be replayed. */
 int cb_adamw_step(float* p, const float* g, float* m, float* v, const unsigned char* flags, void* p_bf16, float* teacher,
                   void* teacher_bf16, long n, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
-                  float grad_scale, float tau, void* stream);
+                  float grad_scale, float tau, const float* dev_hyper, void* stream);
 
 #ifdef __cplusplus
 }
