@@ -28,7 +28,7 @@ SIGNATURES = {
     "cb_colsum_bf16": [_vp, _i, _vp, _i, _i, _vp],
     "cb_cast_f32_bf16": [_vp, _vp, _l, _vp],
     "cb_gather_rows_f32": [_vp, _vp, _vp, _i, _i, _vp],
-    "cb_attn_varlen_fwd": [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _f, _vp],
+    "cb_attn_varlen_fwd": [_vp, _vp, _i, _i, _vp, _vp, _i, _i, _i, _f, _vp],
     "cb_attn_varlen_bwd": [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _f, _vp],
     "cb_gelu_fwd": [_vp, _vp, _l, _vp],
     "cb_gelu_bwd": [_vp, _vp, _vp, _l, _vp],

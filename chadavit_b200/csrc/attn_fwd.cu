@@ -319,11 +319,18 @@ static int launch_fwd(const void* qkv, const AttnFwdArgs& a, int T, int D, cudaS
 
 }  // namespace cb
 
-extern "C" int cb_attn_varlen_fwd(const void* qkv, const int* work, int n_work, void* out, float* lse, int T, int D, int H,
+namespace cb {
+int attn_fwd2_run(const void* qkv, const int* work, int n_work, void* out, float* lse, int T, int D, int H, float softmax_scale,
+                  cudaStream_t s);
+}
+
+extern "C" int cb_attn_varlen_fwd(const void* qkv, const int* work, int n_work, int q_tile, void* out, float* lse, int T, int D, int H,
                                   float softmax_scale, void* stream) {
   using namespace cb;
   CB_CHECK(T > 0 && H > 0 && D % H == 0 && n_work > 0, "attn_fwd: bad shape T=%d D=%d H=%d n_work=%d", T, D, H, n_work);
   CB_CHECK((3 * D) % 8 == 0, "attn_fwd: 3*D must be a multiple of 8");
+  CB_CHECK(q_tile == 128 || q_tile == 256, "attn_fwd: q_tile must be 128 (one query tile per work item) or 256 (two)");
+  if (q_tile == 256) return attn_fwd2_run(qkv, work, n_work, out, lse, T, D, H, softmax_scale, reinterpret_cast<cudaStream_t>(stream));
   AttnFwdArgs a{};
   a.work = reinterpret_cast<const int4*>(work); a.n_work = n_work; a.out = reinterpret_cast<__nv_bfloat16*>(out); a.lse = lse;
   a.T = T; a.D = D; a.scale_log2 = softmax_scale * 1.4426950408889634f;

@@ -1,0 +1,333 @@
+// Varlen attention forward, 2-query-tile variant (the production path; attn_fwd.cu keeps the simpler 1-tile kernel).
+//
+// A work item is (sequence, head, PAIR of 128-query tiles).  Two softmax warpgroups (A: warps 2-5, B: warps 6-9) each own
+// one query tile — no cross-thread row reductions — while a single MMA-issuing thread interleaves the two tiles:
+//     S_A(0) S_B(0) | PV_A(0) S_A(1) | PV_B(0) S_B(1) | PV_A(1) S_A(2) | ...
+// so the tensor pipe works on tile B while tile A is in softmax and vice versa (each tile's S buffer in TMEM is
+// single-buffered and aliased by its bf16 P).  TMEM: S_A 128 | S_B 128 | O_A 128 | O_B 128 columns.
+// Softmax reads S twice from TMEM (max pass, exp pass) instead of holding 128 fp32 in registers, folds the scale into one
+// FFMA per element, masks only in the last (ragged) KV tile, and rescales O lazily (row max grown by > 2^8).
+#include "common.cuh"
+#include "chadavit_b200.h"
+#include "internal.h"
+
+namespace cb {
+
+template <int HD>
+struct Att2Cfg {
+  static constexpr int CHUNK = (HD % 64 == 0) ? 64 : (HD % 32 == 0 ? 32 : 16);
+  static constexpr int NCH = HD / CHUNK;
+  static constexpr int SWZ = CHUNK == 64 ? 3 : (CHUNK == 32 ? 2 : 1);
+  static constexpr int CHUNK_BYTES = 128 * CHUNK * 2;
+  static constexpr int TILE_BYTES = NCH * CHUNK_BYTES;      // one [128 x HD] bf16 tile
+  static constexpr int SBO = 8 * CHUNK * 2;
+  static constexpr int KV_STAGES = HD <= 96 ? 3 : 2;
+  static constexpr int SMEM_BYTES = TILE_BYTES * (2 + 2 * KV_STAGES) + 1024 + 256;
+  static constexpr int COL_S = 0, COL_O = 256;              // + 128 * tile
+};
+
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+struct Attn2Args {
+  const int4* work;  // {q_row0 (global row of tile A), seq_start, seq_end, head}
+  int n_work;
+  __nv_bfloat16* out;
+  float* lse;
+  int T, D;
+  float scale_log2;
+};
+
+template <int HD>
+__global__ void __launch_bounds__(320, 1) attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const Attn2Args a) {
+  using Cfg = Att2Cfg<HD>;
+  constexpr int NS = Cfg::KV_STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                                   // [2] tiles
+  uint8_t* sK = sQ + 2 * Cfg::TILE_BYTES;               // [NS]
+  uint8_t* sV = sK + NS * Cfg::TILE_BYTES;              // [NS]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + NS * Cfg::TILE_BYTES);
+  uint64_t* q_full = bars + 0;
+  uint64_t* q_empty = bars + 1;
+  uint64_t* k_full = bars + 2;              // [NS]
+  uint64_t* v_full = k_full + NS;           // [NS]
+  uint64_t* kv_empty = v_full + NS;         // [NS]
+  uint64_t* s_full = kv_empty + NS;         // [2] per tile
+  uint64_t* p_full = s_full + 2;            // [2] 128 arrivals
+  uint64_t* pv_done = p_full + 2;           // [2]
+  uint64_t* o_full = pv_done + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQKV);
+    mbar_init(q_full, 1); mbar_init(q_empty, 1);
+    for (int i = 0; i < NS; ++i) { mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128); mbar_init(&pv_done[i], 1); mbar_init(&o_full[i], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int st = 0; uint32_t ph = 0, wi = 0;
+      for (int w = blockIdx.x; w < a.n_work; w += gridDim.x, ++wi) {
+        const int4 wk = a.work[w];
+        const int head = wk.w;
+        const int n_kv = (wk.z - wk.y + 127) / 128;
+        const bool two = wk.x + 128 < wk.z;
+        mbar_wait(q_empty, (wi & 1) ^ 1);
+        mbar_expect_tx(q_full, (two ? 2 : 1) * Cfg::TILE_BYTES);
+        for (int t = 0; t < (two ? 2 : 1); ++t)
+#pragma unroll
+          for (int c = 0; c < Cfg::NCH; ++c)
+            tma_load_2d(sQ + t * Cfg::TILE_BYTES + c * Cfg::CHUNK_BYTES, &tmQKV, q_full, head * HD + c * Cfg::CHUNK, wk.x + t * 128);
+        for (int j = 0; j < n_kv; ++j) {
+          mbar_wait(&kv_empty[st], ph ^ 1);
+          const int row = wk.y + j * 128;
+          mbar_expect_tx(&k_full[st], Cfg::TILE_BYTES);
+#pragma unroll
+          for (int c = 0; c < Cfg::NCH; ++c)
+            tma_load_2d(sK + st * Cfg::TILE_BYTES + c * Cfg::CHUNK_BYTES, &tmQKV, &k_full[st], a.D + head * HD + c * Cfg::CHUNK, row);
+          mbar_expect_tx(&v_full[st], Cfg::TILE_BYTES);
+#pragma unroll
+          for (int c = 0; c < Cfg::NCH; ++c)
+            tma_load_2d(sV + st * Cfg::TILE_BYTES + c * Cfg::CHUNK_BYTES, &tmQKV, &v_full[st], 2 * a.D + head * HD + c * Cfg::CHUNK, row);
+          if (++st == NS) { st = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = umma_idesc_bf16(128, 128, false, false);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(128, HD, false, true);
+      int st = 0; uint32_t ph = 0;          // K/V ring position of kv tile j (advanced once per j)
+      uint32_t itc[2] = {0, 0};             // per-tile kv-iteration counters (phases of s_full / p_full / pv_done)
+      uint32_t wi = 0, wo[2] = {0, 0};
+      auto issue_qk = [&](int t, uint32_t k_addr) {
+        const uint32_t q_addr = smem_u32(sQ + t * Cfg::TILE_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk) {
+          const int c = (kk * 16) / Cfg::CHUNK, off = ((kk * 16) % Cfg::CHUNK) * 2;
+          umma_ss(tmem_base + Cfg::COL_S + t * 128, umma_smem_desc(q_addr + c * Cfg::CHUNK_BYTES + off, 16, Cfg::SBO, Cfg::SWZ),
+                  umma_smem_desc(k_addr + c * Cfg::CHUNK_BYTES + off, 16, Cfg::SBO, Cfg::SWZ), idesc_qk, kk > 0 ? 1u : 0u);
+        }
+        tc_commit(&s_full[t]);
+      };
+      auto issue_pv = [&](int t, uint32_t v_addr, bool first) {
+        mbar_wait(&p_full[t], itc[t] & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          umma_ts(tmem_base + Cfg::COL_O + t * 128, tmem_base + Cfg::COL_S + t * 128 + kk * 8,
+                  umma_smem_desc(v_addr + kk * 16 * Cfg::CHUNK * 2, Cfg::CHUNK_BYTES, Cfg::SBO, Cfg::SWZ), idesc_pv, (!first || kk > 0) ? 1u : 0u);
+        tc_commit(&pv_done[t]);
+        ++itc[t];
+      };
+      for (int w = blockIdx.x; w < a.n_work; w += gridDim.x, ++wi) {
+        const int4 wk = a.work[w];
+        const int n_kv = (wk.z - wk.y + 127) / 128;
+        const bool two = wk.x + 128 < wk.z;
+        mbar_wait(q_full, wi & 1);
+        tc_fence_after();
+        // prologue: S_A(0), S_B(0)
+        mbar_wait(&k_full[st], ph);
+        tc_fence_after();
+        issue_qk(0, smem_u32(sK + st * Cfg::TILE_BYTES));
+        if (two) issue_qk(1, smem_u32(sK + st * Cfg::TILE_BYTES));
+        for (int j = 0; j < n_kv; ++j) {
+          const int stn = (st + 1 == NS) ? 0 : st + 1;
+          const uint32_t phn = (st + 1 == NS) ? ph ^ 1 : ph;
+          const bool more = j + 1 < n_kv;
+          mbar_wait(&v_full[st], ph);
+          if (more) mbar_wait(&k_full[stn], phn);
+          tc_fence_after();
+          const uint32_t v_addr = smem_u32(sV + st * Cfg::TILE_BYTES), kn_addr = smem_u32(sK + stn * Cfg::TILE_BYTES);
+          issue_pv(0, v_addr, j == 0);                 // O_A += P_A(j) V_j   (waits for softmax A)
+          if (more) issue_qk(0, kn_addr);              // S_A(j+1): runs while softmax B(j) is still busy
+          if (two) {
+            issue_pv(1, v_addr, j == 0);
+            if (more) issue_qk(1, kn_addr);
+          }
+          tc_commit(&kv_empty[st]);                    // K_j / V_j free once everything issued so far has retired
+          if (j + 2 == n_kv) tc_commit(q_empty);       // the last Q·K^T products are issued: Q may be refilled under the final PVs
+          st = stn; ph = phn;
+        }
+        if (n_kv == 1) tc_commit(q_empty);
+        tc_commit(&o_full[0]);
+        if (two) tc_commit(&o_full[1]);
+        (void)wo;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax warpgroups (tile t = 0: warps 2-5, 1: warps 6-9)
+    const int t = (warp - 2) >> 2;
+    const int q = warp & 3;
+    const int r_in_tile = q * 32 + lane;
+    const uint32_t lane_addr = tmem_base + (uint32_t(q * 32) << 16);
+    const uint32_t s_addr = lane_addr + Cfg::COL_S + t * 128, o_addr = lane_addr + Cfg::COL_O + t * 128;
+    uint32_t it = 0, ow = 0;   // this tile's kv-iteration / work counters
+    for (int w = blockIdx.x; w < a.n_work; w += gridDim.x) {
+      const int4 wk = a.work[w];
+      const int q0 = wk.x + t * 128;
+      if (q0 >= wk.z) continue;                         // odd tail: this item has no second tile
+      const int seq_len = wk.z - wk.y;
+      const int n_kv = (seq_len + 127) / 128;
+      float m_used = -INFINITY, l = 0.f;
+      for (int j = 0; j < n_kv; ++j, ++it) {
+        mbar_wait(&s_full[t], it & 1);
+        tc_fence_after();
+        const int kv_valid = seq_len - j * 128;
+        const bool ragged = kv_valid < 128;
+        // ---- pass 1: row max of the raw scores
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          tmem_ld32(s_addr + c * 32, r);
+          tmem_ld_wait();
+          if (ragged) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) if (c * 32 + i >= kv_valid) r[i] = 0xff800000u;  // -inf
+          }
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            mx0 = fmaxf(mx0, __uint_as_float(r[i])); mx1 = fmaxf(mx1, __uint_as_float(r[i + 1]));
+            mx2 = fmaxf(mx2, __uint_as_float(r[i + 2])); mx3 = fmaxf(mx3, __uint_as_float(r[i + 3]));
+          }
+        }
+        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * a.scale_log2;
+        float alpha = 1.f;
+        const bool need = mx > m_used + 8.f;             // lazy rescale (warp-uniform decision below)
+        const bool any_need = __any_sync(0xffffffffu, need);
+        if (need) { alpha = ex2f(m_used - mx); m_used = mx; }
+        // ---- pass 2: P = exp2(s*scale - m), row sum, bf16 P -> TMEM (aliases S)
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        const float neg_m = -m_used;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          tmem_ld32(s_addr + c * 32, r);
+          tmem_ld_wait();
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            float p0 = ex2f(fmaf(__uint_as_float(r[i]), a.scale_log2, neg_m));
+            float p1 = ex2f(fmaf(__uint_as_float(r[i + 1]), a.scale_log2, neg_m));
+            float p2 = ex2f(fmaf(__uint_as_float(r[i + 2]), a.scale_log2, neg_m));
+            float p3 = ex2f(fmaf(__uint_as_float(r[i + 3]), a.scale_log2, neg_m));
+            if (ragged) {
+              if (c * 32 + i >= kv_valid) p0 = 0.f;
+              if (c * 32 + i + 1 >= kv_valid) p1 = 0.f;
+              if (c * 32 + i + 2 >= kv_valid) p2 = 0.f;
+              if (c * 32 + i + 3 >= kv_valid) p3 = 0.f;
+            }
+            s0 += p0; s1 += p1; s2 += p2; s3 += p3;
+            pk[i >> 1] = pack_bf16(p0, p1);
+            pk[(i >> 1) + 1] = pack_bf16(p2, p3);
+          }
+          tmem_st16(s_addr + c * 16, pk);
+        }
+        l = l * alpha + ((s0 + s1) + (s2 + s3));
+        if (j > 0 && any_need) {
+          mbar_wait(&pv_done[t], (it - 1) & 1);          // O complete (PV of the previous kv tile retired) before the rescale
+          tc_fence_after();
+#pragma unroll
+          for (int c = 0; c < HD; c += 32) {
+            if (HD - c >= 32) {
+              uint32_t o[32];
+              tmem_ld32(o_addr + c, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st32(o_addr + c, o);
+            } else {
+              uint32_t o[16];
+              tmem_ld16(o_addr + c, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st16(o_addr + c, o);
+            }
+          }
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&p_full[t]);
+      }
+      // ---- epilogue: O / l -> bf16, LSE
+      mbar_wait(&o_full[t], ow & 1);
+      ++ow;
+      tc_fence_after();
+      const int grow = q0 + r_in_tile;
+      const bool ok = grow < wk.z;
+      const float inv_l = 1.f / l;
+      __nv_bfloat16* dst = a.out + (long)grow * a.D + wk.w * HD;
+#pragma unroll
+      for (int c = 0; c < HD; c += 16) {
+        uint32_t o[16];
+        tmem_ld16(o_addr + c, o);
+        tmem_ld_wait();
+        if (ok) {
+          *reinterpret_cast<uint4*>(dst + c) = make_uint4(
+              pack_bf16(__uint_as_float(o[0]) * inv_l, __uint_as_float(o[1]) * inv_l), pack_bf16(__uint_as_float(o[2]) * inv_l, __uint_as_float(o[3]) * inv_l),
+              pack_bf16(__uint_as_float(o[4]) * inv_l, __uint_as_float(o[5]) * inv_l), pack_bf16(__uint_as_float(o[6]) * inv_l, __uint_as_float(o[7]) * inv_l));
+          *reinterpret_cast<uint4*>(dst + c + 8) = make_uint4(
+              pack_bf16(__uint_as_float(o[8]) * inv_l, __uint_as_float(o[9]) * inv_l), pack_bf16(__uint_as_float(o[10]) * inv_l, __uint_as_float(o[11]) * inv_l),
+              pack_bf16(__uint_as_float(o[12]) * inv_l, __uint_as_float(o[13]) * inv_l), pack_bf16(__uint_as_float(o[14]) * inv_l, __uint_as_float(o[15]) * inv_l));
+        }
+      }
+      if (ok && a.lse) a.lse[(long)wk.w * a.T + grow] = (m_used + log2f(l)) * 0.6931471805599453f;
+      tc_fence_before();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+template <int HD>
+static int launch_fwd2(const void* qkv, const Attn2Args& a, cudaStream_t stream) {
+  using Cfg = Att2Cfg<HD>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CB_CUDA(cudaFuncSetAttribute(attn_fwd2_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  CUtensorMap tm;
+  uint64_t dims[2] = {(uint64_t)(3 * a.D), (uint64_t)a.T};
+  uint64_t strides[1] = {(uint64_t)(3 * a.D) * 2};
+  uint32_t box[2] = {(uint32_t)Cfg::CHUNK, 128};
+  if (make_tmap(&tm, qkv, 2, dims, strides, box, Cfg::SWZ)) return 1;
+  const int grid = a.n_work < num_sms() ? a.n_work : num_sms();
+  attn_fwd2_kernel<HD><<<grid, 320, Cfg::SMEM_BYTES, stream>>>(tm, a);
+  CB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int attn_fwd2_run(const void* qkv, const int* work, int n_work, void* out, float* lse, int T, int D, int H, float softmax_scale,
+                  cudaStream_t s) {
+  Attn2Args a{};
+  a.work = reinterpret_cast<const int4*>(work); a.n_work = n_work; a.out = reinterpret_cast<__nv_bfloat16*>(out); a.lse = lse;
+  a.T = T; a.D = D; a.scale_log2 = softmax_scale * 1.4426950408889634f;
+  switch (D / H) {
+    case 16: return launch_fwd2<16>(qkv, a, s);
+    case 32: return launch_fwd2<32>(qkv, a, s);
+    case 64: return launch_fwd2<64>(qkv, a, s);
+    case 96: return launch_fwd2<96>(qkv, a, s);
+    case 128: return launch_fwd2<128>(qkv, a, s);
+    default: set_error("attn_fwd: unsupported head_dim %d (supported: 16, 32, 64, 96, 128)", D / H); return 1;
+  }
+}
+
+}  // namespace cb

@@ -207,14 +207,14 @@ def tokenize_bwd(dtokens: torch.Tensor, patches: torch.Tensor, lay: PackedLayout
           T, D, _p(dw_pe), _p(db_pe), _p(dpos_patch), _p(dpos0), _p(dcls_tok), _p(dchan_tok), ks, _stream())
 
 
-def attn_fwd(qkv: torch.Tensor, lay: PackedLayout, nheads: int, *, need_lse: bool = True) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+def attn_fwd(qkv: torch.Tensor, lay: PackedLayout, nheads: int, *, need_lse: bool = True, q_tile: int = 256) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     T, D3 = qkv.shape
     D = D3 // 3
     d = D // nheads
-    work = lay.attn_work(nheads)
+    work = lay.attn_work(nheads, q_tile)
     out = torch.empty(T, D, device=qkv.device, dtype=bf16)
     lse = torch.empty(nheads, T, device=qkv.device, dtype=torch.float32) if need_lse else None
-    _call("cb_attn_varlen_fwd", _p(qkv), _p(work), work.shape[0], _p(out), _p(lse), T, D, nheads, float(d) ** -0.5, _stream(),
+    _call("cb_attn_varlen_fwd", _p(qkv), _p(work), work.shape[0], q_tile, _p(out), _p(lse), T, D, nheads, float(d) ** -0.5, _stream(),
           work=4.0 * D * lay.sum_sq)
     return out, lse
 
