@@ -189,56 +189,77 @@ __global__ void __launch_bounds__(320, 1) attn_fwd2_kernel(const __grid_constant
         tc_fence_after();
         const int kv_valid = seq_len - j * 128;
         const bool ragged = kv_valid < 128;
-        // ---- pass 1: row max of the raw scores
-        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t r[32];
-          tmem_ld32(s_addr + c * 32, r);
-          tmem_ld_wait();
-          if (ragged) {
+        // ---- TMEM read bandwidth (~64 B/clk/SM: 1024 clk per 128x128 fp32 tile) is as scarce as MUFU throughput, so S is
+        // read ONCE per tile in steady state: probabilities are computed speculatively against the running reference max
+        // (valid while the tile max stays within 2^8 of it) and kept packed in registers; only when a row max jumps (always
+        // for the first KV tile, rarely afterwards) is S read a second time.
+        auto max_pass = [&]() -> float {
+          float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) if (c * 32 + i >= kv_valid) r[i] = 0xff800000u;  // -inf
-          }
+          for (int c = 0; c < 4; ++c) {
+            uint32_t r[32];
+            tmem_ld32(s_addr + c * 32, r);
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            mx0 = fmaxf(mx0, __uint_as_float(r[i])); mx1 = fmaxf(mx1, __uint_as_float(r[i + 1]));
-            mx2 = fmaxf(mx2, __uint_as_float(r[i + 2])); mx3 = fmaxf(mx3, __uint_as_float(r[i + 3]));
-          }
-        }
-        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * a.scale_log2;
-        float alpha = 1.f;
-        const bool need = mx > m_used + 8.f;             // lazy rescale (warp-uniform decision below)
-        const bool any_need = __any_sync(0xffffffffu, need);
-        if (need) { alpha = ex2f(m_used - mx); m_used = mx; }
-        // ---- pass 2: P = exp2(s*scale - m), row sum, bf16 P -> TMEM (aliases S)
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-        const float neg_m = -m_used;
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t r[32];
-          tmem_ld32(s_addr + c * 32, r);
-          tmem_ld_wait();
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            float p0 = ex2f(fmaf(__uint_as_float(r[i]), a.scale_log2, neg_m));
-            float p1 = ex2f(fmaf(__uint_as_float(r[i + 1]), a.scale_log2, neg_m));
-            float p2 = ex2f(fmaf(__uint_as_float(r[i + 2]), a.scale_log2, neg_m));
-            float p3 = ex2f(fmaf(__uint_as_float(r[i + 3]), a.scale_log2, neg_m));
-            if (ragged) {
-              if (c * 32 + i >= kv_valid) p0 = 0.f;
-              if (c * 32 + i + 1 >= kv_valid) p1 = 0.f;
-              if (c * 32 + i + 2 >= kv_valid) p2 = 0.f;
-              if (c * 32 + i + 3 >= kv_valid) p3 = 0.f;
+            for (int i = 0; i < 32; i += 4) {
+              float x0 = __uint_as_float(r[i]), x1 = __uint_as_float(r[i + 1]), x2 = __uint_as_float(r[i + 2]), x3 = __uint_as_float(r[i + 3]);
+              if (ragged) {
+                if (c * 32 + i >= kv_valid) x0 = -INFINITY;
+                if (c * 32 + i + 1 >= kv_valid) x1 = -INFINITY;
+                if (c * 32 + i + 2 >= kv_valid) x2 = -INFINITY;
+                if (c * 32 + i + 3 >= kv_valid) x3 = -INFINITY;
+              }
+              mx0 = fmaxf(mx0, x0); mx1 = fmaxf(mx1, x1); mx2 = fmaxf(mx2, x2); mx3 = fmaxf(mx3, x3);
             }
-            s0 += p0; s1 += p1; s2 += p2; s3 += p3;
-            pk[i >> 1] = pack_bf16(p0, p1);
-            pk[(i >> 1) + 1] = pack_bf16(p2, p3);
           }
-          tmem_st16(s_addr + c * 16, pk);
+          return fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * a.scale_log2;
+        };
+        uint32_t pk[64];
+        auto exp_pass = [&](float neg_m, float& mx_out) -> float {
+          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+          float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t r[32];
+            tmem_ld32(s_addr + c * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              float x0 = __uint_as_float(r[i]), x1 = __uint_as_float(r[i + 1]), x2 = __uint_as_float(r[i + 2]), x3 = __uint_as_float(r[i + 3]);
+              if (ragged) {
+                if (c * 32 + i >= kv_valid) x0 = -INFINITY;
+                if (c * 32 + i + 1 >= kv_valid) x1 = -INFINITY;
+                if (c * 32 + i + 2 >= kv_valid) x2 = -INFINITY;
+                if (c * 32 + i + 3 >= kv_valid) x3 = -INFINITY;
+              }
+              mx0 = fmaxf(mx0, x0); mx1 = fmaxf(mx1, x1); mx2 = fmaxf(mx2, x2); mx3 = fmaxf(mx3, x3);
+              const float p0 = ex2f(fmaf(x0, a.scale_log2, neg_m)), p1 = ex2f(fmaf(x1, a.scale_log2, neg_m));
+              const float p2 = ex2f(fmaf(x2, a.scale_log2, neg_m)), p3 = ex2f(fmaf(x3, a.scale_log2, neg_m));
+              s0 += p0; s1 += p1; s2 += p2; s3 += p3;
+              pk[c * 16 + (i >> 1)] = pack_bf16(p0, p1);
+              pk[c * 16 + (i >> 1) + 1] = pack_bf16(p2, p3);
+            }
+          }
+          mx_out = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * a.scale_log2;
+          return (s0 + s1) + (s2 + s3);
+        };
+        float alpha = 1.f, mx_seen;
+        if (j == 0) m_used = max_pass();                 // first KV tile: no reference yet (l == 0, O not started)
+        float tsum = exp_pass(-m_used, mx_seen);
+        const bool need = mx_seen > m_used + 8.f;        // lazy rescale: reference max moves only when outgrown by 2^8
+        const bool any_need = __any_sync(0xffffffffu, need);
+        if (any_need) {                                  // rare: redo this tile against the new reference (warp-uniform)
+          if (need) { alpha = ex2f(m_used - mx_seen); m_used = mx_seen; }
+          tsum = exp_pass(-m_used, mx_seen);
         }
-        l = l * alpha + ((s0 + s1) + (s2 + s3));
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t t16[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) t16[i] = pk[c * 16 + i];
+          tmem_st16(s_addr + c * 16, t16);
+        }
+        l = l * alpha + tsum;
         if (j > 0 && any_need) {
           mbar_wait(&pv_done[t], (it - 1) & 1);          // O complete (PV of the previous kv tile retired) before the rescale
           tc_fence_after();
