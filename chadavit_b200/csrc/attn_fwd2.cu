@@ -42,7 +42,7 @@ struct Attn2Args {
 };
 
 template <int HD>
-__global__ void __launch_bounds__(320, 1) attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const Attn2Args a) {
+__global__ void __maxnreg__(200) attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const Attn2Args a) {
   using Cfg = Att2Cfg<HD>;
   constexpr int NS = Cfg::KV_STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -218,11 +218,13 @@ __global__ void __launch_bounds__(320, 1) attn_fwd2_kernel(const __grid_constant
         auto exp_pass = [&](float neg_m, float& mx_out) -> float {
           float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
           float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+          uint32_t rb[2][32];                      // double buffer: the TMEM read of chunk c+1 is in flight under chunk c's MUFU work
+          tmem_ld32(s_addr, rb[0]);
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            uint32_t r[32];
-            tmem_ld32(s_addr + c * 32, r);
             tmem_ld_wait();
+            if (c < 3) tmem_ld32(s_addr + (c + 1) * 32, rb[(c + 1) & 1]);
+            const uint32_t (&r)[32] = rb[c & 1];
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
               float x0 = __uint_as_float(r[i]), x1 = __uint_as_float(r[i + 1]), x2 = __uint_as_float(r[i + 2]), x3 = __uint_as_float(r[i + 3]);
