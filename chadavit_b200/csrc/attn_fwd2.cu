@@ -42,7 +42,7 @@ struct Attn2Args {
 };
 
 template <int HD>
-__global__ void __maxnreg__(192) attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const Attn2Args a) {
+__global__ void __launch_bounds__(320, 1) attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const Attn2Args a) {
   using Cfg = Att2Cfg<HD>;
   constexpr int NS = Cfg::KV_STAGES;
   extern __shared__ uint8_t smem_raw[];
