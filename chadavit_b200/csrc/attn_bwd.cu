@@ -47,7 +47,7 @@ struct AttnBwdArgs {
 };
 
 template <int HD>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO, const AttnBwdArgs a) {
   using Cfg = BwdCfg<HD>;
   constexpr int NS = Cfg::QDO_STAGES;
@@ -79,7 +79,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     tma_prefetch_desc(&tmDO);
     mbar_init(kv_full, 1); mbar_init(kv_empty, 1);
     for (int i = 0; i < NS; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
-    mbar_init(s_full, 1); mbar_init(dp_full, 1); mbar_init(p_ready, 128); mbar_init(dq_full, 1); mbar_init(dq_drained, 128);
+    mbar_init(s_full, 1); mbar_init(dp_full, 1); mbar_init(p_ready, 256); mbar_init(dq_full, 1); mbar_init(dq_drained, 256);
     mbar_init(dkv_full, 1);
     fence_barrier_init();
   }
@@ -156,7 +156,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           // dV += P^T dO   (A = P^T in TMEM; B = dO tile read MN-major: N = HD, K = q)
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
-            umma_ts(tmem_base + Cfg::COL_DV, tmem_base + Cfg::COL_S + kk * 8,
+            umma_ts(tmem_base + Cfg::COL_DV, tmem_base + Cfg::COL_S + (kk < 4 ? kk * 8 : 64 + (kk - 4) * 8),
                     umma_smem_desc(do_addr + kk * 16 * Cfg::CHUNK * 2, Cfg::CHUNK_BYTES, Cfg::SBO, Cfg::SWZ), idesc_dv,
                     (i > 0 || kk > 0) ? 1u : 0u);
           // dK += dS^T Q   (A = dS^T smem K-major: two [128x64] sub-tiles; B = Q tile MN-major)
@@ -179,9 +179,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     }
   } else {
     // ------------------------------------------------------------------ softmax-backward / dQ drain / dK,dV epilogue
+    // 8 warps: two per TMEM lane quarter; `half` selects which 64 of the 128 q columns (and which 16-column chunks of the
+    // dQ / dK / dV accumulators) this warp handles — the backward softmax is element-wise, so no row reduction is split.
     const int q4 = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int r = q4 * 32 + lane;               // kv row of this thread inside the tile; also q row when draining dQ
-    const int tid128 = (warp - 2) * 32 + lane;  // 0..127
+    const int tid256 = (warp - 2) * 32 + lane;  // 0..255
     const uint32_t lane_addr = tmem_base + (uint32_t(q4 * 32) << 16);
     const float LOG2E = 1.4426950408889634f;
     uint32_t it = 0, wi = 0;
@@ -194,17 +197,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         const int q0 = wk.y + i * 128;
         // stage LSE / delta of this q tile (all 128 threads need all 128 values)
         {
-          const int t = q0 + tid128;
+          const int t = q0 + (tid256 & 127);
           const bool ok = t < wk.z;
-          sLSE[tid128] = ok ? a.lse[(long)head * a.T + t] * LOG2E : INFINITY;   // +inf -> p = 0 for rows past the sequence
-          sDelta[tid128] = ok ? a.delta[(long)head * a.T + t] : 0.f;
+          if (tid256 < 128) sLSE[tid256] = ok ? a.lse[(long)head * a.T + t] * LOG2E : INFINITY;   // +inf -> p = 0 past the sequence
+          else sDelta[tid256 - 128] = ok ? a.delta[(long)head * a.T + t] : 0.f;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         mbar_wait(s_full, it & 1);
         mbar_wait(dp_full, it & 1);
         tc_fence_after();
 #pragma unroll 1
-        for (int c4 = 0; c4 < 4; ++c4) {
+        for (int c4 = half * 2; c4 < half * 2 + 2; ++c4) {
           uint32_t sr[32], dpr[32];
           tmem_ld32(lane_addr + Cfg::COL_S + c4 * 32, sr);
           tmem_ld32(lane_addr + Cfg::COL_DP + c4 * 32, dpr);
@@ -220,7 +223,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             pp[j >> 1] = pack_bf16(p0, p1);
             dsp[j >> 1] = pack_bf16(d0, d1);
           }
-          tmem_st16(lane_addr + Cfg::COL_S + c4 * 16, pp);
+          // P^T (bf16 pairs) stays inside this warp's own half of the S region: q cols 0-63 -> TMEM cols 0..31, 64-127 -> 64..95
+          tmem_st16(lane_addr + Cfg::COL_S + (c4 < 2 ? c4 * 16 : 64 + (c4 - 2) * 16), pp);
           // dS^T row r, q columns [32*c4, 32*c4+32) -> sub-tile (c4>>1), 16B chunks 4*(c4&1) .. +3, 128B swizzle
           uint8_t* base = sDS + (c4 >> 1) * 16384 + r * 128;
 #pragma unroll
@@ -242,25 +246,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           float* dst = a.dq_acc + (long)t * a.D + head * HD;
 #pragma unroll
           for (int c = 0; c < HD; c += 32) {
-            if (HD - c >= 32) {
-              uint32_t o[32];
-              tmem_ld32(lane_addr + Cfg::COL_DP + c, o);
-              tmem_ld_wait();
-              if (ok) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                  atomicAdd(reinterpret_cast<float4*>(dst + c + j), make_float4(__uint_as_float(o[j]), __uint_as_float(o[j + 1]),
-                                                                               __uint_as_float(o[j + 2]), __uint_as_float(o[j + 3])));
-              }
-            } else {
+            const int cc = c + half * 16;
+            if (cc < HD) {
               uint32_t o[16];
-              tmem_ld16(lane_addr + Cfg::COL_DP + c, o);
+              tmem_ld16(lane_addr + Cfg::COL_DP + cc, o);
               tmem_ld_wait();
               if (ok) {
 #pragma unroll
                 for (int j = 0; j < 16; j += 4)
-                  atomicAdd(reinterpret_cast<float4*>(dst + c + j), make_float4(__uint_as_float(o[j]), __uint_as_float(o[j + 1]),
-                                                                               __uint_as_float(o[j + 2]), __uint_as_float(o[j + 3])));
+                  atomicAdd(reinterpret_cast<float4*>(dst + cc + j), make_float4(__uint_as_float(o[j]), __uint_as_float(o[j + 1]),
+                                                                                __uint_as_float(o[j + 2]), __uint_as_float(o[j + 3])));
               }
             }
           }
@@ -279,7 +274,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           __nv_bfloat16* dst = which ? dv_dst : dk_dst;
           const uint32_t col = which ? Cfg::COL_DV : Cfg::COL_DK;
 #pragma unroll
-          for (int c = 0; c < HD; c += 16) {
+          for (int c0 = 0; c0 < HD; c0 += 32) {
+            const int c = c0 + half * 16;
+            if (c >= HD) continue;
             uint32_t o[16];
             tmem_ld16(lane_addr + col + c, o);
             tmem_ld_wait();
@@ -350,7 +347,7 @@ static int launch_bwd(const void* qkv, const void* dO, const AttnBwdArgs& a, cud
     if (make_tmap(&td, dO, 2, dims, strides, box, Cfg::SWZ)) return 1;
   }
   const int grid = a.n_work < num_sms() ? a.n_work : num_sms();
-  attn_bwd_kernel<HD><<<grid, 192, Cfg::SMEM_BYTES, stream>>>(tq, td, a);
+  attn_bwd_kernel<HD><<<grid, 320, Cfg::SMEM_BYTES, stream>>>(tq, td, a);
   CB_CUDA(cudaGetLastError());
   return 0;
 }
