@@ -25,7 +25,8 @@ struct BwdCfg {
   static constexpr int SBO = 8 * CHUNK * 2;
   static constexpr int QDO_STAGES = HD <= 96 ? 2 : 1;
   static constexpr int DS_BYTES = 128 * 128 * 2;  // two [128 x 64] 128B-swizzled sub-tiles
-  static constexpr int SMEM_BYTES = TILE_BYTES * (2 + 2 * QDO_STAGES) + DS_BYTES + 1024 /*lse,delta*/ + 1024 + 256;
+  static constexpr int DQ_STAGE_BYTES = 8 * 2 * 2048;   // dQ drain: per warp 2 x (32 rows x 64 B) staging slabs for TMA reduce-add
+  static constexpr int SMEM_BYTES = TILE_BYTES * (2 + 2 * QDO_STAGES) + DS_BYTES + DQ_STAGE_BYTES + 1024 /*lse,delta*/ + 1024 + 256;
   static constexpr int COL_S = 0, COL_DP = 128, COL_DK = 256, COL_DV = 384;
 };
 
@@ -48,7 +49,8 @@ struct AttnBwdArgs {
 
 template <int HD>
 __global__ void __launch_bounds__(320, 1)
-attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO, const AttnBwdArgs a) {
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                const __grid_constant__ CUtensorMap tmDQ, const AttnBwdArgs a) {
   using Cfg = BwdCfg<HD>;
   constexpr int NS = Cfg::QDO_STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -58,7 +60,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   uint8_t* sQ = sV + Cfg::TILE_BYTES;                  // [NS]
   uint8_t* sDO = sQ + NS * Cfg::TILE_BYTES;            // [NS]
   uint8_t* sDS = sDO + NS * Cfg::TILE_BYTES;           // dS^T
-  float* sLSE = reinterpret_cast<float*>(sDS + Cfg::DS_BYTES);
+  uint8_t* sDQ = sDS + Cfg::DS_BYTES;                  // dQ staging slabs
+  float* sLSE = reinterpret_cast<float*>(sDQ + Cfg::DQ_STAGE_BYTES);
   float* sDelta = sLSE + 128;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + 128);
   uint64_t* kv_full = bars + 0;
@@ -77,6 +80,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQKV);
     tma_prefetch_desc(&tmDO);
+    tma_prefetch_desc(&tmDQ);
     mbar_init(kv_full, 1); mbar_init(kv_empty, 1);
     for (int i = 0; i < NS; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
     mbar_init(s_full, 1); mbar_init(dp_full, 1); mbar_init(p_ready, 256); mbar_init(dq_full, 1); mbar_init(dq_drained, 256);
@@ -187,7 +191,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     const int tid256 = (warp - 2) * 32 + lane;  // 0..255
     const uint32_t lane_addr = tmem_base + (uint32_t(q4 * 32) << 16);
     const float LOG2E = 1.4426950408889634f;
-    uint32_t it = 0, wi = 0;
+    uint32_t it = 0, wi = 0, dq_slab = 0;
     for (int w = blockIdx.x; w < a.n_work; w += gridDim.x, ++wi) {
       const int4 wk = a.work[w];
       const int head = wk.w;
@@ -237,13 +241,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         fence_proxy_async();   // generic-proxy smem writes (dS^T) -> visible to the tensor-core (async) proxy
         tc_fence_before();
         mbar_arrive(p_ready);
-        // ---- drain dQ_i (rows = q) with fp32 atomics
+        // ---- drain dQ_i (rows = q): TMEM -> 64B-swizzled smem slab -> TMA reduce-add (fp32) into the dQ accumulator.
+        // Per-thread REDs would scatter 32 rows per instruction (ncu: the kernel was bound by L2 atomic transactions);
+        // the bulk reduction moves whole 64-byte row segments.  Rows past the sequence end carry exact zeros (P = 0 there).
         mbar_wait(dq_full, it & 1);
         tc_fence_after();
         {
-          const int t = q0 + r;
-          const bool ok = t < wk.z;
-          float* dst = a.dq_acc + (long)t * a.D + head * HD;
+          uint8_t* my = sDQ + (warp - 2) * 4096;
 #pragma unroll
           for (int c = 0; c < HD; c += 32) {
             const int cc = c + half * 16;
@@ -251,12 +255,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
               uint32_t o[16];
               tmem_ld16(lane_addr + Cfg::COL_DP + cc, o);
               tmem_ld_wait();
-              if (ok) {
+              uint8_t* slab = my + (dq_slab & 1) * 2048;
+              if (lane == 0) tma_store_wait_read<1>();      // the slab used two reductions ago has been read
+              __syncwarp();
 #pragma unroll
-                for (int j = 0; j < 16; j += 4)
-                  atomicAdd(reinterpret_cast<float4*>(dst + cc + j), make_float4(__uint_as_float(o[j]), __uint_as_float(o[j + 1]),
-                                                                                __uint_as_float(o[j + 2]), __uint_as_float(o[j + 3])));
-              }
+              for (int k = 0; k < 4; ++k)
+                *reinterpret_cast<uint4*>(slab + lane * 64 + ((k ^ ((lane >> 1) & 3)) << 4)) = make_uint4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) { tma_reduce_add_2d(&tmDQ, slab, head * HD + cc, q0 + q4 * 32); tma_store_commit(); }
+              ++dq_slab;
             }
           }
         }
@@ -291,6 +299,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       }
       tc_fence_before();
     }
+    if (lane == 0) tma_store_wait_all<0>();
   }
   tc_fence_before();
   __syncthreads();
@@ -346,8 +355,15 @@ static int launch_bwd(const void* qkv, const void* dO, const AttnBwdArgs& a, cud
     uint32_t box[2] = {(uint32_t)Cfg::CHUNK, 128};
     if (make_tmap(&td, dO, 2, dims, strides, box, Cfg::SWZ)) return 1;
   }
+  CUtensorMap tdq;
+  {
+    uint64_t dims[2] = {(uint64_t)a.D, (uint64_t)a.T};
+    uint64_t strides[1] = {(uint64_t)a.D * 4};
+    uint32_t box[2] = {16, 32};
+    if (make_tmap(&tdq, a.dq_acc, 2, dims, strides, box, 2, 4)) return 1;
+  }
   const int grid = a.n_work < num_sms() ? a.n_work : num_sms();
-  attn_bwd_kernel<HD><<<grid, 320, Cfg::SMEM_BYTES, stream>>>(tq, td, a);
+  attn_bwd_kernel<HD><<<grid, 320, Cfg::SMEM_BYTES, stream>>>(tq, td, tdq, a);
   CB_CUDA(cudaGetLastError());
   return 0;
 }
