@@ -25,7 +25,8 @@ struct BwdCfg {
   static constexpr int SBO = 8 * CHUNK * 2;
   static constexpr int QDO_STAGES = HD <= 96 ? 2 : 1;
   static constexpr int DS_BYTES = 128 * 128 * 2;  // two [128 x 64] 128B-swizzled sub-tiles
-  static constexpr int DQ_STAGE_BYTES = 8 * 2 * 2048;   // dQ drain: per warp 2 x (32 rows x 64 B) staging slabs for TMA reduce-add
+  static constexpr int DQ_SLABS = (HD + 31) / 32;       // 16-column dQ chunks handled by one epilogue warp
+  static constexpr int DQ_STAGE_BYTES = 8 * DQ_SLABS * 2048;   // dQ drain: per warp DQ_SLABS x (32 rows x 64 B) slabs for TMA reduce-add
   static constexpr int SMEM_BYTES = TILE_BYTES * (2 + 2 * QDO_STAGES) + DS_BYTES + DQ_STAGE_BYTES + 1024 /*lse,delta*/ + 1024 + 256;
   static constexpr int COL_S = 0, COL_DP = 128, COL_DK = 256, COL_DV = 384;
 };
@@ -191,21 +192,24 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     const int tid256 = (warp - 2) * 32 + lane;  // 0..255
     const uint32_t lane_addr = tmem_base + (uint32_t(q4 * 32) << 16);
     const float LOG2E = 1.4426950408889634f;
-    uint32_t it = 0, wi = 0, dq_slab = 0;
+    uint32_t it = 0, wi = 0;
     for (int w = blockIdx.x; w < a.n_work; w += gridDim.x, ++wi) {
       const int4 wk = a.work[w];
       const int head = wk.w;
       const int nq = (wk.z - wk.y + 127) / 128;
       const bool kv_ok = wk.x + r < wk.z;
+      // LSE (threads 0-127) / delta (threads 128-255) of a q tile: loaded into a register one iteration ahead (the global
+      // latency hides under the wait for the dV/dK/dQ MMAs), published to smem at the start of the iteration.
+      const float* stage_src = (tid256 < 128 ? a.lse : a.delta) + (long)head * a.T;
+      auto stage_load = [&](int i_) -> float {
+        const int t = wk.y + i_ * 128 + (tid256 & 127);
+        if (t < wk.z) return tid256 < 128 ? __ldg(stage_src + t) * LOG2E : __ldg(stage_src + t);
+        return tid256 < 128 ? INFINITY : 0.f;            // +inf -> p = 0 for q rows past the sequence
+      };
+      float stage_val = stage_load(0);
       for (int i = 0; i < nq; ++i, ++it) {
         const int q0 = wk.y + i * 128;
-        // stage LSE / delta of this q tile (all 128 threads need all 128 values)
-        {
-          const int t = q0 + (tid256 & 127);
-          const bool ok = t < wk.z;
-          if (tid256 < 128) sLSE[tid256] = ok ? a.lse[(long)head * a.T + t] * LOG2E : INFINITY;   // +inf -> p = 0 past the sequence
-          else sDelta[tid256 - 128] = ok ? a.delta[(long)head * a.T + t] : 0.f;
-        }
+        if (tid256 < 128) sLSE[tid256] = stage_val; else sDelta[tid256 - 128] = stage_val;
         asm volatile("bar.sync 1, 256;" ::: "memory");
         mbar_wait(s_full, it & 1);
         mbar_wait(dp_full, it & 1);
@@ -244,28 +248,33 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         // ---- drain dQ_i (rows = q): TMEM -> 64B-swizzled smem slab -> TMA reduce-add (fp32) into the dQ accumulator.
         // Per-thread REDs would scatter 32 rows per instruction (ncu: the kernel was bound by L2 atomic transactions);
         // the bulk reduction moves whole 64-byte row segments.  Rows past the sequence end carry exact zeros (P = 0 there).
+        if (i + 1 < nq) stage_val = stage_load(i + 1);
+        if (lane == 0) tma_store_wait_read<0>();          // last iteration's reductions have long finished reading the slabs
         mbar_wait(dq_full, it & 1);
         tc_fence_after();
         {
-          uint8_t* my = sDQ + (warp - 2) * 4096;
+          uint8_t* my = sDQ + (warp - 2) * (Cfg::DQ_SLABS * 2048);
+          uint32_t o[Cfg::DQ_SLABS][16];
 #pragma unroll
-          for (int c = 0; c < HD; c += 32) {
-            const int cc = c + half * 16;
-            if (cc < HD) {
-              uint32_t o[16];
-              tmem_ld16(lane_addr + Cfg::COL_DP + cc, o);
-              tmem_ld_wait();
-              uint8_t* slab = my + (dq_slab & 1) * 2048;
-              if (lane == 0) tma_store_wait_read<1>();      // the slab used two reductions ago has been read
-              __syncwarp();
+          for (int k = 0; k < Cfg::DQ_SLABS; ++k)
+            if (k * 32 + half * 16 < HD) tmem_ld16(lane_addr + Cfg::COL_DP + k * 32 + half * 16, o[k]);
+          tmem_ld_wait();
+          __syncwarp();
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                *reinterpret_cast<uint4*>(slab + lane * 64 + ((k ^ ((lane >> 1) & 3)) << 4)) = make_uint4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
-              fence_proxy_async();
-              __syncwarp();
-              if (lane == 0) { tma_reduce_add_2d(&tmDQ, slab, head * HD + cc, q0 + q4 * 32); tma_store_commit(); }
-              ++dq_slab;
+          for (int k = 0; k < Cfg::DQ_SLABS; ++k)
+            if (k * 32 + half * 16 < HD) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<uint4*>(my + k * 2048 + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
+                    make_uint4(o[k][4 * j], o[k][4 * j + 1], o[k][4 * j + 2], o[k][4 * j + 3]);
             }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < Cfg::DQ_SLABS; ++k)
+              if (k * 32 + half * 16 < HD) tma_reduce_add_2d(&tmDQ, my + k * 2048, head * HD + k * 32 + half * 16, q0 + q4 * 32);
+            tma_store_commit();
           }
         }
         tc_fence_before();
