@@ -282,8 +282,7 @@ class ChAdaViT(nn.Module):
         dz2, dz2h = ops.layernorm_bwd(dxo, z2, a.v32(pre + "norm2.weight"), m2, r2, dgamma=g("norm2.weight"), dbeta=g("norm2.bias"),
                                       dcolsum=g("linear2.bias"), want_bf16=True)
         ops.gemm(dz2h, hid, a_mn=True, b_mn=True, flags=A, out=g("linear2.weight"), k_splits=sk(mt(D) * (FFN_DIM // 256)))
-        dh = ops.gemm(dz2h, a.v16(pre + "linear2.weight"), b_mn=True, aux=hid, flags=ops.EPI_RELU_MASK)
-        ops.colsum(dh, g("linear1.bias"))
+        dh = ops.gemm(dz2h, a.v16(pre + "linear2.weight"), b_mn=True, aux=hid, flags=ops.EPI_RELU_MASK, colsum=g("linear1.bias"))
         ops.gemm(dh, y, a_mn=True, b_mn=True, flags=A, out=g("linear1.weight"), k_splits=sk(mt(FFN_DIM) * mt(D)))
         dy = ops.gemm(dh, a.v16(pre + "linear1.weight"), b_mn=True, aux=dz2, flags=ops.EPI_RESIDUAL_F32 | ops.EPI_OUT_F32)
         # y = LN1(z1), z1 = x + att Wo^T + bo      (second use of norm1: gradients accumulate)

@@ -222,7 +222,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
           for (int i = 0; i < 8; ++i) { acc[i].x *= g.alpha; acc[i].y *= g.alpha; acc[i].z *= g.alpha; acc[i].w *= g.alpha; }
         }
-        if (!col_ok || nrows <= 0) continue;
+        if ((!col_ok || nrows <= 0) && !(mode == EM_BF16_MASK && g.colsum)) continue;   // (shuffles below need the full warp)
         if (mode == EM_BF16) {
           const float lo = (g.flags & CB_EPI_RELU) ? 0.f : -INFINITY;
           __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(g.C) + row0 * g.ldc + gcol;
@@ -236,14 +236,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         } else if (mode == EM_BF16_MASK) {
           __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(g.C) + row0 * g.ldc + gcol;
+          float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             if (i < nrows) {
               const float4 v = acc[i];
               const float2 f0 = unpack_bf16(m16[i].x), f1 = unpack_bf16(m16[i].y);
-              *reinterpret_cast<uint2*>(dst + (long)i * 4 * g.ldc) =
-                  make_uint2(pack_bf16(f0.x > 0.f ? v.x : 0.f, f0.y > 0.f ? v.y : 0.f), pack_bf16(f1.x > 0.f ? v.z : 0.f, f1.y > 0.f ? v.w : 0.f));
+              const float o0 = f0.x > 0.f ? v.x : 0.f, o1 = f0.y > 0.f ? v.y : 0.f, o2 = f1.x > 0.f ? v.z : 0.f, o3 = f1.y > 0.f ? v.w : 0.f;
+              cs.x += o0; cs.y += o1; cs.z += o2; cs.w += o3;
+              *reinterpret_cast<uint2*>(dst + (long)i * 4 * g.ldc) = make_uint2(pack_bf16(o0, o1), pack_bf16(o2, o3));
             }
+          }
+          if (g.colsum) {   // fused bias gradient: sum the 32 rows of this slab (4 lanes share a column chunk), one vector RED
+#pragma unroll
+            for (int o = 8; o <= 16; o <<= 1) {
+              cs.x += __shfl_xor_sync(0xffffffffu, cs.x, o); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, o);
+              cs.z += __shfl_xor_sync(0xffffffffu, cs.z, o); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, o);
+            }
+            if (rb_row == 0) atomicAdd(reinterpret_cast<float4*>(g.colsum + gcol), cs);
           }
         } else if (mode == EM_F32) {
           float* dst = reinterpret_cast<float*>(g.C) + row0 * g.ldc + gcol;
@@ -373,8 +383,10 @@ int gemm_run(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn,
 
 extern "C" int cb_gemm_bf16(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* C, int ldc, int M,
                             int N, int K, const float* bias, const void* aux, int ld_aux, int flags, float alpha,
-                            int k_splits, void* stream) {
+                            int k_splits, float* colsum, void* stream) {
   cb::GemmArgs g{};
+  g.colsum = colsum;
+  CB_CHECK(!colsum || ((flags & CB_EPI_RELU_MASK) && !(flags & (CB_EPI_OUT_F32 | CB_EPI_ATOMIC))), "cb_gemm_bf16: colsum is only fused into the ReLU-mask epilogue");
   g.M = M; g.N = N; g.K = K; g.k_splits = k_splits; g.C = C; g.ldc = ldc; g.bias = bias;
   g.aux = reinterpret_cast<const __nv_bfloat16*>(aux); g.ld_aux = ld_aux; g.flags = flags; g.alpha = alpha;
   CB_CHECK(!(flags & CB_EPI_TOKENIZE), "cb_gemm_bf16: use cb_tokenize_fwd for the tokenizer epilogue");

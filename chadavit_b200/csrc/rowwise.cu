@@ -173,22 +173,33 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
 }
 
 // ------------------------------------------------------------------------------------------------ column sums
-// out[n] += sum_t x[t, n]   (bias gradients of in_proj / linear1).  grid (row chunks, column groups of 2048).
+// out[n] += sum_t x[t, n]   (bias gradients of in_proj / linear1).  grid (row chunks, column groups of 2048 columns).
+// The 256 threads of a block are laid out as ncx column chunks (8 columns = one 16-byte load each) x nry rows, so narrow
+// matrices (N = 576 -> 72 chunks x 3 rows) still use the whole block; partial sums meet in smem, then one fp32 atomic per column.
 __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int T, int N, int ld,
                                                      int rows_per_block) {
-  const int c8 = (blockIdx.y * blockDim.x + threadIdx.x) * 8;
-  if (c8 >= N) return;
-  const int t0 = blockIdx.x * rows_per_block, t1 = min(T, t0 + rows_per_block);
-  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll 4
-  for (int t = t0; t < t1; ++t) {
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + (long)t * ld + c8));
-    const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+  __shared__ float red[2048];
+  const int ncols = min(N - blockIdx.y * 2048, 2048);
+  const int ncx = ncols / 8, nry = 256 / ncx;
+  for (int i = threadIdx.x; i < ncols; i += 256) red[i] = 0.f;
+  __syncthreads();
+  const int cx = threadIdx.x % ncx, ry = threadIdx.x / ncx;
+  if (ry < nry) {
+    const int c8 = blockIdx.y * 2048 + cx * 8;
+    const int t0 = blockIdx.x * rows_per_block, t1 = min(T, t0 + rows_per_block);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll 8
+    for (int t = t0 + ry; t < t1; t += nry) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + (long)t * ld + c8));
+      const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { const float2 f = unpack_bf16(uu[j]); acc[2 * j] += f.x; acc[2 * j + 1] += f.y; }
+      for (int j = 0; j < 4; ++j) { const float2 f = unpack_bf16(uu[j]); acc[2 * j] += f.x; acc[2 * j + 1] += f.y; }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&red[cx * 8 + j], acc[j]);
   }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) atomicAdd(out + c8 + j, acc[j]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < ncols; i += 256) atomicAdd(out + blockIdx.y * 2048 + i, red[i]);
 }
 
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long n) {
@@ -266,9 +277,9 @@ extern "C" int cb_layernorm_bwd(const float* dy, const float* x, const int* idx,
 extern "C" int cb_colsum_bf16(const void* x, int ld, float* out, int T, int N, void* stream) {
   CB_CHECK(T > 0 && N % 8 == 0 && ld % 8 == 0, "colsum: T=%d N=%d ld=%d", T, N, ld);
   const int col_groups = (N + 2047) / 2048;
-  int row_blocks = (num_sms() * 4 + col_groups - 1) / col_groups;
+  int row_blocks = (num_sms() * 8 + col_groups - 1) / col_groups;
   int rpb = (T + row_blocks - 1) / row_blocks;
-  if (rpb < 16) rpb = 16;
+  if (rpb < 32) rpb = 32;
   row_blocks = (T + rpb - 1) / rpb;
   colsum_kernel<<<dim3(row_blocks, col_groups), 256, 0, STREAM>>>(BF(x), out, T, N, ld, rpb);
   CB_CUDA(cudaGetLastError());

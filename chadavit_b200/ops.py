@@ -58,7 +58,7 @@ def sync_check() -> None:
 # ------------------------------------------------------------------------------------------------ GEMM
 def gemm(A: torch.Tensor, B: torch.Tensor, *, a_mn: bool = False, b_mn: bool = False, bias: Optional[torch.Tensor] = None,
          aux: Optional[torch.Tensor] = None, flags: int = 0, out: Optional[torch.Tensor] = None, alpha: float = 1.0,
-         k_splits: int = 1) -> torch.Tensor:
+         k_splits: int = 1, colsum: Optional[torch.Tensor] = None) -> torch.Tensor:
     """C[M,N] (+)= alpha * op(A) op(B)^T.  a_mn/b_mn: the operand is stored [K, M] / [K, N] (MN-major)."""
     assert A.dtype == bf16 and B.dtype == bf16 and A.dim() == 2 and B.dim() == 2
     assert A.stride(1) == 1 and B.stride(1) == 1
@@ -69,7 +69,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
         out = torch.empty(M, N, device=A.device, dtype=torch.float32 if flags & (EPI_OUT_F32 | EPI_ATOMIC) else bf16)
     assert out.shape == (M, N) and out.stride(1) == 1
     _call("cb_gemm_bf16", _p(A), A.stride(0), int(a_mn), _p(B), B.stride(0), int(b_mn), _p(out), out.stride(0), M, N, K,
-          _p(bias), _p(aux), aux.stride(0) if aux is not None else 0, flags, float(alpha), k_splits, _stream(), work=2.0 * M * N * K)
+          _p(bias), _p(aux), aux.stride(0) if aux is not None else 0, flags, float(alpha), k_splits, _p(colsum), _stream(), work=2.0 * M * N * K)
     return out
 
 

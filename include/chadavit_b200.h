@@ -48,10 +48,12 @@ int cb_sync_check(void* stream);
  * row-major (lda).  Same for B / b_mn with [N,K] vs [K,N].  Replaces every nn.Linear / F.linear on the path
  * (MHA in/out projection chada_vit.py:106, linear1/linear2 :115, DINOHead.mlp / last_layer dino.py:65-81) and
  * their autograd backward products.  N, lda, ldb multiples of 8; MN-major dims multiples of 32.
+ * colsum (optional, only with CB_EPI_RELU_MASK): fp32 [N] += column sums of the stored C, i.e. the bias gradient of
+ * linear1 fused into the product that makes d(hidden).
  */
 int cb_gemm_bf16(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* C, int ldc, int M, int N,
                  int K, const float* bias, const void* aux, int ld_aux, int flags, float alpha, int k_splits,
-                 void* stream);
+                 float* colsum, void* stream);
 
 /*
  * TokenLearner + channel_aware_tokenization (chada_vit.py:118-134, 219-270) on the packed layout.

@@ -65,8 +65,11 @@ def test_gemm_epilogues():
     assert (C - (ref + res32)).abs().max().item() < 1e-2
     C = ops.gemm(A, B, bias=bias, flags=ops.EPI_RELU)
     assert (C.float() - ref.relu()).abs().max().item() < 0.05
-    C = ops.gemm(A, B, aux=res, flags=ops.EPI_RELU_MASK)
-    assert (C.float() - _ref(A, B, False, False) * (res.float() > 0)).abs().max().item() < 0.05
+    cs = torch.ones(N, device="cuda")
+    C = ops.gemm(A, B, aux=res, flags=ops.EPI_RELU_MASK, colsum=cs)
+    masked = _ref(A, B, False, False) * (res.float() > 0)
+    assert (C.float() - masked).abs().max().item() < 0.05
+    assert (cs - 1 - masked.sum(0)).abs().max().item() < 0.05          # fused bias-gradient column sums
     # split-K atomic accumulation into an existing fp32 buffer
     acc = torch.ones(M, N, device="cuda")
     ops.gemm(A, B, flags=ops.EPI_ATOMIC, out=acc, k_splits=7)
