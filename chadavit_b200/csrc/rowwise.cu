@@ -172,6 +172,143 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
   }
 }
 
+// ---- D in {64,128,192,256}: 8 lanes per row, 4 rows per warp (all 32 lanes busy at D=192, 4x the bytes in flight per warp)
+__device__ __forceinline__ float group8_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2); v += __shfl_xor_sync(0xffffffffu, v, 4);
+  return v;
+}
+
+template <int NJ>
+__global__ void __launch_bounds__(256) layernorm_fwd_g8_kernel(const float* __restrict__ x, const int* __restrict__ in_idx,
+                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                               __nv_bfloat16* __restrict__ y, float* __restrict__ y32,
+                                                               float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows, float eps) {
+  constexpr int D = NJ * 64;
+  const int lane = threadIdx.x & 31, grp = lane >> 3, gl = lane & 7;
+  const int wg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nwg = gridDim.x * (blockDim.x >> 5);
+  float gg[NJ][8], bb[NJ][8];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) { ld8(gamma + j * 64 + gl * 8, gg[j]); ld8(beta + j * 64 + gl * 8, bb[j]); }
+  for (int rb = wg * 4; rb < rows; rb += nwg * 4) {
+    const int r = rb + grp;
+    const bool ok = r < rows;
+    const long src = ok ? (in_idx ? in_idx[r] : r) : 0;
+    float v[NJ][8];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      if (ok) ld8(x + src * D + j * 64 + gl * 8, v[j]);
+      else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[j][k] = 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s += v[j][k];
+    }
+    const float mean = group8_sum(s) * (1.f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { const float d = v[j][k] - mean; q += d * d; }
+    const float rstd = rsqrtf(group8_sum(q) * (1.f / D) + eps);
+    if (ok) {
+      if (gl == 0) { if (mean_out) mean_out[r] = mean; if (rstd_out) rstd_out[r] = rstd; }
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        float o[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = (v[j][k] - mean) * rstd * gg[j][k] + bb[j][k];
+        if (y) st8_bf16(y + (long)r * D + j * 64 + gl * 8, o);
+        if (y32) st8(y32 + (long)r * D + j * 64 + gl * 8, o);
+      }
+    }
+  }
+}
+
+template <int NJ>
+__global__ void __launch_bounds__(256) layernorm_bwd_g8_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                               const int* __restrict__ idx, const float* __restrict__ gamma,
+                                                               const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                                                               const float* __restrict__ dres, float* __restrict__ dx32,
+                                                               __nv_bfloat16* __restrict__ dx16, float* __restrict__ dgamma,
+                                                               float* __restrict__ dbeta, float* __restrict__ dcolsum, int rows) {
+  constexpr int D = NJ * 64;
+  __shared__ float red[3 * D];
+  const int lane = threadIdx.x & 31, grp = lane >> 3, gl = lane & 7;
+  const int wg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nwg = gridDim.x * (blockDim.x >> 5);
+  for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  float ag[NJ][8], ab[NJ][8], ac[NJ][8], gam[NJ][8];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    ld8(gamma + j * 64 + gl * 8, gam[j]);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { ag[j][k] = 0.f; ab[j][k] = 0.f; ac[j][k] = 0.f; }
+  }
+  for (int rb = wg * 4; rb < rows; rb += nwg * 4) {
+    const int r = rb + grp;
+    const bool ok = r < rows;
+    const long xi = ok ? (idx ? idx[r] : r) : 0;
+    const float mean = ok ? mean_in[r] : 0.f, rstd = ok ? rstd_in[r] : 0.f;
+    float xh[NJ][8], g[NJ][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      float d[8];
+      if (ok) { ld8(dy + (long)r * D + j * 64 + gl * 8, d); ld8(x + xi * D + j * 64 + gl * 8, xh[j]); }
+      else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { d[k] = 0.f; xh[j][k] = 0.f; }
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        xh[j][k] = (xh[j][k] - mean) * rstd;
+        ag[j][k] += d[k] * xh[j][k]; ab[j][k] += d[k];
+        g[j][k] = d[k] * gam[j][k];
+        s1 += g[j][k]; s2 += g[j][k] * xh[j][k];
+      }
+    }
+    s1 = group8_sum(s1) * (1.f / D); s2 = group8_sum(s2) * (1.f / D);
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      float o[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { o[k] = rstd * (g[j][k] - s1 - xh[j][k] * s2); ac[j][k] += o[k]; }
+      if (ok) {
+        if (dres) {
+          float e[8];
+          ld8(dres + xi * D + j * 64 + gl * 8, e);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o[k] += e[k];
+        }
+        if (dx32) st8(dx32 + xi * D + j * 64 + gl * 8, o);
+        if (dx16) st8_bf16(dx16 + xi * D + j * 64 + gl * 8, o);
+      }
+    }
+  }
+  // fold the 4 row groups of the warp, then the warps of the block, then one atomic per column per block
+#pragma unroll
+  for (int j = 0; j < NJ; ++j)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float a = ag[j][k], b = ab[j][k], c = ac[j][k];
+      a += __shfl_xor_sync(0xffffffffu, a, 8); a += __shfl_xor_sync(0xffffffffu, a, 16);
+      b += __shfl_xor_sync(0xffffffffu, b, 8); b += __shfl_xor_sync(0xffffffffu, b, 16);
+      c += __shfl_xor_sync(0xffffffffu, c, 8); c += __shfl_xor_sync(0xffffffffu, c, 16);
+      if (grp == 0) {
+        const int col = j * 64 + gl * 8 + k;
+        atomicAdd(&red[col], a); atomicAdd(&red[D + col], b); atomicAdd(&red[2 * D + col], c);
+      }
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    if (dgamma) atomicAdd(dgamma + i, red[i]);
+    if (dbeta) atomicAdd(dbeta + i, red[D + i]);
+    if (dcolsum) atomicAdd(dcolsum + i, red[2 * D + i]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ column sums
 // out[n] += sum_t x[t, n]   (bias gradients of in_proj / linear1).  grid (row chunks, column groups of 2048 columns).
 // The 256 threads of a block are laid out as ncx column chunks (8 columns = one 16-byte load each) x nry rows, so narrow
@@ -254,7 +391,12 @@ extern "C" int cb_layernorm_fwd(const float* x, const int* in_idx, const float* 
   int blocks = (rows + 7) / 8;
   if (blocks > num_sms() * 8) blocks = num_sms() * 8;
 #define LNF(N) layernorm_fwd_kernel<N><<<blocks, 256, 0, STREAM>>>(x, in_idx, gamma, beta, BFM(y), y_f32, mean, rstd, rows, D, eps)
-  if (D <= 256) LNF(1); else if (D <= 512) LNF(2); else LNF(4);
+#define LNFG(N) layernorm_fwd_g8_kernel<N><<<gblocks, 256, 0, STREAM>>>(x, in_idx, gamma, beta, BFM(y), y_f32, mean, rstd, rows, eps)
+  int gblocks = (rows + 31) / 32;
+  if (gblocks > num_sms() * 8) gblocks = num_sms() * 8;
+  if (D == 64) LNFG(1); else if (D == 128) LNFG(2); else if (D == 192) LNFG(3); else if (D == 256) LNFG(4);
+  else if (D <= 256) LNF(1); else if (D <= 512) LNF(2); else LNF(4);
+#undef LNFG
 #undef LNF
   CB_CUDA(cudaGetLastError());
   return 0;
@@ -268,7 +410,12 @@ extern "C" int cb_layernorm_bwd(const float* dy, const float* x, const int* idx,
   int blocks = (rows + 7) / 8;
   if (blocks > num_sms() * 4) blocks = num_sms() * 4;
 #define LNB(N) layernorm_bwd_kernel<N><<<blocks, 256, 3 * D * sizeof(float), STREAM>>>(dy, x, idx, gamma, mean, rstd, dres, dx_f32, BFM(dx_bf16), dgamma, dbeta, dcolsum, rows, D)
-  if (D <= 256) LNB(1); else if (D <= 512) LNB(2); else LNB(4);
+#define LNBG(N) layernorm_bwd_g8_kernel<N><<<gblocks, 256, 0, STREAM>>>(dy, x, idx, gamma, mean, rstd, dres, dx_f32, BFM(dx_bf16), dgamma, dbeta, dcolsum, rows)
+  int gblocks = (rows + 31) / 32;
+  if (gblocks > num_sms() * 4) gblocks = num_sms() * 4;
+  if (D == 64) LNBG(1); else if (D == 128) LNBG(2); else if (D == 192) LNBG(3); else if (D == 256) LNBG(4);
+  else if (D <= 256) LNB(1); else if (D <= 512) LNB(2); else LNB(4);
+#undef LNBG
 #undef LNB
   CB_CUDA(cudaGetLastError());
   return 0;

@@ -11,7 +11,7 @@ def _rand(shape, seed, scale=1.0, dtype=torch.bfloat16):
     return (torch.randn(shape, generator=g) * scale).to(dtype).cuda()
 
 
-@pytest.mark.parametrize("D", [32, 192, 768])
+@pytest.mark.parametrize("D", [32, 64, 192, 256, 768])
 def test_layernorm_fwd_bwd(D):
     from chadavit_b200 import ops
     T = 1237
