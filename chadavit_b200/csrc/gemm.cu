@@ -163,8 +163,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       // accumulator wait) and the TMEM read of slab s+1 is issued right after slab s was staged, under its math/stores.
       const bool has_bias = g.bias != nullptr && split == 0 && mode != EM_BF16_MASK;
       float4 bias_next = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (has_bias && last_slab >= 0 && n0 + half * 32 + rb_chunk * 4 < g.N)
+      float biasl_next = 0.f;                         // EM_BF16: bias of column (slab start + lane)
+      if (mode == EM_BF16) {
+        if (has_bias && last_slab >= 0 && n0 + half * 32 + lane < g.N) biasl_next = __ldg(g.bias + n0 + half * 32 + lane);
+      } else if (has_bias && last_slab >= 0 && n0 + half * 32 + rb_chunk * 4 < g.N) {
         bias_next = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + half * 32 + rb_chunk * 4));
+      }
       mbar_wait(&acc_full[buf], aph);
       tc_fence_after();
       if (last_slab < 0) {   // nothing to do for this warp in this tile: still release the accumulator
@@ -183,7 +187,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int gcol = n0 + c + rb_chunk * 4;
         const bool col_ok = gcol < g.N;
         const float4 bias4 = bias_next;
-        if (has_bias && sl + 2 < n_slabs && gcol + 64 < g.N) bias_next = __ldg(reinterpret_cast<const float4*>(g.bias + gcol + 64));
+        if (mode != EM_BF16 && has_bias && sl + 2 < n_slabs && gcol + 64 < g.N) bias_next = __ldg(reinterpret_cast<const float4*>(g.bias + gcol + 64));
         // accumulator-independent operands (ReLU mask / fp32 residual) are requested before the TMEM wait
         uint2 m16[8];
         float4 res[8];
@@ -204,6 +208,38 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         tmem_ld_wait();
         if (sl == last_slab) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&acc_empty[buf]); }
+        if (mode == EM_BF16) {
+          // bf16 outputs: bias (+ReLU) and the bf16 rounding happen in the thread=row layout (the bias of column c+lane
+          // lives in lane `lane`, broadcast by shuffles), so only 64 B per row go through the smem slab (half the traffic
+          // of staging fp32: ncu showed the L1TEX/smem pipe as the busiest unit of these write-heavy GEMMs).
+          const float bl = biasl_next;
+          if (has_bias && sl + 2 < n_slabs && n0 + c + 64 + lane < g.N) biasl_next = __ldg(g.bias + n0 + c + 64 + lane);
+          const float lo = (g.flags & CB_EPI_RELU) ? 0.f : -INFINITY;
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const float b0 = __shfl_sync(0xffffffffu, bl, j), b1 = __shfl_sync(0xffffffffu, bl, j + 1);
+            pk[j >> 1] = pack_bf16(fmaxf(fmaf(__uint_as_float(r[j]), g.alpha, b0), lo), fmaxf(fmaf(__uint_as_float(r[j + 1]), g.alpha, b1), lo));
+          }
+          uint8_t* srow64 = slab + lane * 64;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            *reinterpret_cast<uint4*>(srow64 + ((k ^ ((lane >> 1) & 3)) << 4)) = make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
+          __syncwarp();
+          if (sl + 2 < n_slabs) tmem_ld32(t_addr + c + 64, r);   // next slab's accumulator, in flight during the stores below
+          const int ch = lane & 3;
+          const int gcol8 = n0 + c + ch * 8;
+          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(g.C) + gcol8;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rl = i * 8 + (lane >> 2);
+            const long grow = (long)m0 + q * 32 + rl;
+            const uint4 val = *reinterpret_cast<const uint4*>(slab + rl * 64 + ((ch ^ ((rl >> 1) & 3)) << 4));
+            if (grow < g.M && gcol8 < g.N) *reinterpret_cast<uint4*>(dst + grow * g.ldc) = val;
+          }
+          __syncwarp();
+          continue;
+        }
 #pragma unroll
         for (int k = 0; k < 8; ++k)
           *reinterpret_cast<uint4*>(srow + ((k ^ (lane & 7)) << 4)) = make_uint4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
