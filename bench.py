@@ -131,7 +131,7 @@ def run_reference_arm(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n_img = 2
+    n_img = 4
     t0 = time.perf_counter()
     ips, sec = cpu_port_step(n_img, cores, reps=max(1, args.steps), warmup=min(1, args.warmup))
     line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": "imgs/s", "n_gpus": args.gpus, "steps": args.steps,
@@ -151,7 +151,7 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -277,7 +277,7 @@ def main():
     cpu = None
     if not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        n_img = 2
+        n_img = 8
         ips, sec = cpu_port_step(n_img, cores, reps=1, warmup=0)
         cpu = {"value": ips, "unit": "imgs/s", "cores": cores, "kind": "port",
                "sample": f"{n_img} images x 8 crops, one step (fwd+bwd+AdamW+EMA) of the oracle port of the reference modules, fp32, {sec:.1f} s"}
@@ -299,6 +299,9 @@ def main():
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
         "roofline": roofline,
+        "attn_tflops": {"fwd": roof["cb_attn_varlen_fwd"]["achieved_tflops"], "bwd": roof["cb_attn_varlen_bwd"]["achieved_tflops"],
+                        "fwd_frac_of_peak": roof["cb_attn_varlen_fwd"]["frac"], "bwd_frac_of_peak": roof["cb_attn_varlen_bwd"]["frac"],
+                        "peak_tflops": tf_peak, "flops_model": "fwd 4*D*sum(S_b^2), bwd 10*D*sum(S_b^2) per layer call, packed real tokens only"},
         "cpu_baseline": cpu,
         "loss": loss_val,
     }
