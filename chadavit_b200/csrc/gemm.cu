@@ -189,12 +189,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const float4 bias4 = bias_next;
         if (mode != EM_BF16 && has_bias && sl + 2 < n_slabs && gcol + 64 < g.N) bias_next = __ldg(reinterpret_cast<const float4*>(g.bias + gcol + 64));
         // accumulator-independent operands (ReLU mask / fp32 residual) are requested before the TMEM wait
-        uint2 m16[8];
+        uint4 mk[4];            // EM_BF16_MASK: the ReLU mask (hidden activations) of this lane's 4 x 8 output elements
         float4 res[8];
         if (mode == EM_BF16_MASK) {
-          const __nv_bfloat16* ap = g.aux + row0 * g.ld_aux + gcol;
+          const int gc8 = n0 + c + (lane & 3) * 8;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) m16[i] = (col_ok && i < nrows) ? __ldg(reinterpret_cast<const uint2*>(ap + (long)i * 4 * g.ld_aux)) : make_uint2(0u, 0u);
+          for (int i = 0; i < 4; ++i) {
+            const long grow = (long)m0 + q * 32 + i * 8 + (lane >> 2);
+            mk[i] = (grow < g.M && gc8 < g.N) ? __ldg(reinterpret_cast<const uint4*>(g.aux + grow * g.ld_aux + gc8)) : make_uint4(0u, 0u, 0u, 0u);
+          }
         }
         if (mode == EM_F32) {
           if (g.flags & CB_EPI_RESIDUAL_F32) {
@@ -240,6 +243,53 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           __syncwarp();
           continue;
         }
+        if (mode == EM_BF16_MASK) {
+          // d(hidden) = (dz2 . W2) masked by hidden > 0: the product is rounded to bf16 in the row layout, staged as 64 B
+          // rows, and masked in the coalesced read-back with 16-byte mask loads.
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) pk[j >> 1] = pack_bf16(__uint_as_float(r[j]) * g.alpha, __uint_as_float(r[j + 1]) * g.alpha);
+          uint8_t* srow64 = slab + lane * 64;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            *reinterpret_cast<uint4*>(srow64 + ((k ^ ((lane >> 1) & 3)) << 4)) = make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
+          __syncwarp();
+          if (sl + 2 < n_slabs) tmem_ld32(t_addr + c + 64, r);
+          const int ch = lane & 3;
+          const int gcol8 = n0 + c + ch * 8;
+          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(g.C) + gcol8;
+          float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rl = i * 8 + (lane >> 2);
+            const long grow = (long)m0 + q * 32 + rl;
+            uint4 val = *reinterpret_cast<const uint4*>(slab + rl * 64 + ((ch ^ ((rl >> 1) & 3)) << 4));
+            uint32_t* vv = &val.x;
+            const uint32_t* mm = &mk[i].x;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              // bf16 > 0  <=>  its bit pattern, read as a signed 16-bit integer, is > 0
+              const uint32_t sel = ((short)(mm[k] & 0xffffu) > 0 ? 0xffffu : 0u) | ((int)mm[k] >= 0x10000 ? 0xffff0000u : 0u);
+              vv[k] &= sel;
+              const float2 f = unpack_bf16(vv[k]);
+              cs[2 * k] += f.x; cs[2 * k + 1] += f.y;
+            }
+            if (grow < g.M && gcol8 < g.N) *reinterpret_cast<uint4*>(dst + grow * g.ldc) = val;
+          }
+          if (g.colsum) {   // fused linear1 bias gradient: fold the 8 row-lanes that share a column chunk, one vector RED pair
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              cs[k] += __shfl_xor_sync(0xffffffffu, cs[k], 4); cs[k] += __shfl_xor_sync(0xffffffffu, cs[k], 8);
+              cs[k] += __shfl_xor_sync(0xffffffffu, cs[k], 16);
+            }
+            if (lane < 4 && gcol8 < g.N) {
+              atomicAdd(reinterpret_cast<float4*>(g.colsum + gcol8), make_float4(cs[0], cs[1], cs[2], cs[3]));
+              atomicAdd(reinterpret_cast<float4*>(g.colsum + gcol8 + 4), make_float4(cs[4], cs[5], cs[6], cs[7]));
+            }
+          }
+          __syncwarp();
+          continue;
+        }
 #pragma unroll
         for (int k = 0; k < 8; ++k)
           *reinterpret_cast<uint4*>(srow + ((k ^ (lane & 7)) << 4)) = make_uint4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
@@ -258,7 +308,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
           for (int i = 0; i < 8; ++i) { acc[i].x *= g.alpha; acc[i].y *= g.alpha; acc[i].z *= g.alpha; acc[i].w *= g.alpha; }
         }
-        if ((!col_ok || nrows <= 0) && !(mode == EM_BF16_MASK && g.colsum)) continue;   // (shuffles below need the full warp)
+        if (!col_ok || nrows <= 0) continue;
         if (mode == EM_BF16) {
           const float lo = (g.flags & CB_EPI_RELU) ? 0.f : -INFINITY;
           __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(g.C) + row0 * g.ldc + gcol;
@@ -269,27 +319,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               *reinterpret_cast<uint2*>(dst + (long)i * 4 * g.ldc) =
                   make_uint2(pack_bf16(fmaxf(v.x + bias4.x, lo), fmaxf(v.y + bias4.y, lo)), pack_bf16(fmaxf(v.z + bias4.z, lo), fmaxf(v.w + bias4.w, lo)));
             }
-          }
-        } else if (mode == EM_BF16_MASK) {
-          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(g.C) + row0 * g.ldc + gcol;
-          float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            if (i < nrows) {
-              const float4 v = acc[i];
-              const float2 f0 = unpack_bf16(m16[i].x), f1 = unpack_bf16(m16[i].y);
-              const float o0 = f0.x > 0.f ? v.x : 0.f, o1 = f0.y > 0.f ? v.y : 0.f, o2 = f1.x > 0.f ? v.z : 0.f, o3 = f1.y > 0.f ? v.w : 0.f;
-              cs.x += o0; cs.y += o1; cs.z += o2; cs.w += o3;
-              *reinterpret_cast<uint2*>(dst + (long)i * 4 * g.ldc) = make_uint2(pack_bf16(o0, o1), pack_bf16(o2, o3));
-            }
-          }
-          if (g.colsum) {   // fused bias gradient: sum the 32 rows of this slab (4 lanes share a column chunk), one vector RED
-#pragma unroll
-            for (int o = 8; o <= 16; o <<= 1) {
-              cs.x += __shfl_xor_sync(0xffffffffu, cs.x, o); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, o);
-              cs.z += __shfl_xor_sync(0xffffffffu, cs.z, o); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, o);
-            }
-            if (rb_row == 0) atomicAdd(reinterpret_cast<float4*>(g.colsum + gcol), cs);
           }
         } else if (mode == EM_F32) {
           float* dst = reinterpret_cast<float*>(g.C) + row0 * g.ldc + gcol;
