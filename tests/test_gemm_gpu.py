@@ -69,7 +69,8 @@ def test_gemm_epilogues():
     C = ops.gemm(A, B, aux=res, flags=ops.EPI_RELU_MASK, colsum=cs)
     masked = _ref(A, B, False, False) * (res.float() > 0)
     assert (C.float() - masked).abs().max().item() < 0.05
-    assert (cs - 1 - masked.sum(0)).abs().max().item() < 0.05          # fused bias-gradient column sums
+    assert (cs - 1 - C.float().sum(0)).abs().max().item() < 1e-2       # fused bias-gradient column sums (of the stored bf16 values)
+    assert (cs - 1 - masked.sum(0)).abs().max().item() < 0.5
     # split-K atomic accumulation into an existing fp32 buffer
     acc = torch.ones(M, N, device="cuda")
     ops.gemm(A, B, flags=ops.EPI_ATOMIC, out=acc, k_splits=7)
