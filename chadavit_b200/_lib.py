@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libchadavit_b200.so")
+_VARIANT = os.environ.get("CB_VARIANT", "")   # debug builds only (chadavit_b200/build.py); the product library has no suffix
+LIB_PATH = os.path.join(_HERE, "lib", "libchadavit_b200" + ("_" + _VARIANT if _VARIANT else "") + ".so")
 
 _vp, _i, _f, _l = C.c_void_p, C.c_int, C.c_float, C.c_long
 

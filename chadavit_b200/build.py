@@ -17,13 +17,16 @@ import sys
 ROOT = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(ROOT, "csrc")
 INC = os.path.join(os.path.dirname(ROOT), "include")
-OBJ = os.path.join(ROOT, "csrc", "_obj")
+# CB_VARIANT=<name> (with CB_NVCC_EXTRA=<flags>) builds a debug variant next to the product library, e.g. the in-kernel
+# timeline build: CB_VARIANT=tl CB_NVCC_EXTRA=-DCB_TIMELINE -> lib/libchadavit_b200_tl.so (loaded when CB_VARIANT=tl is set).
+VARIANT = os.environ.get("CB_VARIANT", "")
+OBJ = os.path.join(ROOT, "csrc", "_obj" + ("_" + VARIANT if VARIANT else ""))
 LIBDIR = os.path.join(ROOT, "lib")
-LIB = os.path.join(LIBDIR, "libchadavit_b200.so")
+LIB = os.path.join(LIBDIR, "libchadavit_b200" + ("_" + VARIANT if VARIANT else "") + ".so")
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
-         "-Xcompiler", "-fPIC", "-I", INC, "-I", CSRC]
+         "-Xcompiler", "-fPIC", "-I", INC, "-I", CSRC, *os.environ.get("CB_NVCC_EXTRA", "").split()]
 
 
 def _newest_header() -> float:

@@ -15,6 +15,10 @@
 
 namespace cb {
 
+#ifdef CB_TIMELINE
+static __device__ unsigned long long g_cb_timeline[CB_TL_ROLES][CB_TL_LEN];
+#endif
+
 template <int HD>
 struct BwdCfg {
   static constexpr int CHUNK = (HD % 64 == 0) ? 64 : (HD % 32 == 0 ? 32 : 16);
@@ -77,8 +81,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   uint64_t* dkv_full = dq_drained + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dkv_full + 1);
 
+  // warps 0-7: softmax-backward / drain / epilogue, warp 8: TMA producer, warp 9: MMA issuer (last warp = highest issue priority)
+  constexpr int W_TMA = 8, W_MMA = 9;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp == 0 && lane == 0) {
+  if (warp == W_TMA && lane == 0) {
     tma_prefetch_desc(&tmQKV);
     tma_prefetch_desc(&tmDO);
     tma_prefetch_desc(&tmDQ);
@@ -88,13 +94,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     mbar_init(dkv_full, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (warp == W_MMA) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == W_TMA) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       uint32_t it = 0, wi = 0;
@@ -122,64 +128,81 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+  } else if (warp == W_MMA) {
+    // ------------------------------------------------------------------ MMA issuer (whole warp convergent, one elected lane
+    // issues: descriptors stay in uniform registers and the UTCHMMAs are emitted back to back)
+    {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);   // S^T, dP^T : both K-major
       constexpr uint32_t idesc_dv = umma_idesc_bf16(128, HD, false, true);    // dV (TS) / dK (SS): B MN-major
       constexpr uint32_t idesc_dq = umma_idesc_bf16(128, HD, true, true);     // dQ: A (dS^T) MN-major, B (K) MN-major
-      const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), ds_addr = smem_u32(sDS);
+      const uint64_t k_kd = umma_smem_desc(smem_u32(sK), 16, Cfg::SBO, Cfg::SWZ), v_kd = umma_smem_desc(smem_u32(sV), 16, Cfg::SBO, Cfg::SWZ);
+      const uint64_t q_kd0 = umma_smem_desc(smem_u32(sQ), 16, Cfg::SBO, Cfg::SWZ), do_kd0 = umma_smem_desc(smem_u32(sDO), 16, Cfg::SBO, Cfg::SWZ);
+      const uint64_t do_md0 = umma_smem_desc(smem_u32(sDO), Cfg::CHUNK_BYTES, Cfg::SBO, Cfg::SWZ);   // dO / Q / K tiles read MN-major
+      const uint64_t q_md0 = umma_smem_desc(smem_u32(sQ), Cfg::CHUNK_BYTES, Cfg::SBO, Cfg::SWZ);
+      const uint64_t k_md = umma_smem_desc(smem_u32(sK), Cfg::CHUNK_BYTES, Cfg::SBO, Cfg::SWZ);
+      const uint64_t ds_kd = umma_smem_desc(smem_u32(sDS), 16, 1024, 3), ds_md = umma_smem_desc(smem_u32(sDS), 16384, 1024, 3);
       uint32_t it = 0, wi = 0;
+      CB_TL_DECL(tl);
       for (int w = blockIdx.x; w < a.n_work; w += gridDim.x, ++wi) {
         const int4 wk = a.work[w];
         const int nq = (wk.z - wk.y + 127) / 128;
         mbar_wait(kv_full, wi & 1);
         for (int i = 0; i < nq; ++i, ++it) {
           const int s = it % NS; const uint32_t ph = (it / NS) & 1;
-          const uint32_t q_addr = smem_u32(sQ + s * Cfg::TILE_BYTES), do_addr = smem_u32(sDO + s * Cfg::TILE_BYTES);
+          const uint64_t q_kd = umma_desc_add(q_kd0, s * Cfg::TILE_BYTES), do_kd = umma_desc_add(do_kd0, s * Cfg::TILE_BYTES);
+          const uint64_t q_md = umma_desc_add(q_md0, s * Cfg::TILE_BYTES), do_md = umma_desc_add(do_md0, s * Cfg::TILE_BYTES);
+          CB_TL(0, tl, 1);
           mbar_wait(&qdo_full[s], ph);
           tc_fence_after();
+          CB_TL(0, tl, 2);
           // S^T = K Q^T
+          if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < HD / 16; ++kk) {
-            const int c = (kk * 16) / Cfg::CHUNK, off = ((kk * 16) % Cfg::CHUNK) * 2;
-            umma_ss(tmem_base + Cfg::COL_S, umma_smem_desc(k_addr + c * Cfg::CHUNK_BYTES + off, 16, Cfg::SBO, Cfg::SWZ),
-                    umma_smem_desc(q_addr + c * Cfg::CHUNK_BYTES + off, 16, Cfg::SBO, Cfg::SWZ), idesc_s, kk > 0 ? 1u : 0u);
+            for (int kk = 0; kk < HD / 16; ++kk) {
+              const int c = (kk * 16) / Cfg::CHUNK, off = ((kk * 16) % Cfg::CHUNK) * 2;
+              umma_ss(tmem_base + Cfg::COL_S, umma_desc_add(k_kd, c * Cfg::CHUNK_BYTES + off), umma_desc_add(q_kd, c * Cfg::CHUNK_BYTES + off), idesc_s, kk > 0 ? 1u : 0u);
+            }
+            tc_commit(s_full);
           }
-          tc_commit(s_full);
+          __syncwarp();
           // dP^T = V dO^T   (its TMEM region held dQ of the previous iteration: wait until that was drained)
           if (it > 0) { mbar_wait(dq_drained, (it - 1) & 1); tc_fence_after(); }
+          CB_TL(0, tl, 3);
+          if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < HD / 16; ++kk) {
-            const int c = (kk * 16) / Cfg::CHUNK, off = ((kk * 16) % Cfg::CHUNK) * 2;
-            umma_ss(tmem_base + Cfg::COL_DP, umma_smem_desc(v_addr + c * Cfg::CHUNK_BYTES + off, 16, Cfg::SBO, Cfg::SWZ),
-                    umma_smem_desc(do_addr + c * Cfg::CHUNK_BYTES + off, 16, Cfg::SBO, Cfg::SWZ), idesc_s, kk > 0 ? 1u : 0u);
+            for (int kk = 0; kk < HD / 16; ++kk) {
+              const int c = (kk * 16) / Cfg::CHUNK, off = ((kk * 16) % Cfg::CHUNK) * 2;
+              umma_ss(tmem_base + Cfg::COL_DP, umma_desc_add(v_kd, c * Cfg::CHUNK_BYTES + off), umma_desc_add(do_kd, c * Cfg::CHUNK_BYTES + off), idesc_s, kk > 0 ? 1u : 0u);
+            }
+            tc_commit(dp_full);
           }
-          tc_commit(dp_full);
+          __syncwarp();
           mbar_wait(p_ready, it & 1);
           tc_fence_after();
-          // dV += P^T dO   (A = P^T in TMEM; B = dO tile read MN-major: N = HD, K = q)
+          CB_TL(0, tl, 4);
+          if (elect_one()) {
+            // dV += P^T dO   (A = P^T in TMEM; B = dO tile read MN-major: N = HD, K = q)
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk)
-            umma_ts(tmem_base + Cfg::COL_DV, tmem_base + Cfg::COL_S + (kk < 4 ? kk * 8 : 64 + (kk - 4) * 8),
-                    umma_smem_desc(do_addr + kk * 16 * Cfg::CHUNK * 2, Cfg::CHUNK_BYTES, Cfg::SBO, Cfg::SWZ), idesc_dv,
-                    (i > 0 || kk > 0) ? 1u : 0u);
-          // dK += dS^T Q   (A = dS^T smem K-major: two [128x64] sub-tiles; B = Q tile MN-major)
+            for (int kk = 0; kk < 8; ++kk)
+              umma_ts(tmem_base + Cfg::COL_DV, tmem_base + Cfg::COL_S + (kk < 4 ? kk * 8 : 64 + (kk - 4) * 8), umma_desc_add(do_md, kk * 16 * Cfg::CHUNK * 2), idesc_dv,
+                      (i > 0 || kk > 0) ? 1u : 0u);
+            // dK += dS^T Q   (A = dS^T smem K-major: two [128x64] sub-tiles; B = Q tile MN-major)
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk)
-            umma_ss(tmem_base + Cfg::COL_DK, umma_smem_desc(ds_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024, 3),
-                    umma_smem_desc(q_addr + kk * 16 * Cfg::CHUNK * 2, Cfg::CHUNK_BYTES, Cfg::SBO, Cfg::SWZ), idesc_dv,
-                    (i > 0 || kk > 0) ? 1u : 0u);
-          // dQ_i = dS K    (A = dS^T smem read MN-major: M = q (2 blocks of 64, LBO 16 KB), K = kv; B = K tile MN-major)
+            for (int kk = 0; kk < 8; ++kk)
+              umma_ss(tmem_base + Cfg::COL_DK, umma_desc_add(ds_kd, (kk >> 2) * 16384 + (kk & 3) * 32), umma_desc_add(q_md, kk * 16 * Cfg::CHUNK * 2), idesc_dv,
+                      (i > 0 || kk > 0) ? 1u : 0u);
+            // dQ_i = dS K    (A = dS^T smem read MN-major: M = q (2 blocks of 64, LBO 16 KB), K = kv; B = K tile MN-major)
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk)
-            umma_ss(tmem_base + Cfg::COL_DP, umma_smem_desc(ds_addr + kk * 2048, 16384, 1024, 3),
-                    umma_smem_desc(k_addr + kk * 16 * Cfg::CHUNK * 2, Cfg::CHUNK_BYTES, Cfg::SBO, Cfg::SWZ), idesc_dq, kk > 0 ? 1u : 0u);
-          tc_commit(dq_full);
-          tc_commit(&qdo_empty[s]);
+            for (int kk = 0; kk < 8; ++kk)
+              umma_ss(tmem_base + Cfg::COL_DP, umma_desc_add(ds_md, kk * 2048), umma_desc_add(k_md, kk * 16 * Cfg::CHUNK * 2), idesc_dq, kk > 0 ? 1u : 0u);
+            tc_commit(dq_full);
+            tc_commit(&qdo_empty[s]);
+          }
+          __syncwarp();
+          CB_TL(0, tl, 5);
         }
-        tc_commit(dkv_full);
-        tc_commit(kv_empty);
+        if (elect_one()) { tc_commit(dkv_full); tc_commit(kv_empty); }
+        __syncwarp();
       }
     }
   } else {
@@ -187,12 +210,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     // 8 warps: two per TMEM lane quarter; `half` selects which 64 of the 128 q columns (and which 16-column chunks of the
     // dQ / dK / dV accumulators) this warp handles — the backward softmax is element-wise, so no row reduction is split.
     const int q4 = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int half = warp >> 2;
     const int r = q4 * 32 + lane;               // kv row of this thread inside the tile; also q row when draining dQ
-    const int tid256 = (warp - 2) * 32 + lane;  // 0..255
+    const int tid256 = warp * 32 + lane;        // 0..255
     const uint32_t lane_addr = tmem_base + (uint32_t(q4 * 32) << 16);
     const float LOG2E = 1.4426950408889634f;
     uint32_t it = 0, wi = 0;
+    CB_TL_DECL(tl);
+    const bool tl_on = (warp == 0 || warp == 4) && lane == 0;
+    const int tl_role = warp == 0 ? 1 : 2;
     for (int w = blockIdx.x; w < a.n_work; w += gridDim.x, ++wi) {
       const int4 wk = a.work[w];
       const int head = wk.w;
@@ -211,9 +237,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         const int q0 = wk.y + i * 128;
         if (tid256 < 128) sLSE[tid256] = stage_val; else sDelta[tid256 - 128] = stage_val;
         asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (tl_on) CB_TL(tl_role, tl, 1);
         mbar_wait(s_full, it & 1);
+        if (tl_on) CB_TL(tl_role, tl, 2);
         mbar_wait(dp_full, it & 1);
         tc_fence_after();
+        if (tl_on) CB_TL(tl_role, tl, 3);
 #pragma unroll 1
         for (int c4 = half * 2; c4 < half * 2 + 2; ++c4) {
           uint32_t sr[32], dpr[32];
@@ -245,6 +274,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         fence_proxy_async();   // generic-proxy smem writes (dS^T) -> visible to the tensor-core (async) proxy
         tc_fence_before();
         mbar_arrive(p_ready);
+        if (tl_on) CB_TL(tl_role, tl, 4);
         // ---- drain dQ_i (rows = q): TMEM -> 64B-swizzled smem slab -> TMA reduce-add (fp32) into the dQ accumulator.
         // Per-thread REDs would scatter 32 rows per instruction (ncu: the kernel was bound by L2 atomic transactions);
         // the bulk reduction moves whole 64-byte row segments.  Rows past the sequence end carry exact zeros (P = 0 there).
@@ -252,8 +282,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         if (lane == 0) tma_store_wait_read<0>();          // last iteration's reductions have long finished reading the slabs
         mbar_wait(dq_full, it & 1);
         tc_fence_after();
+        if (tl_on) CB_TL(tl_role, tl, 5);
         {
-          uint8_t* my = sDQ + (warp - 2) * (Cfg::DQ_SLABS * 2048);
+          uint8_t* my = sDQ + warp * (Cfg::DQ_SLABS * 2048);
           uint32_t o[Cfg::DQ_SLABS][16];
 #pragma unroll
           for (int k = 0; k < Cfg::DQ_SLABS; ++k)
@@ -279,6 +310,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         }
         tc_fence_before();
         mbar_arrive(dq_drained);
+        if (tl_on) CB_TL(tl_role, tl, 6);
       }
       // ---- dK, dV of this kv tile -> bf16 into dqkv
       mbar_wait(dkv_full, wi & 1);
@@ -312,7 +344,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (warp == W_MMA) tmem_dealloc(tmem_base, 512);
 }
 
 // delta[h, t] = sum_c dO[t, h*d + c] * O[t, h*d + c]     (one warp per token row)
@@ -378,6 +410,16 @@ static int launch_bwd(const void* qkv, const void* dO, const AttnBwdArgs& a, cud
 }
 
 }  // namespace cb
+
+#ifdef CB_TIMELINE
+extern "C" int cb_debug_timeline_bwd(void* dst) {
+  CB_CUDA(cudaDeviceSynchronize());
+  CB_CUDA(cudaMemcpyFromSymbol(dst, cb::g_cb_timeline, sizeof(cb::g_cb_timeline)));
+  static unsigned long long zeros[CB_TL_ROLES][CB_TL_LEN];
+  CB_CUDA(cudaMemcpyToSymbol(cb::g_cb_timeline, zeros, sizeof(zeros)));
+  return 0;
+}
+#endif
 
 extern "C" int cb_attn_varlen_bwd(const void* dout, const void* qkv, const void* out, const float* lse, const int* work, int n_work,
                                   float* delta_ws, float* dq_acc_ws, void* dqkv, int T, int D, int H, float softmax_scale, void* stream) {

@@ -213,12 +213,29 @@ __host__ __device__ constexpr uint64_t umma_smem_desc_hi(uint32_t sbo_bytes, int
 __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, int swz) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16 | umma_smem_desc_hi(sbo_bytes, swz);
 }
+// Descriptor of (base + byte_off) from the descriptor of `base` (same LBO / SBO / swizzle): only the 14-bit start-address
+// field moves, and smem addresses (< 256 KB) never carry out of it -> ONE 32-bit add per MMA operand in the issue loop.
+__device__ __forceinline__ uint64_t umma_desc_add(uint64_t desc, uint32_t byte_off) {
+  return (desc & 0xFFFFFFFF00000000ull) | (uint64_t)((uint32_t)desc + (byte_off >> 4));
+}
 // kind::f16 instruction descriptor: bf16 x bf16 -> fp32
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, bool a_mn, bool b_mn) {
   return (1u << 4)                      // D = F32
          | (1u << 7) | (1u << 10)       // A, B = BF16
          | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+
+// Debug-only in-kernel timeline (-DCB_TIMELINE, tools/timeline.py): CTA 0 records (clock64 << 8 | tag) per role.
+#ifdef CB_TIMELINE
+#define CB_TL_ROLES 4
+#define CB_TL_LEN 4096
+// each translation unit that records defines its own `static __device__ unsigned long long g_cb_timeline[CB_TL_ROLES][CB_TL_LEN]`
+#define CB_TL_DECL(n) uint32_t n = 0
+#define CB_TL(role, n, tag) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (n) < CB_TL_LEN) g_cb_timeline[role][(n)++] = ((unsigned long long)clock64() << 8) | (unsigned)(tag); } while (0)
+#else
+#define CB_TL_DECL(n)
+#define CB_TL(role, n, tag)
+#endif
 
 // bf16 helpers
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {

@@ -1,7 +1,8 @@
 // Persistent, warp-specialised tcgen05 GEMM for sm_100a:  C[M,N] (+)= op(A)[M,K] * op(B)[N,K]^T
 //   * operands bf16, accumulate fp32 in TMEM (double-buffered accumulators: epilogue of tile i overlaps MMA of tile i+1)
 //   * TMA (cp.async.bulk.tensor) loads into 128B/64B-swizzled smem stages, mbarrier full/empty ring
-//   * warp 0 = TMA producer, warp 1 = MMA issuer (single thread), warps 2..9 = epilogue
+//   * warps 0..7 = epilogue, warp 8 = TMA producer, warp 9 = MMA issuer (single thread; the LAST warp because the issue
+//     arbiter of an SMSP prefers its highest warp id: below the busy epilogue warps the issuer starved)
 //   * either operand may be K-major ([rows,K] row-major) or MN-major ([K,rows] row-major); the latter is what the
 //     weight-gradient (dW = dY^T X) and input-gradient (dX = dY W) products of the encoder need without transposes
 //   * epilogue (8 warps): TMEM -> registers (bias, ReLU, residual add, ReLU-mask, tokenizer embeddings) -> 128B-swizzled
@@ -47,7 +48,8 @@ __device__ __forceinline__ void operand_load(void* smem, const CUtensorMap* tm, 
 
 enum EpiMode { EM_BF16 = 0, EM_BF16_MASK = 1, EM_F32 = 2, EM_ATOMIC = 3, EM_TOKENIZE = 4 };
 
-constexpr int GEMM_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int GEMM_THREADS = 320;  // warps 0..7 epilogue, warp 8 TMA, warp 9 MMA
+constexpr int GEMM_W_TMA = 8, GEMM_W_MMA = 9;
 
 template <int BN, int AMODE, int BMODE, int EM>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -71,20 +73,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int kb_per = (kb_total + g.k_splits - 1) / g.k_splits;
   const int num_tiles = num_m * num_n * g.k_splits;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == GEMM_W_TMA && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int i = 0; i < Cfg::STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  if (warp == GEMM_W_MMA) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == GEMM_W_TMA) {
     if (lane == 0) {
       int s = 0; uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -100,29 +102,35 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, AMODE != 0, BMODE != 0);
-      int s = 0; uint32_t ph = 0; int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const int split = tile / (num_m * num_n);
-        const int kb0 = split * kb_per, kb1 = min(kb0 + kb_per, kb_total);
-        const int buf = it & 1; const uint32_t aph = (it >> 1) & 1;
-        mbar_wait(&acc_empty[buf], aph ^ 1);
+  } else if (warp == GEMM_W_MMA) {
+    // The whole warp runs the loop convergently, one elected lane issues: warp-uniform control flow lets the compiler keep
+    // descriptors in uniform registers and emit back-to-back UTCHMMA (under `if (lane == 0)` each MMA cost ~12 instructions).
+    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, AMODE != 0, BMODE != 0);
+    const uint64_t a_desc0 = operand_desc<AMODE>(smem_u32(sA), 0), b_desc0 = operand_desc<BMODE>(smem_u32(sB), 0);
+    constexpr uint32_t a_kstep = AMODE == 0 ? 32 : (AMODE == 1 ? 2048 : 1024), b_kstep = BMODE == 0 ? 32 : (BMODE == 1 ? 2048 : 1024);
+    int s = 0; uint32_t ph = 0; int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int split = tile / (num_m * num_n);
+      const int kb0 = split * kb_per, kb1 = min(kb0 + kb_per, kb_total);
+      const int buf = it & 1; const uint32_t aph = (it >> 1) & 1;
+      mbar_wait(&acc_empty[buf], aph ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + buf * Cfg::ACC_STRIDE;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full[s], ph);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * Cfg::ACC_STRIDE;
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&full[s], ph);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(sA + s * Cfg::A_BYTES), b_addr = smem_u32(sB + s * Cfg::B_BYTES);
+        const uint64_t ad = umma_desc_add(a_desc0, s * Cfg::A_BYTES), bd = umma_desc_add(b_desc0, s * Cfg::B_BYTES);
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
-            umma_ss(d_tmem, operand_desc<AMODE>(a_addr, k), operand_desc<BMODE>(b_addr, k), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            umma_ss(d_tmem, umma_desc_add(ad, k * a_kstep), umma_desc_add(bd, k * b_kstep), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           tc_commit(&empty[s]);
-          if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
         }
-        tc_commit(&acc_full[buf]);
+        __syncwarp();
+        if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
       }
+      if (elect_one()) tc_commit(&acc_full[buf]);
+      __syncwarp();
     }
   } else {
     // ---------------- epilogue: 8 warps; warp w owns TMEM lanes 32*(w&3) .. +31 (rows) and every other 32-column slab.
@@ -131,7 +139,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // the per-column vectors are loaded once per slab (the L1 is ~3 KB next to 225 KB of smem: scalar __ldg's would all
     // be serialised L2 round trips).
     const int q = warp & 3;
-    const int ew = warp - 2;                     // 0..7
+    const int ew = warp;                         // 0..7
     const int half = ew >> 2;                    // which of the two warps of this lane quarter
     constexpr int mode = EM;   // compile-time epilogue mode: dead branches and their register arrays disappear
     uint8_t* slab = sEpi + ew * EPI_SLAB_BYTES;
@@ -368,7 +376,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  if (warp == GEMM_W_MMA) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
 // ------------------------------------------------------------------------------------------------ host
