@@ -53,7 +53,7 @@ struct AttnBwdArgs {
 };
 
 template <int HD>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(352, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                 const __grid_constant__ CUtensorMap tmDQ, const AttnBwdArgs a) {
   using Cfg = BwdCfg<HD>;
@@ -79,10 +79,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   uint64_t* dq_full = p_ready + 1;
   uint64_t* dq_drained = dq_full + 1;      // 128 arrivals
   uint64_t* dkv_full = dq_drained + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dkv_full + 1);
+  uint64_t* dq_staged = dkv_full + 1;      // 256 arrivals: dQ_i sits in the smem slabs, ready for the bulk reductions
+  uint64_t* stage_free = dq_staged + 1;    // the reductions of dQ_i have finished reading the slabs
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stage_free + 1);
 
-  // warps 0-7: softmax-backward / drain / epilogue, warp 8: TMA producer, warp 9: MMA issuer (last warp = highest issue priority)
-  constexpr int W_TMA = 8, W_MMA = 9;
+  // warps 0-7: softmax-backward / dQ staging / epilogue, warp 8: TMA producer, warp 9: MMA issuer, warp 10: dQ reduction issuer
+  constexpr int W_TMA = 8, W_MMA = 9, W_RED = 10;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == W_TMA && lane == 0) {
     tma_prefetch_desc(&tmQKV);
@@ -91,7 +93,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     mbar_init(kv_full, 1); mbar_init(kv_empty, 1);
     for (int i = 0; i < NS; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
     mbar_init(s_full, 1); mbar_init(dp_full, 1); mbar_init(p_ready, 256); mbar_init(dq_full, 1); mbar_init(dq_drained, 256);
-    mbar_init(dkv_full, 1);
+    mbar_init(dkv_full, 1); mbar_init(dq_staged, 256); mbar_init(stage_free, 1);
     fence_barrier_init();
   }
   if (warp == W_MMA) tmem_alloc(tmem_slot, 512);
@@ -104,11 +106,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       uint32_t it = 0, wi = 0;
-      for (int w = blockIdx.x; w < a.n_work; w += gridDim.x, ++wi) {
+      for (int w = blockIdx.x; w < a.n_work; w += gridDim.x) {
         const int4 wk = a.work[w];
+        if (wk.z <= wk.y) continue;               // empty slot of the balanced schedule
         const int head = wk.w;
         const int nq = (wk.z - wk.y + 127) / 128;
         mbar_wait(kv_empty, (wi & 1) ^ 1);
+        ++wi;
         mbar_expect_tx(kv_full, 2 * Cfg::TILE_BYTES);
 #pragma unroll
         for (int c = 0; c < Cfg::NCH; ++c) {
@@ -128,6 +132,37 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         }
       }
     }
+  } else if (warp == W_RED) {
+    // ------------------------------------------------------------------ dQ reduction issuer
+    // dQ_i (rows = q) leaves through TMA reduce-add (fp32) from the 64B-swizzled slabs the softmax warps filled: whole
+    // 64-byte row segments instead of per-thread REDs (which scatter 32 rows per instruction).  Issuing the 24 bulk reductions
+    // of a tile takes ~1200 clk (the issuing thread blocks on the TMA queue), so a warp of its own does it: the softmax warps
+    // and the tensor pipe move on to the next q tile meanwhile.
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int w = blockIdx.x; w < a.n_work; w += gridDim.x) {
+        const int4 wk = a.work[w];
+        if (wk.z <= wk.y) continue;
+        const int head = wk.w;
+        const int nq = (wk.z - wk.y + 127) / 128;
+        for (int i = 0; i < nq; ++i, ++it) {
+          mbar_wait(dq_staged, it & 1);
+          const int q0 = wk.y + i * 128;
+#pragma unroll 1
+          for (int ww = 0; ww < 8; ++ww) {
+            const int q4 = ww & 3, half = ww >> 2;
+#pragma unroll
+            for (int k = 0; k < Cfg::DQ_SLABS; ++k)
+              if (k * 32 + half * 16 < HD)
+                tma_reduce_add_2d(&tmDQ, sDQ + ww * (Cfg::DQ_SLABS * 2048) + k * 2048, head * HD + k * 32 + half * 16, q0 + q4 * 32);
+          }
+          tma_store_commit();
+          tma_store_wait_read<0>();
+          mbar_arrive(stage_free);
+        }
+      }
+      tma_store_wait_all<0>();
+    }
   } else if (warp == W_MMA) {
     // ------------------------------------------------------------------ MMA issuer (whole warp convergent, one elected lane
     // issues: descriptors stay in uniform registers and the UTCHMMAs are emitted back to back)
@@ -143,19 +178,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       const uint64_t ds_kd = umma_smem_desc(smem_u32(sDS), 16, 1024, 3), ds_md = umma_smem_desc(smem_u32(sDS), 16384, 1024, 3);
       uint32_t it = 0, wi = 0;
       CB_TL_DECL(tl);
-      for (int w = blockIdx.x; w < a.n_work; w += gridDim.x, ++wi) {
+      for (int w = blockIdx.x; w < a.n_work; w += gridDim.x) {
         const int4 wk = a.work[w];
+        if (wk.z <= wk.y) continue;
         const int nq = (wk.z - wk.y + 127) / 128;
         mbar_wait(kv_full, wi & 1);
-        for (int i = 0; i < nq; ++i, ++it) {
-          const int s = it % NS; const uint32_t ph = (it / NS) & 1;
-          const uint64_t q_kd = umma_desc_add(q_kd0, s * Cfg::TILE_BYTES), do_kd = umma_desc_add(do_kd0, s * Cfg::TILE_BYTES);
-          const uint64_t q_md = umma_desc_add(q_md0, s * Cfg::TILE_BYTES), do_md = umma_desc_add(do_md0, s * Cfg::TILE_BYTES);
-          CB_TL(0, tl, 1);
-          mbar_wait(&qdo_full[s], ph);
+        ++wi;
+        auto issue_s = [&](uint32_t itx) {   // S^T = K Q^T of iteration itx (its Q tile must have landed)
+          const int sx = itx % NS;
+          const uint64_t q_kd = umma_desc_add(q_kd0, sx * Cfg::TILE_BYTES);
+          mbar_wait(&qdo_full[sx], (itx / NS) & 1);
           tc_fence_after();
-          CB_TL(0, tl, 2);
-          // S^T = K Q^T
           if (elect_one()) {
 #pragma unroll
             for (int kk = 0; kk < HD / 16; ++kk) {
@@ -165,9 +198,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             tc_commit(s_full);
           }
           __syncwarp();
-          // dP^T = V dO^T   (its TMEM region held dQ of the previous iteration: wait until that was drained)
-          if (it > 0) { mbar_wait(dq_drained, (it - 1) & 1); tc_fence_after(); }
-          CB_TL(0, tl, 3);
+        };
+        auto issue_dp = [&](uint32_t itx) {  // dP^T = V dO^T of iteration itx; its TMEM region held dQ of iteration itx-1
+          const int sx = itx % NS;
+          const uint64_t do_kd = umma_desc_add(do_kd0, sx * Cfg::TILE_BYTES);
+          if (itx > 0) { mbar_wait(dq_drained, (itx - 1) & 1); tc_fence_after(); }
           if (elect_one()) {
 #pragma unroll
             for (int kk = 0; kk < HD / 16; ++kk) {
@@ -177,10 +212,24 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             tc_commit(dp_full);
           }
           __syncwarp();
+        };
+        issue_s(it);
+        issue_dp(it);
+        for (int i = 0; i < nq; ++i, ++it) {
+          const int s = it % NS;
+          const uint64_t q_md = umma_desc_add(q_md0, s * Cfg::TILE_BYTES), do_md = umma_desc_add(do_md0, s * Cfg::TILE_BYTES);
+          CB_TL(0, tl, 3);
           mbar_wait(p_ready, it & 1);
           tc_fence_after();
           CB_TL(0, tl, 4);
           if (elect_one()) {
+            // dQ_i = dS K first: its read-out by the softmax warps then runs under dV / dK / the next S^T, and the next dP^T
+            // (same TMEM columns) can follow without a bubble.  A = dS^T smem read MN-major (M = q: 2 blocks of 64, LBO
+            // 16 KB; K = kv), B = K tile MN-major.
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)
+              umma_ss(tmem_base + Cfg::COL_DP, umma_desc_add(ds_md, kk * 2048), umma_desc_add(k_md, kk * 16 * Cfg::CHUNK * 2), idesc_dq, kk > 0 ? 1u : 0u);
+            tc_commit(dq_full);
             // dV += P^T dO   (A = P^T in TMEM; B = dO tile read MN-major: N = HD, K = q)
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk)
@@ -191,14 +240,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             for (int kk = 0; kk < 8; ++kk)
               umma_ss(tmem_base + Cfg::COL_DK, umma_desc_add(ds_kd, (kk >> 2) * 16384 + (kk & 3) * 32), umma_desc_add(q_md, kk * 16 * Cfg::CHUNK * 2), idesc_dv,
                       (i > 0 || kk > 0) ? 1u : 0u);
-            // dQ_i = dS K    (A = dS^T smem read MN-major: M = q (2 blocks of 64, LBO 16 KB), K = kv; B = K tile MN-major)
-#pragma unroll
-            for (int kk = 0; kk < 8; ++kk)
-              umma_ss(tmem_base + Cfg::COL_DP, umma_desc_add(ds_md, kk * 2048), umma_desc_add(k_md, kk * 16 * Cfg::CHUNK * 2), idesc_dq, kk > 0 ? 1u : 0u);
-            tc_commit(dq_full);
             tc_commit(&qdo_empty[s]);
           }
           __syncwarp();
+          // next q tile: S^T right behind (the in-order pipe has retired dV, the last reader of P^T, by then), then dP^T as soon
+          // as dQ_i has been read out of its columns
+          if (i + 1 < nq) { issue_s(it + 1); issue_dp(it + 1); }
           CB_TL(0, tl, 5);
         }
         if (elect_one()) { tc_commit(dkv_full); tc_commit(kv_empty); }
@@ -219,17 +266,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     CB_TL_DECL(tl);
     const bool tl_on = (warp == 0 || warp == 4) && lane == 0;
     const int tl_role = warp == 0 ? 1 : 2;
-    for (int w = blockIdx.x; w < a.n_work; w += gridDim.x, ++wi) {
+    for (int w = blockIdx.x; w < a.n_work; w += gridDim.x) {
       const int4 wk = a.work[w];
+      if (wk.z <= wk.y) continue;
       const int head = wk.w;
       const int nq = (wk.z - wk.y + 127) / 128;
       const bool kv_ok = wk.x + r < wk.z;
       // LSE (threads 0-127) / delta (threads 128-255) of a q tile: loaded into a register one iteration ahead (the global
       // latency hides under the wait for the dV/dK/dQ MMAs), published to smem at the start of the iteration.
       const float* stage_src = (tid256 < 128 ? a.lse : a.delta) + (long)head * a.T;
-      auto stage_load = [&](int i_) -> float {
+      auto stage_load = [&](int i_) -> float {           // LSE in the exp2 domain / delta pre-multiplied by the softmax scale
         const int t = wk.y + i_ * 128 + (tid256 & 127);
-        if (t < wk.z) return tid256 < 128 ? __ldg(stage_src + t) * LOG2E : __ldg(stage_src + t);
+        if (t < wk.z) return tid256 < 128 ? __ldg(stage_src + t) * LOG2E : __ldg(stage_src + t) * a.scale;
         return tid256 < 128 ? INFINITY : 0.f;            // +inf -> p = 0 for q rows past the sequence
       };
       float stage_val = stage_load(0);
@@ -243,35 +291,54 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         mbar_wait(dp_full, it & 1);
         tc_fence_after();
         if (tl_on) CB_TL(tl_role, tl, 3);
-#pragma unroll 1
-        for (int c4 = half * 2; c4 < half * 2 + 2; ++c4) {
-          uint32_t sr[32], dpr[32];
-          tmem_ld32(lane_addr + Cfg::COL_S + c4 * 32, sr);
-          tmem_ld32(lane_addr + Cfg::COL_DP + c4 * 32, dpr);
-          tmem_ld_wait();
-          uint32_t pp[16], dsp[16];
+        // This warp's 64 q columns in four 16-column chunks (ptxas re-uses one register set: load -> math per chunk).
+        // Per element: p = exp2(s c - lse) (FFMA + MUFU), dS = p (dP scale - delta scale) (FFMA + FMUL), two bf16 packs per
+        // pair; LSE / delta come as broadcast 16-byte smem loads (4 q columns each).  kv rows past the sequence end must
+        // contribute nothing to dQ = dS K: their packed dS words are cleared with one AND per pair (their P rows only feed
+        // dV / dK rows that are never stored).
+        {
+          const uint32_t keep = kv_ok ? 0xffffffffu : 0u;
+          uint32_t sr[2][16], dpr[2][16];
+          tmem_ld16(lane_addr + Cfg::COL_S + half * 64, sr[0]);
+          tmem_ld16(lane_addr + Cfg::COL_DP + half * 64, dpr[0]);
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            float p0 = fast_exp2_b(__uint_as_float(sr[j]) * a.scale_log2 - sLSE[c4 * 32 + j]);
-            float p1 = fast_exp2_b(__uint_as_float(sr[j + 1]) * a.scale_log2 - sLSE[c4 * 32 + j + 1]);
-            if (!kv_ok) { p0 = 0.f; p1 = 0.f; }
-            const float d0 = p0 * (__uint_as_float(dpr[j]) - sDelta[c4 * 32 + j]) * a.scale;
-            const float d1 = p1 * (__uint_as_float(dpr[j + 1]) - sDelta[c4 * 32 + j + 1]) * a.scale;
-            pp[j >> 1] = pack_bf16(p0, p1);
-            dsp[j >> 1] = pack_bf16(d0, d1);
-          }
-          // P^T (bf16 pairs) stays inside this warp's own half of the S region: q cols 0-63 -> TMEM cols 0..31, 64-127 -> 64..95
-          tmem_st16(lane_addr + Cfg::COL_S + (c4 < 2 ? c4 * 16 : 64 + (c4 - 2) * 16), pp);
-          // dS^T row r, q columns [32*c4, 32*c4+32) -> sub-tile (c4>>1), 16B chunks 4*(c4&1) .. +3, 128B swizzle
-          uint8_t* base = sDS + (c4 >> 1) * 16384 + r * 128;
+          for (int j = 0; j < 4; ++j) {
+            const int c8 = half * 4 + j;               // 16-column chunk index within the 128 q columns
+            tmem_ld_wait();
+            if (j < 3) {
+              tmem_ld16(lane_addr + Cfg::COL_S + (c8 + 1) * 16, sr[(j + 1) & 1]);
+              tmem_ld16(lane_addr + Cfg::COL_DP + (c8 + 1) * 16, dpr[(j + 1) & 1]);
+            }
+            const uint32_t (&sv)[16] = sr[j & 1];
+            const uint32_t (&dv)[16] = dpr[j & 1];
+            uint32_t pp[8], dsp[8];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int chunk = ((c4 & 1) * 4 + k) ^ (r & 7);
-            *reinterpret_cast<uint4*>(base + chunk * 16) = make_uint4(dsp[4 * k], dsp[4 * k + 1], dsp[4 * k + 2], dsp[4 * k + 3]);
+            for (int e = 0; e < 16; e += 4) {
+              const float4 l4 = *reinterpret_cast<const float4*>(sLSE + c8 * 16 + e), d4 = *reinterpret_cast<const float4*>(sDelta + c8 * 16 + e);
+              const float p0 = fast_exp2_b(fmaf(__uint_as_float(sv[e]), a.scale_log2, -l4.x)), p1 = fast_exp2_b(fmaf(__uint_as_float(sv[e + 1]), a.scale_log2, -l4.y));
+              const float p2 = fast_exp2_b(fmaf(__uint_as_float(sv[e + 2]), a.scale_log2, -l4.z)), p3 = fast_exp2_b(fmaf(__uint_as_float(sv[e + 3]), a.scale_log2, -l4.w));
+              const float e0 = p0 * fmaf(__uint_as_float(dv[e]), a.scale, -d4.x), e1 = p1 * fmaf(__uint_as_float(dv[e + 1]), a.scale, -d4.y);
+              const float e2 = p2 * fmaf(__uint_as_float(dv[e + 2]), a.scale, -d4.z), e3 = p3 * fmaf(__uint_as_float(dv[e + 3]), a.scale, -d4.w);
+              pp[e >> 1] = pack_bf16(p0, p1); pp[(e >> 1) + 1] = pack_bf16(p2, p3);
+              dsp[e >> 1] = pack_bf16(e0, e1) & keep; dsp[(e >> 1) + 1] = pack_bf16(e2, e3) & keep;
+            }
+            // P^T (bf16 pairs) stays inside this warp's own half of the S region (columns already read): q cols 0-63 -> TMEM
+            // cols 0..31, 64-127 -> 64..95
+            tmem_st8(lane_addr + Cfg::COL_S + half * 64 + j * 8, pp);
+            // dS^T row r, q columns [16 c8, 16 c8 + 16) -> sub-tile (c8 >> 2), 16B chunks 2 (c8 & 3), +1, 128B swizzle
+            uint8_t* base = sDS + (c8 >> 2) * 16384 + r * 128;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              const int chunk = ((c8 & 3) * 2 + k) ^ (r & 7);
+              *reinterpret_cast<uint4*>(base + chunk * 16) = make_uint4(dsp[4 * k], dsp[4 * k + 1], dsp[4 * k + 2], dsp[4 * k + 3]);
+            }
           }
         }
+        if (tl_on) CB_TL(tl_role, tl, 31);
         tmem_st_wait();
+        if (tl_on) CB_TL(tl_role, tl, 32);
         fence_proxy_async();   // generic-proxy smem writes (dS^T) -> visible to the tensor-core (async) proxy
+        if (tl_on) CB_TL(tl_role, tl, 33);
         tc_fence_before();
         mbar_arrive(p_ready);
         if (tl_on) CB_TL(tl_role, tl, 4);
@@ -279,7 +346,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         // Per-thread REDs would scatter 32 rows per instruction (ncu: the kernel was bound by L2 atomic transactions);
         // the bulk reduction moves whole 64-byte row segments.  Rows past the sequence end carry exact zeros (P = 0 there).
         if (i + 1 < nq) stage_val = stage_load(i + 1);
-        if (lane == 0) tma_store_wait_read<0>();          // last iteration's reductions have long finished reading the slabs
         mbar_wait(dq_full, it & 1);
         tc_fence_after();
         if (tl_on) CB_TL(tl_role, tl, 5);
@@ -290,7 +356,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           for (int k = 0; k < Cfg::DQ_SLABS; ++k)
             if (k * 32 + half * 16 < HD) tmem_ld16(lane_addr + Cfg::COL_DP + k * 32 + half * 16, o[k]);
           tmem_ld_wait();
-          __syncwarp();
+          tc_fence_before();
+          mbar_arrive(dq_drained);                          // the dQ / dP^T columns may be overwritten from here on
+          if (tl_on) CB_TL(tl_role, tl, 21);
+          if (it > 0) mbar_wait(stage_free, (it - 1) & 1);  // the previous tile's reductions have finished reading the slabs
 #pragma unroll
           for (int k = 0; k < Cfg::DQ_SLABS; ++k)
             if (k * 32 + half * 16 < HD) {
@@ -300,20 +369,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                     make_uint4(o[k][4 * j], o[k][4 * j + 1], o[k][4 * j + 2], o[k][4 * j + 3]);
             }
           fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) {
-#pragma unroll
-            for (int k = 0; k < Cfg::DQ_SLABS; ++k)
-              if (k * 32 + half * 16 < HD) tma_reduce_add_2d(&tmDQ, my + k * 2048, head * HD + k * 32 + half * 16, q0 + q4 * 32);
-            tma_store_commit();
-          }
+          mbar_arrive(dq_staged);                           // warp 10 issues the bulk reductions (issuing them blocks ~400 clk each)
+          if (tl_on) CB_TL(tl_role, tl, 6);
         }
-        tc_fence_before();
-        mbar_arrive(dq_drained);
-        if (tl_on) CB_TL(tl_role, tl, 6);
       }
       // ---- dK, dV of this kv tile -> bf16 into dqkv
       mbar_wait(dkv_full, wi & 1);
+      ++wi;
       tc_fence_after();
       {
         __nv_bfloat16* dk_dst = a.dqkv + (long)(wk.x + r) * (3 * a.D) + a.D + head * HD;
@@ -340,7 +402,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       }
       tc_fence_before();
     }
-    if (lane == 0) tma_store_wait_all<0>();
   }
   tc_fence_before();
   __syncthreads();
@@ -404,7 +465,7 @@ static int launch_bwd(const void* qkv, const void* dO, const AttnBwdArgs& a, cud
     if (make_tmap(&tdq, a.dq_acc, 2, dims, strides, box, 2, 4)) return 1;
   }
   const int grid = a.n_work < num_sms() ? a.n_work : num_sms();
-  attn_bwd_kernel<HD><<<grid, 320, Cfg::SMEM_BYTES, stream>>>(tq, td, tdq, a);
+  attn_bwd_kernel<HD><<<grid, 352, Cfg::SMEM_BYTES, stream>>>(tq, td, tdq, a);
   CB_CUDA(cudaGetLastError());
   return 0;
 }

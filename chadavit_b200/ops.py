@@ -169,6 +169,40 @@ class PackedLayout:
             self._work[(nheads, tile)] = w.to(self.device, non_blocking=True)
         return self._work[(nheads, tile)]
 
+    def attn_schedule(self, nheads: int, tile: int, kind: str, n_ctas: Optional[int] = None) -> torch.Tensor:
+        """Work list of `attn_work` re-ordered for the persistent kernels, which give CTA c the slots c, c + G, c + 2G, ...:
+        items are assigned longest-processing-time-first to the least loaded of the G CTAs and written back round-major,
+        padded with empty slots (seq_end <= seq_start, skipped by the kernels).  Pure host arithmetic on Python ints.
+        kind = "fwd" (cost ~ kv sub-tiles x query tiles of the item) or "bwd" (cost ~ query tiles per kv tile)."""
+        import heapq
+        G = n_ctas or _lib.load().cb_num_sms()
+        key = (nheads, tile, kind, G)
+        if key not in self._work:
+            w = self.attn_work(nheads, tile).cpu().numpy()
+            if len(w) <= G:
+                self._work[key] = self.attn_work(nheads, tile)
+                return self._work[key]
+            seq = (w[:, 2] - w[:, 1]).astype(np.int64)
+            if kind == "fwd":
+                ntile = np.minimum((w[:, 2] - w[:, 0] + 127) // 128, tile // 128)
+                cost = ((seq + 63) // 64) * ntile + 3
+            else:
+                cost = (seq + 127) // 128 + 1
+            order = np.argsort(-cost, kind="stable")
+            heap = [(0, c) for c in range(G)]
+            lists = [[] for _ in range(G)]
+            for i in order:
+                load, c = heapq.heappop(heap)
+                lists[c].append(i)
+                heapq.heappush(heap, (load + int(cost[i]), c))
+            rounds = max(len(l) for l in lists)
+            out = np.zeros((rounds * G, 4), dtype=np.int32)
+            for c, l in enumerate(lists):
+                for r, i in enumerate(l):
+                    out[r * G + c] = w[i]
+            self._work[key] = torch.from_numpy(out).to(self.device, non_blocking=True)
+        return self._work[key]
+
     def non_cls_rows(self) -> torch.Tensor:
         """Packed rows of all patch tokens in (b, c, p) order (return_all_tokens=True output order, chada_vit.py:283-287)."""
         if not hasattr(self, "_noncls"):
@@ -211,7 +245,7 @@ def attn_fwd(qkv: torch.Tensor, lay: PackedLayout, nheads: int, *, need_lse: boo
     T, D3 = qkv.shape
     D = D3 // 3
     d = D // nheads
-    work = lay.attn_work(nheads, q_tile)
+    work = lay.attn_schedule(nheads, q_tile, "fwd") if q_tile == 256 else lay.attn_work(nheads, q_tile)
     out = torch.empty(T, D, device=qkv.device, dtype=bf16)
     lse = torch.empty(nheads, T, device=qkv.device, dtype=torch.float32) if need_lse else None
     _call("cb_attn_varlen_fwd", _p(qkv), _p(work), work.shape[0], q_tile, _p(out), _p(lse), T, D, nheads, float(d) ** -0.5, _stream(),
@@ -224,7 +258,7 @@ def attn_bwd(dout: torch.Tensor, qkv: torch.Tensor, out: torch.Tensor, lse: torc
     T, D3 = qkv.shape
     D = D3 // 3
     d = D // nheads
-    work = lay.attn_work(nheads)
+    work = lay.attn_schedule(nheads, 128, "bwd")
     delta = torch.empty(nheads, T, device=qkv.device, dtype=torch.float32)
     dq_acc = torch.empty(T, D, device=qkv.device, dtype=torch.float32)
     dqkv = torch.empty(T, D3, device=qkv.device, dtype=bf16)
