@@ -243,6 +243,16 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, bool a_mn, 
 #define CB_TL(role, n, tag)
 #endif
 
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): one full 32-byte sector per lane
+__device__ __forceinline__ void ldg256(const void* p, uint32_t (&r)[8]) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void stg256(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f, uint32_t g, uint32_t h) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e), "r"(f), "r"(g), "r"(h) : "memory");
+}
+
 // bf16 helpers
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
@@ -256,6 +266,20 @@ __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
+}
+// Column sums of a 32 x 32 block held as (lane = row, v[c] = column c): returns, in lane c, the sum over all 32 lanes of their
+// v[c].  Transpose-reduce butterfly: 16 + 8 + 4 + 2 + 1 = 31 shuffles (each step halves the values a lane still carries).
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int w = 16; w >= 1; w >>= 1) {
+    const bool up = (lane & w) != 0;
+#pragma unroll
+    for (int k = 0; k < w; ++k) {
+      const float send = up ? v[k] : v[k + w], keep = up ? v[k + w] : v[k];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+    }
+  }
+  return v[0];
 }
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll

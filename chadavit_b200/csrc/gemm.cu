@@ -14,6 +14,10 @@
 
 namespace cb {
 
+#ifdef CB_TIMELINE
+static __device__ unsigned long long g_cb_timeline[CB_TL_ROLES][CB_TL_LEN];
+#endif
+
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int EPI_SLAB_BYTES = 32 * 128;            // one warp's slab: 32 rows x 128 B
@@ -51,27 +55,40 @@ enum EpiMode { EM_BF16 = 0, EM_BF16_MASK = 1, EM_F32 = 2, EM_ATOMIC = 3, EM_TOKE
 constexpr int GEMM_THREADS = 320;  // warps 0..7 epilogue, warp 8 TMA, warp 9 MMA
 constexpr int GEMM_W_TMA = 8, GEMM_W_MMA = 9;
 
-template <int BN, int AMODE, int BMODE, int EM>
+// WRES ("weights resident", K <= 192, no split-K): a CTA keeps ONE column tile of B — the whole [BN x K] weight block — in
+// shared memory for its lifetime and streams row tiles of A past it (full-K A tiles in a 2-deep ring, one barrier round trip
+// and 12 back-to-back MMAs per output tile).  The small-K products of the encoder (qkv, proj, fc1 and the input-gradient
+// GEMMs against W2 / Wo) are bound by shared-memory bandwidth, not by the tensor pipe: per 128 x 256 output tile the staged
+// kernel moved 144 KB of operands INTO smem by TMA, 144 KB out again for the MMAs and 128 KB through the epilogue slabs
+// (3250 clk at 128 B/clk against 1536 clk of MMA; ncu: L1TEX/smem pipe the busiest unit).  Re-loading the same 96 KB weight
+// tile for every row tile was the avoidable third of that.
+constexpr int WRES_A_STAGES = 2;
+
+template <int BN, int AMODE, int BMODE, int EM, bool WRES>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + Cfg::STAGES * Cfg::A_BYTES;
-  uint8_t* sEpi = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
+  const int kb_total = (g.K + BK - 1) / BK;
+  // staged: [STAGES x A k-block][STAGES x B k-block][epilogue slabs]; WRES: [kb_total x B k-block][2 x kb_total x A k-block][slabs]
+  uint8_t* sB = WRES ? smem : smem + Cfg::STAGES * Cfg::A_BYTES;
+  uint8_t* sA = WRES ? smem + kb_total * Cfg::B_BYTES : smem;
+  uint8_t* sEpi = WRES ? sA + WRES_A_STAGES * kb_total * Cfg::A_BYTES : smem + Cfg::STAGES * Cfg::STAGE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + EPI_BYTES);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + Cfg::STAGES;
+  uint64_t* full = bars;                         // WRES: full[0..1] = A stage landed, full[2] = weights landed
+  uint64_t* empty = bars + Cfg::STAGES;          // WRES: empty[0..1]
   uint64_t* acc_full = bars + 2 * Cfg::STAGES;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_m = (g.M + BM - 1) / BM, num_n = (g.N + BN - 1) / BN;
-  const int kb_total = (g.K + BK - 1) / BK;
   const int kb_per = (kb_total + g.k_splits - 1) / g.k_splits;
   const int num_tiles = num_m * num_n * g.k_splits;
+  // tile enumeration: staged = tiles blockIdx.x, + gridDim.x, ... (n fastest); WRES = fixed column tile blockIdx.x % num_n, row
+  // tiles blockIdx.x / num_n, + gridDim.x / num_n, ...  (the host launches a multiple of num_n CTAs)
+  const int w_n0 = (blockIdx.x % num_n) * BN, w_m_first = blockIdx.x / num_n, w_m_step = gridDim.x / num_n;
 
   if (warp == GEMM_W_TMA && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -87,7 +104,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == GEMM_W_TMA) {
-    if (lane == 0) {
+    if (WRES) {
+      if (lane == 0) {
+        mbar_expect_tx(&full[2], kb_total * Cfg::B_BYTES);
+        for (int kb = 0; kb < kb_total; ++kb) operand_load<BMODE>(sB + kb * Cfg::B_BYTES, &tmB, &full[2], kb * BK, w_n0);
+        int s = 0; uint32_t ph = 0;
+        for (int mi = w_m_first; mi < num_m; mi += w_m_step) {
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_expect_tx(&full[s], kb_total * Cfg::A_BYTES);
+          for (int kb = 0; kb < kb_total; ++kb) operand_load<AMODE>(sA + (s * kb_total + kb) * Cfg::A_BYTES, &tmA, &full[s], kb * BK, mi * BM);
+          if (++s == WRES_A_STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    } else if (lane == 0) {
       int s = 0; uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int split = tile / (num_m * num_n), mn = tile % (num_m * num_n);
@@ -109,6 +138,34 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const uint64_t a_desc0 = operand_desc<AMODE>(smem_u32(sA), 0), b_desc0 = operand_desc<BMODE>(smem_u32(sB), 0);
     constexpr uint32_t a_kstep = AMODE == 0 ? 32 : (AMODE == 1 ? 2048 : 1024), b_kstep = BMODE == 0 ? 32 : (BMODE == 1 ? 2048 : 1024);
     int s = 0; uint32_t ph = 0; int it = 0;
+    if (WRES) {
+      mbar_wait(&full[2], 0);
+      CB_TL_DECL(tl);
+      for (int mi = w_m_first; mi < num_m; mi += w_m_step, ++it) {
+        const int buf = it & 1; const uint32_t aph = (it >> 1) & 1;
+        CB_TL(0, tl, 1);
+        mbar_wait(&acc_empty[buf], aph ^ 1);
+        CB_TL(0, tl, 2);
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        CB_TL(0, tl, 3);
+        const uint32_t d_tmem = tmem_base + buf * Cfg::ACC_STRIDE;
+        const uint64_t ad = umma_desc_add(a_desc0, s * kb_total * Cfg::A_BYTES);
+        if (elect_one()) {
+          for (int kb = 0; kb < kb_total; ++kb) {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_ss(d_tmem, umma_desc_add(ad, kb * Cfg::A_BYTES + k * a_kstep), umma_desc_add(b_desc0, kb * Cfg::B_BYTES + k * b_kstep), idesc,
+                      (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(&empty[s]);
+          tc_commit(&acc_full[buf]);
+        }
+        __syncwarp();
+        CB_TL(0, tl, 4);
+        if (++s == WRES_A_STAGES) { s = 0; ph ^= 1; }
+      }
+    } else
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int split = tile / (num_m * num_n);
       const int kb0 = split * kb_per, kb1 = min(kb0 + kb_per, kb_total);
@@ -142,13 +199,151 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int ew = warp;                         // 0..7
     const int half = ew >> 2;                    // which of the two warps of this lane quarter
     constexpr int mode = EM;   // compile-time epilogue mode: dead branches and their register arrays disappear
+    // ---------------- row-direct epilogue (bf16 / fp32 outputs of a CTA with a FIXED column tile: WRES or a single column tile)
+    // A thread owns a ROW of the accumulator, i.e. 32 consecutive output columns per slab = 64 contiguous bytes of a bf16
+    // row (128 of an fp32 row): it stores them itself as full 32-byte sectors (STG.256).  No smem staging, no warp
+    // synchronisation, ~95 instead of ~170 instructions per slab; the bias of the column tile sits in smem (broadcast LDS).
+    // In-kernel timeline of fc1 (profiles/r01_timeline_gemm.txt): the staged epilogue needed 1100 clk per slab, 4400 clk per
+    // 128 x 256 tile against 1536 clk of MMA — the tensor pipe waited for the epilogue 60 % of the time.
+    if ((mode == EM_BF16 || mode == EM_F32 || mode == EM_BF16_MASK) && g.direct && (WRES || num_n == 1)) {
+      float* sBias = reinterpret_cast<float*>(sEpi);
+      const int n0 = WRES ? w_n0 : 0;
+      for (int i = threadIdx.x; i < BN; i += 256) sBias[i] = (g.bias != nullptr && n0 + i < g.N) ? __ldg(g.bias + n0 + i) : 0.f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const int n_lim = min(BN, g.N - n0);
+      const int n_slabs = (n_lim + 31) / 32;
+      const float lo = (g.flags & CB_EPI_RELU) ? 0.f : -INFINITY;
+      const bool has_res = mode == EM_F32 && (g.flags & CB_EPI_RESIDUAL_F32);
+      // EM_BF16_MASK: fused bias gradient of linear1 = column sums of the STORED (masked, bf16-rounded) values.  Lane c of this
+      // warp accumulates column 32 sl + c of its slabs over all row tiles of the CTA (the column tile is fixed), one atomic each
+      // at the end.  csum[j] belongs to slab half + 2 j.
+      float csum[4] = {0.f, 0.f, 0.f, 0.f};
+      int it = 0;
+      for (int tile = WRES ? w_m_first : blockIdx.x; tile < (WRES ? num_m : num_tiles); tile += (WRES ? w_m_step : gridDim.x), ++it) {
+        const int m0 = (WRES ? tile : tile / num_n) * BM;     // num_n == 1 in the staged case (k_splits == 1: no atomic mode here)
+        const int buf = it & 1; const uint32_t aph = (it >> 1) & 1;
+        const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + buf * Cfg::ACC_STRIDE;
+        const long row = (long)m0 + q * 32 + lane;
+        const bool row_ok = row < g.M;
+        // Accumulator-independent operand of a slab (fp32 residual row segment, 128 B, or ReLU mask = hidden activations, 64 B):
+        // requested TWO slabs ahead — the first two before the accumulator wait — so that the DRAM latency (~1000 clk) of these
+        // row-strided reads is covered by the processing of the slabs in between (8 warps x 2 loads in flight per thread).
+        constexpr int NAUX = mode == EM_F32 ? 32 : 16;
+        auto aux_load = [&](uint32_t (&m)[NAUX], int sl) {
+          const int c = sl * 32;
+#pragma unroll
+          for (int e = 0; e < NAUX; ++e) m[e] = 0u;
+          if (!row_ok) return;
+          if (mode == EM_F32) {
+            if (!has_res) return;
+            const float* rp = reinterpret_cast<const float*>(g.aux) + row * g.ld_aux + n0 + c;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (c + 8 * k + 8 <= n_lim) ldg256(rp + 8 * k, *reinterpret_cast<uint32_t(*)[8]>(&m[8 * k]));
+          } else if (mode == EM_BF16_MASK) {
+            const __nv_bfloat16* mp = g.aux + row * g.ld_aux + n0 + c;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              if (c + 16 * k + 16 <= n_lim) ldg256(mp + 16 * k, *reinterpret_cast<uint32_t(*)[8]>(&m[8 * k]));
+              else if (c + 16 * k + 8 <= n_lim) { const uint4 m4 = __ldg(reinterpret_cast<const uint4*>(mp + 16 * k)); m[8 * k] = m4.x; m[8 * k + 1] = m4.y; m[8 * k + 2] = m4.z; m[8 * k + 3] = m4.w; }
+            }
+          }
+        };
+        // one slab: accumulator wait -> next slab's TMEM read -> math -> stores.  `x` holds this slab, `nxt` receives the next
+        // one (two statically indexed register sets, alternated by the unrolled sequence below); `m` = its residual / mask.
+        auto slab_step = [&](uint32_t (&x)[32], uint32_t (&nxt)[32], const uint32_t (&m)[NAUX], int sl, float& cs) {
+          const int c = sl * 32;
+          tmem_ld_wait();
+          if (sl + 2 < n_slabs) tmem_ld32(t_addr + c + 64, nxt);                // next slab in flight under this slab's math
+          else { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&acc_empty[buf]); }   // accumulator fully read
+          if (mode == EM_BF16_MASK) {
+            // d(hidden) = (dz2 . W2) where hidden > 0.  bf16 > 0  <=>  its bit pattern, read as a signed 16-bit integer, is > 0.
+            uint32_t pk[16];
+            float f[32];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const uint32_t mm = m[e];
+              const uint32_t sel = ((short)(mm & 0xffffu) > 0 ? 0xffffu : 0u) | ((int)mm >= 0x10000 ? 0xffff0000u : 0u);
+              pk[e] = pack_bf16(__uint_as_float(x[2 * e]) * g.alpha, __uint_as_float(x[2 * e + 1]) * g.alpha) & sel;   // rows past M: mask = 0
+              const float2 u = unpack_bf16(pk[e]);
+              f[2 * e] = u.x; f[2 * e + 1] = u.y;
+            }
+            if (row_ok) {
+              __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(g.C) + row * g.ldc + n0 + c;
+              if (c + 32 <= n_lim) {
+                stg256(dst, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
+                stg256(dst + 16, pk[8], pk[9], pk[10], pk[11], pk[12], pk[13], pk[14], pk[15]);
+              } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  if (c + 8 * k < n_lim) *reinterpret_cast<uint4*>(dst + 8 * k) = make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
+              }
+            }
+            if (g.colsum) cs += warp_colsum32(f, lane);
+            return;
+          }
+          if (!row_ok) return;
+          if (mode == EM_BF16) {
+            uint32_t pk[16];
+#pragma unroll
+            for (int e = 0; e < 32; e += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(sBias + c + e);
+              pk[e >> 1] = pack_bf16(fmaxf(fmaf(__uint_as_float(x[e]), g.alpha, b4.x), lo), fmaxf(fmaf(__uint_as_float(x[e + 1]), g.alpha, b4.y), lo));
+              pk[(e >> 1) + 1] = pack_bf16(fmaxf(fmaf(__uint_as_float(x[e + 2]), g.alpha, b4.z), lo), fmaxf(fmaf(__uint_as_float(x[e + 3]), g.alpha, b4.w), lo));
+            }
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(g.C) + row * g.ldc + n0 + c;
+            if (c + 32 <= n_lim) {
+              stg256(dst, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
+              stg256(dst + 16, pk[8], pk[9], pk[10], pk[11], pk[12], pk[13], pk[14], pk[15]);
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (c + 8 * k < n_lim) *reinterpret_cast<uint4*>(dst + 8 * k) = make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
+            }
+          } else {
+            float* dst = reinterpret_cast<float*>(g.C) + row * g.ldc + n0 + c;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (c + 8 * k + 8 <= n_lim) {
+                const float4 b0 = *reinterpret_cast<const float4*>(sBias + c + 8 * k), b1 = *reinterpret_cast<const float4*>(sBias + c + 8 * k + 4);
+                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                uint32_t o[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] = __float_as_uint(fmaxf(fmaf(__uint_as_float(x[8 * k + e]), g.alpha, bb[e]), lo) + __uint_as_float(m[(8 * k + e) % NAUX]));
+                stg256(dst + 8 * k, o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]);
+              }
+            }
+          }
+        };
+        const int s0 = half, s1 = half + 2, s2 = half + 4, s3 = half + 6;     // this warp's slabs (BN <= 256: at most four)
+        uint32_t xa[32], xb[32], ma[NAUX], mb[NAUX];
+        if (mode != EM_BF16) { if (s0 < n_slabs) aux_load(ma, s0); if (s1 < n_slabs) aux_load(mb, s1); }
+        mbar_wait(&acc_full[buf], aph);
+        tc_fence_after();
+        if (s0 < n_slabs) tmem_ld32(t_addr + s0 * 32, xa);
+        else { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&acc_empty[buf]); }   // no slab for this warp in a narrow tile
+        if (s0 < n_slabs) { slab_step(xa, xb, ma, s0, csum[0]); if (mode != EM_BF16 && s2 < n_slabs) aux_load(ma, s2); }
+        if (s1 < n_slabs) { slab_step(xb, xa, mb, s1, csum[1]); if (mode != EM_BF16 && s3 < n_slabs) aux_load(mb, s3); }
+        if (s2 < n_slabs) slab_step(xa, xb, ma, s2, csum[2]);
+        if (s3 < n_slabs) slab_step(xb, xa, mb, s3, csum[3]);
+      }
+      if (mode == EM_BF16_MASK && g.colsum) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int col = n0 + (half + 2 * j) * 32 + lane;
+          if (half + 2 * j < n_slabs && col < g.N) atomicAdd(g.colsum + col, csum[j]);
+        }
+      }
+    } else {
     uint8_t* slab = sEpi + ew * EPI_SLAB_BYTES;
     uint8_t* srow = slab + lane * 128;
     const int rb_row = lane >> 3, rb_chunk = lane & 7;   // read-back mapping: 8 lanes cover one 128-byte row (4 columns each)
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int split = tile / (num_m * num_n), mn = tile % (num_m * num_n);
-      const int m0 = (mn / num_n) * BM, n0 = (mn % num_n) * BN;
+    CB_TL_DECL(tl);
+    const bool tl_on = (warp == 0 || warp == 4);
+    for (int tile = WRES ? w_m_first : blockIdx.x; tile < (WRES ? num_m : num_tiles); tile += (WRES ? w_m_step : gridDim.x), ++it) {
+      const int split = WRES ? 0 : tile / (num_m * num_n), mn = WRES ? 0 : tile % (num_m * num_n);
+      const int m0 = WRES ? tile * BM : (mn / num_n) * BM, n0 = WRES ? w_n0 : (mn % num_n) * BN;
       const int buf = it & 1; const uint32_t aph = (it >> 1) & 1;
       const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + buf * Cfg::ACC_STRIDE;
       const int n_lim = min(BN, g.N - n0);  // valid columns of this tile (multiple of 8)
@@ -177,8 +372,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       } else if (has_bias && last_slab >= 0 && n0 + half * 32 + rb_chunk * 4 < g.N) {
         bias_next = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + half * 32 + rb_chunk * 4));
       }
+      if (tl_on) CB_TL(1 + half, tl, 1);
       mbar_wait(&acc_full[buf], aph);
       tc_fence_after();
+      if (tl_on) CB_TL(1 + half, tl, 2);
       if (last_slab < 0) {   // nothing to do for this warp in this tile: still release the accumulator
         tc_fence_before();
         __syncwarp();
@@ -218,6 +415,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }
         tmem_ld_wait();
+        if (tl_on) CB_TL(1 + half, tl, 3);
         if (sl == last_slab) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&acc_empty[buf]); }
         if (mode == EM_BF16) {
           // bf16 outputs: bias (+ReLU) and the bf16 rounding happen in the thread=row layout (the bias of column c+lane
@@ -373,6 +571,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       }
     }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -394,19 +593,39 @@ static int encode_operand(CUtensorMap* tm, const void* base, int rows, int K, in
   return make_tmap(tm, base, 3, dims, strides, box, mode == 1 ? 3 : 2);
 }
 
+template <int BN, int AMODE, int BMODE, int EM, bool WRES>
+static int launch_k(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  const int kb_total = (g.K + BK - 1) / BK;
+  const int smem_bytes = WRES ? kb_total * Cfg::B_BYTES + WRES_A_STAGES * kb_total * Cfg::A_BYTES + EPI_BYTES + 1024 + 256 : Cfg::SMEM_BYTES;
+  static int attr_set = 0;
+  if (attr_set < smem_bytes) {
+    CB_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, AMODE, BMODE, EM, WRES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    attr_set = smem_bytes;
+  }
+  const int num_m = (g.M + BM - 1) / BM, num_n = (g.N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n * g.k_splits;
+  int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+  if (WRES) {   // a multiple of the column-tile count: CTA c owns column tile c % num_n
+    const int per_n = max(1, min(num_sms() / num_n, num_m));
+    grid = per_n * num_n;
+  }
+  gemm_kernel<BN, AMODE, BMODE, EM, WRES><<<grid, GEMM_THREADS, smem_bytes, stream>>>(tmA, tmB, g);
+  CB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// weights-resident variant: A K-major, K <= 192, no split-K, bf16 / masked-bf16 / fp32(+residual) epilogues
 template <int BN, int AMODE, int BMODE, int EM>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CB_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, AMODE, BMODE, EM>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
+  if constexpr (AMODE == 0 && (EM == EM_BF16 || EM == EM_BF16_MASK || EM == EM_F32)) {
+    const int kb_total = (g.K + BK - 1) / BK;
+    const bool fits = kb_total * Cfg::B_BYTES + WRES_A_STAGES * kb_total * Cfg::A_BYTES + EPI_BYTES + 1024 + 256 <= 227 * 1024;
+    const int num_n = (g.N + BN - 1) / BN;
+    if (g.k_splits == 1 && kb_total <= 3 && fits && num_n <= num_sms() && g.M >= 4 * BM) return launch_k<BN, AMODE, BMODE, EM, true>(tmA, tmB, g, stream);
   }
-  const int num_tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN) * g.k_splits;
-  const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-  gemm_kernel<BN, AMODE, BMODE, EM><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, g);
-  CB_CUDA(cudaGetLastError());
-  return 0;
+  return launch_k<BN, AMODE, BMODE, EM, false>(tmA, tmB, g, stream);
 }
 
 // Instantiated (operand layout, epilogue) pairs: forward products are K-major x K-major; input gradients read the weight
@@ -442,6 +661,13 @@ int gemm_run(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn,
     g.k_splits = (kb_total + kb_per - 1) / kb_per;
     CB_CHECK(g.flags & CB_EPI_ATOMIC, "gemm: split-K requires the atomic epilogue");
   }
+  {
+    const int esz = (g.flags & (CB_EPI_OUT_F32 | CB_EPI_ATOMIC)) ? 4 : 2;
+    const bool c_ok = (reinterpret_cast<uintptr_t>(g.C) & 31) == 0 && ((long)g.ldc * esz) % 32 == 0 && g.N % 8 == 0;
+    const int asz = (g.flags & CB_EPI_RESIDUAL_F32) ? 4 : 2;
+    const bool aux_ok = !(g.flags & (CB_EPI_RESIDUAL_F32 | CB_EPI_RELU_MASK)) || ((reinterpret_cast<uintptr_t>(g.aux) & 31) == 0 && ((long)g.ld_aux * asz) % 32 == 0);
+    g.direct = (c_ok && aux_ok) ? 1 : 0;
+  }
   CUtensorMap tmA, tmB;
   if (encode_operand(&tmA, A, g.M, g.K, lda, am, BM)) return 1;
   if (encode_operand(&tmB, B, g.N, g.K, ldb, bm, BN)) return 1;
@@ -453,6 +679,16 @@ int gemm_run(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn,
 }
 
 }  // namespace cb
+
+#ifdef CB_TIMELINE
+extern "C" int cb_debug_timeline_gemm(void* dst) {
+  CB_CUDA(cudaDeviceSynchronize());
+  CB_CUDA(cudaMemcpyFromSymbol(dst, cb::g_cb_timeline, sizeof(cb::g_cb_timeline)));
+  static unsigned long long zeros[CB_TL_ROLES][CB_TL_LEN];
+  CB_CUDA(cudaMemcpyToSymbol(cb::g_cb_timeline, zeros, sizeof(zeros)));
+  return 0;
+}
+#endif
 
 extern "C" int cb_gemm_bf16(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* C, int ldc, int M,
                             int N, int K, const float* bias, const void* aux, int ld_aux, int flags, float alpha,

@@ -14,6 +14,7 @@ struct GemmArgs {
   int ld_aux;
   int flags;
   float alpha;
+  int direct;             // set by gemm_run: C / aux are 32-byte aligned with 32-byte row pitches -> row-direct epilogue allowed
   float* colsum;          // optional fp32 [N]: += column sums of the stored C (EM_BF16_MASK only: bias gradient of linear1)
   // tokenizer epilogue (CB_EPI_TOKENIZE): A rows are already in packed token order (CLS rows hold zeros);
   // row t of sequence b (cu[b] <= t < cu[b+1]): off = t - cu[b]; off == 0 -> CLS row = cls_row, else

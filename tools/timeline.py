@@ -30,19 +30,27 @@ rd = getattr(lib, f"cb_debug_timeline_{which}")
 rd.argtypes, rd.restype = [C.c_void_p], C.c_int
 
 out, lse = ops.attn_fwd(qkv, lay, 2)
-for _ in range(3):
+T, F = 68664, 2048
+x16, w1, b1 = r(T, D), r(F, D), torch.randn(F, device=dev)
+hid_out = torch.empty(T, F, device=dev, dtype=bf16)
+
+
+def run():
     if which == "fwd":
         ops.attn_fwd(qkv, lay, 2)
-    else:
+    elif which == "bwd":
         ops.attn_bwd(do, qkv, out, lse, lay, 2)
+    else:   # gemm: fc1
+        ops.gemm(x16, w1, bias=b1, flags=ops.EPI_RELU, out=hid_out)
+
+
+for _ in range(3):
+    run()
 torch.cuda.synchronize()
 rd(buf.ctypes.data)  # discard warm-up
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
-if which == "fwd":
-    ops.attn_fwd(qkv, lay, 2)
-else:
-    ops.attn_bwd(do, qkv, out, lse, lay, 2)
+run()
 e1.record()
 torch.cuda.synchronize()
 print(f"# {which} {shape}: {e0.elapsed_time(e1) * 1e3:.1f} us (instrumented)")
