@@ -251,11 +251,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         };
         // one slab: accumulator wait -> next slab's TMEM read -> math -> stores.  `x` holds this slab, `nxt` receives the next
         // one (two statically indexed register sets, alternated by the unrolled sequence below); `m` = its residual / mask.
-        auto slab_step = [&](uint32_t (&x)[32], uint32_t (&nxt)[32], const uint32_t (&m)[NAUX], int sl, float& cs) {
+        auto slab_step = [&](uint32_t (&x)[32], uint32_t (&nxt)[32], const uint32_t (&m)[NAUX], int sl, int sl_next, float& cs) {
           const int c = sl * 32;
           tmem_ld_wait();
-          if (sl + 2 < n_slabs) tmem_ld32(t_addr + c + 64, nxt);                // next slab in flight under this slab's math
-          else { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&acc_empty[buf]); }   // accumulator fully read
+          if (sl_next < n_slabs) tmem_ld32(t_addr + sl_next * 32, nxt);         // next slab in flight under this slab's math
+          else { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&acc_empty[buf]); }   // accumulator fully read (the list is ascending: no later slab of this warp exists)
           if (mode == EM_BF16_MASK) {
             // d(hidden) = (dz2 . W2) where hidden > 0.  bf16 > 0  <=>  its bit pattern, read as a signed 16-bit integer, is > 0.
             uint32_t pk[16];
@@ -315,23 +315,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
           }
         };
-        const int s0 = half, s1 = half + 2, s2 = half + 4, s3 = half + 6;     // this warp's slabs (BN <= 256: at most four)
+        // this warp's slabs (BN <= 256: at most four): PAIRS of adjacent slabs, so that a thread writes 128 contiguous bytes of a
+        // bf16 row (a whole line) back to back instead of leaving every line half-written until the partner warp gets to it
+        const int s0 = 2 * half, s1 = 2 * half + 1, s2 = 2 * half + 4, s3 = 2 * half + 5;
         uint32_t xa[32], xb[32], ma[NAUX], mb[NAUX];
         if (mode != EM_BF16) { if (s0 < n_slabs) aux_load(ma, s0); if (s1 < n_slabs) aux_load(mb, s1); }
         mbar_wait(&acc_full[buf], aph);
         tc_fence_after();
         if (s0 < n_slabs) tmem_ld32(t_addr + s0 * 32, xa);
         else { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&acc_empty[buf]); }   // no slab for this warp in a narrow tile
-        if (s0 < n_slabs) { slab_step(xa, xb, ma, s0, csum[0]); if (mode != EM_BF16 && s2 < n_slabs) aux_load(ma, s2); }
-        if (s1 < n_slabs) { slab_step(xb, xa, mb, s1, csum[1]); if (mode != EM_BF16 && s3 < n_slabs) aux_load(mb, s3); }
-        if (s2 < n_slabs) slab_step(xa, xb, ma, s2, csum[2]);
-        if (s3 < n_slabs) slab_step(xb, xa, mb, s3, csum[3]);
+        if (s0 < n_slabs) { slab_step(xa, xb, ma, s0, s1, csum[0]); if (mode != EM_BF16 && s2 < n_slabs) aux_load(ma, s2); }
+        if (s1 < n_slabs) { slab_step(xb, xa, mb, s1, s2, csum[1]); if (mode != EM_BF16 && s3 < n_slabs) aux_load(mb, s3); }
+        if (s2 < n_slabs) slab_step(xa, xb, ma, s2, s3, csum[2]);
+        if (s3 < n_slabs) slab_step(xb, xa, mb, s3, n_slabs, csum[3]);
       }
       if (mode == EM_BF16_MASK && g.colsum) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int col = n0 + (half + 2 * j) * 32 + lane;
-          if (half + 2 * j < n_slabs && col < g.N) atomicAdd(g.colsum + col, csum[j]);
+          const int sj = 2 * half + (j & 1) + 4 * (j >> 1);
+          const int col = n0 + sj * 32 + lane;
+          if (sj < n_slabs && col < g.N) atomicAdd(g.colsum + col, csum[j]);
         }
       }
     } else {
