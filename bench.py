@@ -248,8 +248,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(t[0]), float(t[1])
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        finish(world)
         return
 
     peaks = {}
@@ -275,7 +274,7 @@ def main():
                           f"({ms_eager / args.steps:.1f} ms/step eager vs {ms / args.steps:.1f} ms/step timed)"}
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:   # reported on rank 0 at N = 1 only
         cores = os.cpu_count() or 1
         n_img = 8
         ips, sec = cpu_port_step(n_img, cores, reps=1, warmup=0)
@@ -306,8 +305,25 @@ def main():
         "loss": loss_val,
     }
     print(json.dumps(line), flush=True)
+    finish(world)
+
+
+def finish(world: int):
+    """Leave without tearing anything down.  With N > 1 the interpreter / NCCL / CUDA-graph teardown after the result line has
+    been seen to hang (one rank in destroy_process_group while the other already left); the run is over once rank 0 has
+    printed, so every rank meets at one last barrier (bounded by a watchdog) and exits hard."""
+    sys.stdout.flush()
+    sys.stderr.flush()
     if world > 1:
-        dist.destroy_process_group()
+        import torch.distributed as dist
+        threading.Timer(20.0, lambda: os._exit(0)).start()
+        try:
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+        except Exception:
+            pass
+    os._exit(0)
 
 
 if __name__ == "__main__":
