@@ -212,7 +212,7 @@ def main():
     launches = launches_per_step * args.steps
     # ---- instrumented eager pass of the same step: CUDA-event duration of every attention / GEMM launch (roofline)
     model.use_cuda_graph, keep = False, model.use_cuda_graph
-    ops.PROFILE = {"cb_attn_varlen_fwd": [0, 0.0, []], "cb_attn_varlen_bwd": [0, 0.0, []], "cb_gemm_bf16": [0, 0.0, []]}
+    ops.PROFILE = {"cb_attn_varlen_fwd": [0, 0.0, [], 0.0], "cb_attn_varlen_bwd": [0, 0.0, [], 0.0], "cb_gemm_bf16": [0, 0.0, [], 0.0]}
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
@@ -222,9 +222,9 @@ def main():
     ms_eager = ev0.elapsed_time(ev1)
     model.use_cuda_graph = keep
     prof = {}
-    for name, (n, work, evs) in ops.PROFILE.items():
+    for name, (n, work, evs, nbytes) in ops.PROFILE.items():
         t = sum(a.elapsed_time(b) for a, b in evs)
-        prof[name] = {"launches": n, "ms_total": t, "work": work}
+        prof[name] = {"launches": n, "ms_total": t, "work": work, "bytes": nbytes}
     ops.PROFILE = None
     loss_val = float(loss.item())
 
@@ -258,18 +258,29 @@ def main():
     except Exception:
         pass
     tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)   # kernels timed inside a long step -> sustained figure
-    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s (B200_PROFILING.md)"
-    top = max(prof, key=lambda k: prof[k]["ms_total"])
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained / hbm_gbs" if peaks else "fallback 1.4 PFLOP/s, 6.65 TB/s (B200_PROFILING.md)"
     roof = {}
     for name, p in prof.items():
-        ach = p["work"] / (p["ms_total"] * 1e-3) / 1e12 if p["ms_total"] > 0 else 0.0
+        sec = p["ms_total"] * 1e-3
+        ach = p["work"] / sec / 1e12 if sec > 0 else 0.0
+        gbs = p["bytes"] / sec / 1e9 if sec > 0 else 0.0
         roof[name] = {"launches_per_step": p["launches"] / args.steps, "ms_per_step": p["ms_total"] / args.steps,
-                      "share_of_step": p["ms_total"] / ms_eager, "achieved_tflops": ach, "frac": ach / tf_peak}
+                      "share_of_step": p["ms_total"] / ms_eager, "achieved_tflops": ach, "frac": ach / tf_peak,
+                      "achieved_gbs": gbs, "frac_hbm": gbs / hbm_peak}
+    # The dominant SINGLE kernel of the step is the attention backward (profiles/r01_launches_bench_step.txt: 13.4 % of the
+    # kernel time; the GEMM class is larger in total but is 14 instantiations over a dozen shapes, most of them HBM-bound:
+    # see "all" for its aggregate TFLOP/s and GB/s).  `traffic` = dram read + write bytes of one launch from the committed
+    # `ncu --set full` capture of the same kernel on the same ragged batch (profiles/r01_ncu_attn_bwd.txt).
+    top = "cb_attn_varlen_bwd"
     tp = prof[top]
-    roofline = {"kernel": top, "bound": "tensor", "achieved": roof[top]["achieved_tflops"], "peak": tf_peak, "unit": "TFLOP/s",
-                "frac": roof[top]["frac"], "traffic": None, "peak_source": peak_src,
-                "algorithmic_flops_per_launch": tp["work"] / max(1, tp["launches"]),
+    roofline = {"kernel": "attn_bwd_kernel<96> (cb_attn_varlen_bwd)", "bound": "tensor", "achieved": roof[top]["achieved_tflops"], "peak": tf_peak,
+                "unit": "TFLOP/s", "frac": roof[top]["frac"], "traffic": 223.1e6, "traffic_source": "profiles/r01_ncu_attn_bwd.txt",
+                "peak_source": peak_src, "algorithmic_flops_per_launch": tp["work"] / max(1, tp["launches"]),
+                "algorithmic_bytes_per_launch": tp["bytes"] / max(1, tp["launches"]),
                 "avg_launch_ms": tp["ms_total"] / max(1, tp["launches"]), "all": roof,
+                "hbm_note": "a one-directional HBM stream tops out near 3.9 TB/s (write) / 4.3 TB/s (read) on this part; only mixed "
+                            "traffic reaches the 6.55 TB/s copy figure (tools/membw.py, profiles/r01_hw_probes.txt)",
                 "timing": "CUDA events around every launch of the class in an instrumented eager pass of the same step "
                           f"({ms_eager / args.steps:.1f} ms/step eager vs {ms / args.steps:.1f} ms/step timed)"}
 

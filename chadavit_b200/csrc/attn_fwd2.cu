@@ -97,7 +97,7 @@ __device__ __forceinline__ float sub_row_max(uint32_t s_addr, int kvv) {
 // p = exp2(s * scale_log2 + neg_m) for the 64 scores, packed to bf16 in pk; returns their sum, mx_out = their maximum in the
 // exp2 domain.  The TMEM read of the second 32 columns is in flight under the first 32 columns' MUFU work.
 #ifndef CB_ATTN_POLY
-#define CB_ATTN_POLY 1
+#define CB_ATTN_POLY 0   // measured: no gain yet (688 vs 690 TFLOP/s) — the exp phase is latency-, not MUFU-bound; kept for the next round
 #endif
 template <bool RAGGED>
 __device__ __forceinline__ float sub_exp(uint32_t s_addr, float scale_log2, float neg_m, int kvv, uint32_t (&pk)[32], float& mx_out) {

@@ -31,11 +31,11 @@ def _stream():
 # kernels launched per C-ABI call (for bench.py's gpu_launches claim; memsets are not counted)
 _KERNELS_PER_CALL = {"cb_tokenize_fwd": 2, "cb_tokenize_bwd": 2, "cb_attn_varlen_bwd": 3, "cb_sync_check": 0}
 
-# Optional per-kernel-class device timing (bench.py): PROFILE[name] = [n_launches, work, [(start_evt, end_evt), ...]]
+# Optional per-kernel-class device timing (bench.py): PROFILE[name] = [n_launches, flops, [(start_evt, end_evt), ...], bytes]
 PROFILE = None
 
 
-def _call(name: str, *args, work: float = 0.0) -> None:
+def _call(name: str, *args, work: float = 0.0, nbytes: float = 0.0) -> None:
     lib = _lib.load()
     _lib.launch_count += _KERNELS_PER_CALL.get(name, 1)
     if PROFILE is not None and name in PROFILE:
@@ -47,6 +47,8 @@ def _call(name: str, *args, work: float = 0.0) -> None:
         rec[0] += 1
         rec[1] += work
         rec[2].append((e0, e1))
+        if len(rec) > 3:
+            rec[3] += nbytes
         return
     _lib.check(getattr(lib, name)(*args), name)
 
@@ -69,7 +71,8 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
         out = torch.empty(M, N, device=A.device, dtype=torch.float32 if flags & (EPI_OUT_F32 | EPI_ATOMIC) else bf16)
     assert out.shape == (M, N) and out.stride(1) == 1
     _call("cb_gemm_bf16", _p(A), A.stride(0), int(a_mn), _p(B), B.stride(0), int(b_mn), _p(out), out.stride(0), M, N, K,
-          _p(bias), _p(aux), aux.stride(0) if aux is not None else 0, flags, float(alpha), k_splits, _p(colsum), _stream(), work=2.0 * M * N * K)
+          _p(bias), _p(aux), aux.stride(0) if aux is not None else 0, flags, float(alpha), k_splits, _p(colsum), _stream(), work=2.0 * M * N * K,
+          nbytes=2.0 * (M * K + N * K) + float(M) * N * out.element_size() + (float(M) * N * aux.element_size() if aux is not None else 0.0))
     return out
 
 
@@ -249,7 +252,7 @@ def attn_fwd(qkv: torch.Tensor, lay: PackedLayout, nheads: int, *, need_lse: boo
     out = torch.empty(T, D, device=qkv.device, dtype=bf16)
     lse = torch.empty(nheads, T, device=qkv.device, dtype=torch.float32) if need_lse else None
     _call("cb_attn_varlen_fwd", _p(qkv), _p(work), work.shape[0], q_tile, _p(out), _p(lse), T, D, nheads, float(d) ** -0.5, _stream(),
-          work=4.0 * D * lay.sum_sq)
+          work=4.0 * D * lay.sum_sq, nbytes=8.0 * T * D)
     return out, lse
 
 
@@ -263,7 +266,7 @@ def attn_bwd(dout: torch.Tensor, qkv: torch.Tensor, out: torch.Tensor, lse: torc
     dq_acc = torch.empty(T, D, device=qkv.device, dtype=torch.float32)
     dqkv = torch.empty(T, D3, device=qkv.device, dtype=bf16)
     _call("cb_attn_varlen_bwd", _p(dout), _p(qkv), _p(out), _p(lse), _p(work), work.shape[0], _p(delta), _p(dq_acc), _p(dqkv), T, D,
-          nheads, float(d) ** -0.5, _stream(), work=10.0 * D * lay.sum_sq)
+          nheads, float(d) ** -0.5, _stream(), work=10.0 * D * lay.sum_sq, nbytes=18.0 * T * D)
     return dqkv
 
 

@@ -103,7 +103,9 @@ int cb_small_matmul_f32(const float* A, const float* B, float* C, int M, int N, 
  *   qkv bf16 [T, 3D] (= in_proj output: q | k | v, head h in columns h*d..(h+1)*d of each third)
  *   work int32 [n_work, 4] = {first query row (global), seq_start, seq_end, head}: one entry per q_tile query rows
  *        (q_tile = 256: two 128-row tiles per item, two softmax warpgroups, the production kernel; 128: one tile),
- *        built on the host from list_num_channels (no device sync), longest sequences first
+ *        built on the host from list_num_channels (no device sync).  The persistent kernels give CTA c the entries c, c + G,
+ *        c + 2G, ... (G = min(n_work, SM count)); the q_tile = 256 kernel and the backward skip EMPTY entries (seq_end <=
+ *        seq_start), so the host may pad the list to balance the CTAs (PackedLayout.attn_schedule: LPT assignment)
  *   out bf16 [T, D];  lse fp32 [H, T] (log-sum-exp of the scaled scores, natural log) or NULL
  */
 int cb_attn_varlen_fwd(const void* qkv, const int* work, int n_work, int q_tile, void* out, float* lse, int T, int D, int H,
