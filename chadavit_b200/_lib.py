@@ -25,6 +25,7 @@ SIGNATURES = {
     "cb_tokenize_bwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp],
     "cb_small_matmul_f32": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "cb_layernorm_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp],
+    "cb_layernorm2_fwd": [_vp, _vp, _vp, _f, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
     "cb_layernorm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],  # dy x idx g mean rstd dres dx32 dx16 dg db dc
     "cb_colsum_bf16": [_vp, _i, _vp, _i, _i, _vp],
     "cb_cast_f32_bf16": [_vp, _vp, _l, _vp],

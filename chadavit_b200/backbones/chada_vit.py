@@ -213,9 +213,9 @@ class ChAdaViT(nn.Module):
         tok, patches = ops.tokenize_fwd(x, lay, P, a.v16("token_learner.proj.weight").view(D, P * P), a.v32("token_learner.proj.bias"),
                                         pos_patch, pos[0], a.v32("cls_token").view(D), chan)
         blocks = []
-        h = tok
+        h, pre = tok, None          # pre = (u, mean, rstd) of this block's norm1(x) when the previous block already produced it
         for i in range(self.depth):
-            h, sv = self._block_fwd(i, h, lay, save)
+            h, sv, pre = self._block_fwd(i, h, lay, save, pre)
             blocks.append(sv)
         idx = lay.non_cls_rows() if self.return_all_tokens else lay.cu[:-1]
         _, out, mean, rstd = ops.layernorm_fwd(h, a.v32("norm.weight"), a.v32("norm.bias"), self.norm.eps, in_idx=idx, out_bf16=False,
@@ -226,25 +226,37 @@ class ChAdaViT(nn.Module):
         s.lay, s.patches, s.blocks, s.x_last, s.fin_idx, s.fin_mean, s.fin_rstd, s.interp, s.hw = lay, patches, blocks, h, idx, mean, rstd, interp, (H, W)
         return out, s
 
-    def _block_fwd(self, i: int, x: torch.Tensor, lay: ops.PackedLayout, save: bool):
+    def _block_fwd(self, i: int, x: torch.Tensor, lay: ops.PackedLayout, save: bool, pre_u=None):
         """x fp32 [T,D] -> x' fp32 [T,D].  The residual stream and every LayerNorm input stay fp32; bf16 is used only for
-        tensor-core operands (u, qkv, att, y, hid)."""
+        tensor-core operands (u, qkv, att, y, hid).  norm2 of this block and norm1 of the next run as ONE kernel
+        (ops.layernorm2_fwd): the third return value hands (u, mean, rstd) of the next block's norm1 to its caller."""
         a, pre = self.arena, f"blocks.{i}."
         eps = self.blocks[i].norm1.eps
         g1, b1 = a.v32(pre + "norm1.weight"), a.v32(pre + "norm1.bias")
         R = ops.EPI_RESIDUAL_F32 | ops.EPI_OUT_F32
-        u, _, m1a, r1a = ops.layernorm_fwd(x, g1, b1, eps, save_stats=save)
+        if pre_u is not None:
+            u, m1a, r1a = pre_u
+        else:
+            u, _, m1a, r1a = ops.layernorm_fwd(x, g1, b1, eps, save_stats=save)
         qkv = ops.gemm(u, a.v16(pre + "self_attn.in_proj_weight"), bias=a.v32(pre + "self_attn.in_proj_bias"))
         att, lse = ops.attn_fwd(qkv, lay, self.num_heads, need_lse=save)
         z1 = ops.gemm(att, a.v16(pre + "self_attn.out_proj.weight"), bias=a.v32(pre + "self_attn.out_proj.bias"), aux=x, flags=R)
         y, y32, m1b, r1b = ops.layernorm_fwd(z1, g1, b1, eps, out_f32=True, save_stats=save)
         hid = ops.gemm(y, a.v16(pre + "linear1.weight"), bias=a.v32(pre + "linear1.bias"), flags=ops.EPI_RELU)
         z2 = ops.gemm(hid, a.v16(pre + "linear2.weight"), bias=a.v32(pre + "linear2.bias"), aux=y32, flags=R)
-        _, out, m2, r2 = ops.layernorm_fwd(z2, a.v32(pre + "norm2.weight"), a.v32(pre + "norm2.bias"), self.blocks[i].norm2.eps,
-                                           out_bf16=False, out_f32=True, save_stats=save)
+        nxt = None
+        if i + 1 < self.depth and x.shape[1] in (64, 128, 192, 256):
+            npre = f"blocks.{i + 1}."
+            out, un, m2, r2, mn, rn = ops.layernorm2_fwd(z2, a.v32(pre + "norm2.weight"), a.v32(pre + "norm2.bias"), self.blocks[i].norm2.eps,
+                                                         a.v32(npre + "norm1.weight"), a.v32(npre + "norm1.bias"), self.blocks[i + 1].norm1.eps,
+                                                         save_stats=save)
+            nxt = (un, mn, rn)
+        else:
+            _, out, m2, r2 = ops.layernorm_fwd(z2, a.v32(pre + "norm2.weight"), a.v32(pre + "norm2.bias"), self.blocks[i].norm2.eps,
+                                               out_bf16=False, out_f32=True, save_stats=save)
         if not save:
-            return out, None
-        return out, (x, u, m1a, r1a, qkv, att, lse, z1, m1b, r1b, y, hid, z2, m2, r2)
+            return out, None, nxt
+        return out, (x, u, m1a, r1a, qkv, att, lse, z1, m1b, r1b, y, hid, z2, m2, r2), nxt
 
     # ------------------------------------------------------------------ backward on the packed layout
     def _backward_impl(self, s: _Saved, dout: torch.Tensor, gflat: torch.Tensor) -> None:

@@ -226,6 +226,76 @@ __global__ void __launch_bounds__(256) layernorm_fwd_g8_kernel(const float* __re
   }
 }
 
+// Two LayerNorms back to back on a row kept in registers: y1 = LN_a(x) (fp32: the residual stream entering the next block,
+// chada_vit.py:100 norm2) and y2 = LN_b(y1) (bf16: the next block's norm1 output, the QKV GEMM operand, chada_vit.py:96).
+// Separate launches would write y1 and read it straight back (768 of 2688 bytes per token).
+template <int NJ>
+__global__ void __launch_bounds__(256) layernorm2_fwd_g8_kernel(const float* __restrict__ x, const float* __restrict__ gamma_a,
+                                                                const float* __restrict__ beta_a, float eps_a, const float* __restrict__ gamma_b,
+                                                                const float* __restrict__ beta_b, float eps_b, float* __restrict__ y1,
+                                                                __nv_bfloat16* __restrict__ y2, float* __restrict__ mean_a,
+                                                                float* __restrict__ rstd_a, float* __restrict__ mean_b, float* __restrict__ rstd_b,
+                                                                int rows) {
+  constexpr int D = NJ * 64;
+  const int lane = threadIdx.x & 31, grp = lane >> 3, gl = lane & 7;
+  const int wg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nwg = gridDim.x * (blockDim.x >> 5);
+  for (int rb = wg * 4; rb < rows; rb += nwg * 4) {
+    const int r = rb + grp;
+    const bool ok = r < rows;
+    float v[NJ][8];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      if (ok) ld8(x + (long)r * D + j * 64 + gl * 8, v[j]);
+      else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[j][k] = 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s += v[j][k];
+    }
+    const float m_a = group8_sum(s) * (1.f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { const float d = v[j][k] - m_a; q += d * d; }
+    const float r_a = rsqrtf(group8_sum(q) * (1.f / D) + eps_a);
+    s = 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      float gg[8], bb[8];
+      ld8(gamma_a + j * 64 + gl * 8, gg); ld8(beta_a + j * 64 + gl * 8, bb);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { v[j][k] = (v[j][k] - m_a) * r_a * gg[k] + bb[k]; s += v[j][k]; }
+      if (ok && y1) st8(y1 + (long)r * D + j * 64 + gl * 8, v[j]);
+    }
+    const float m_b = group8_sum(s) * (1.f / D);
+    q = 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { const float d = v[j][k] - m_b; q += d * d; }
+    const float r_b = rsqrtf(group8_sum(q) * (1.f / D) + eps_b);
+    if (ok) {
+      if (gl == 0) {
+        if (mean_a) mean_a[r] = m_a;
+        if (rstd_a) rstd_a[r] = r_a;
+        if (mean_b) mean_b[r] = m_b;
+        if (rstd_b) rstd_b[r] = r_b;
+      }
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        float gg[8], bb[8], o[8];
+        ld8(gamma_b + j * 64 + gl * 8, gg); ld8(beta_b + j * 64 + gl * 8, bb);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = (v[j][k] - m_b) * r_b * gg[k] + bb[k];
+        st8_bf16(y2 + (long)r * D + j * 64 + gl * 8, o);
+      }
+    }
+  }
+}
+
 template <int NJ>
 __global__ void __launch_bounds__(256) layernorm_bwd_g8_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                                const int* __restrict__ idx, const float* __restrict__ gamma,
@@ -398,6 +468,19 @@ extern "C" int cb_layernorm_fwd(const float* x, const int* in_idx, const float* 
   else if (D <= 256) LNF(1); else if (D <= 512) LNF(2); else LNF(4);
 #undef LNFG
 #undef LNF
+  CB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int cb_layernorm2_fwd(const float* x, const float* gamma_a, const float* beta_a, float eps_a, const float* gamma_b,
+                                 const float* beta_b, float eps_b, float* y1_f32, void* y2_bf16, float* mean_a, float* rstd_a, float* mean_b,
+                                 float* rstd_b, int rows, int D, void* stream) {
+  CB_CHECK(rows > 0 && (D == 64 || D == 128 || D == 192 || D == 256) && y2_bf16, "layernorm2_fwd: rows=%d D=%d (D must be 64, 128, 192 or 256)", rows, D);
+  int gblocks = (rows + 31) / 32;
+  if (gblocks > num_sms() * 8) gblocks = num_sms() * 8;
+#define LN2G(N) layernorm2_fwd_g8_kernel<N><<<gblocks, 256, 0, STREAM>>>(x, gamma_a, beta_a, eps_a, gamma_b, beta_b, eps_b, y1_f32, BFM(y2_bf16), mean_a, rstd_a, mean_b, rstd_b, rows)
+  if (D == 64) LN2G(1); else if (D == 128) LN2G(2); else if (D == 192) LN2G(3); else LN2G(4);
+#undef LN2G
   CB_CUDA(cudaGetLastError());
   return 0;
 }

@@ -97,6 +97,18 @@ def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps:
     return y, y32, mean, rstd
 
 
+def layernorm2_fwd(x: torch.Tensor, gamma_a, beta_a, eps_a: float, gamma_b, beta_b, eps_b: float, *, save_stats: bool = True):
+    """y1 = LN_a(x) fp32, y2 = LN_b(y1) bf16 in one pass.  Returns (y1, y2, mean_a, rstd_a, mean_b, rstd_b)."""
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    rows, D = x.shape
+    y1 = torch.empty(rows, D, device=x.device, dtype=torch.float32)
+    y2 = torch.empty(rows, D, device=x.device, dtype=bf16)
+    st = [torch.empty(rows, device=x.device, dtype=torch.float32) if save_stats else None for _ in range(4)]
+    _call("cb_layernorm2_fwd", _p(x), _p(gamma_a), _p(beta_a), float(eps_a), _p(gamma_b), _p(beta_b), float(eps_b), _p(y1), _p(y2),
+          _p(st[0]), _p(st[1]), _p(st[2]), _p(st[3]), rows, D, _stream())
+    return (y1, y2, *st)
+
+
 def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor, *,
                   dgamma: torch.Tensor, dbeta: torch.Tensor, dcolsum: Optional[torch.Tensor] = None,
                   dres: Optional[torch.Tensor] = None, idx: Optional[torch.Tensor] = None, want_f32: bool = True,

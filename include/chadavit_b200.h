@@ -85,6 +85,14 @@ int cb_im2col_bf16(const float* x, void* patches, int G, int H, int W, int patch
  */
 int cb_layernorm_fwd(const float* x, const int* in_idx, const float* gamma, const float* beta, void* y, float* y_f32,
                      float* mean, float* rstd, int rows, int D, float eps, void* stream);
+/*
+ * Two LayerNorms back to back on rows kept in registers: y1 = LN_a(x) (fp32, may be NULL) and y2 = LN_b(y1) (bf16) —
+ * norm2 of block i (chada_vit.py:100) followed by norm1 of block i+1 (chada_vit.py:96), without writing y1 and reading it
+ * straight back.  D in {64, 128, 192, 256}.  mean/rstd of either stage fp32 [rows] or NULL.
+ */
+int cb_layernorm2_fwd(const float* x, const float* gamma_a, const float* beta_a, float eps_a, const float* gamma_b,
+                      const float* beta_b, float eps_b, float* y1_f32, void* y2_bf16, float* mean_a, float* rstd_a, float* mean_b,
+                      float* rstd_b, int rows, int D, void* stream);
 /* dx[idx[r]] = dLN(dy[r]) (+ dres[idx[r]]), written as fp32 (dx_f32) and/or bf16 (dx_bf16); dy, x, dres fp32;
  * dgamma/dbeta/dcolsum (= column sum of dLN, i.e. the bias gradient of the preceding linear) fp32 [D], ACCUMULATED. */
 int cb_layernorm_bwd(const float* dy, const float* x, const int* idx, const float* gamma, const float* mean,

@@ -11,6 +11,25 @@ def _rand(shape, seed, scale=1.0, dtype=torch.bfloat16):
     return (torch.randn(shape, generator=g) * scale).to(dtype).cuda()
 
 
+@pytest.mark.parametrize("D", [64, 192, 256])
+def test_layernorm2_fwd(D):
+    """norm2 of block i fused with norm1 of block i+1 (chada_vit.py:100, :96) == two torch LayerNorms."""
+    from chadavit_b200 import ops
+    T = 1237
+    x = _rand((T, D), 11, 2.0, dtype=torch.float32)
+    ga, gb = 1 + 0.2 * _rand((D,), 12, dtype=torch.float32), 1 + 0.2 * _rand((D,), 13, dtype=torch.float32)
+    ba, bb = 0.1 * _rand((D,), 14, dtype=torch.float32), 0.1 * _rand((D,), 15, dtype=torch.float32)
+    y1, y2, ma, ra, mb, rb = ops.layernorm2_fwd(x, ga, ba, 1e-5, gb, bb, 1e-6)
+    ops.sync_check()
+    r1 = F.layer_norm(x, (D,), ga, ba, 1e-5)
+    r2 = F.layer_norm(r1, (D,), gb, bb, 1e-6)
+    assert (y1 - r1).abs().max().item() < 1e-5 and (y2.float() - r2).abs().max().item() < 0.03
+    _, _, m_ref, r_ref = ops.layernorm_fwd(x, ga, ba, 1e-5)
+    _, _, m2_ref, r2_ref = ops.layernorm_fwd(y1, gb, bb, 1e-6)
+    assert (ma - m_ref).abs().max().item() < 1e-6 and (ra - r_ref).abs().max().item() < 1e-4 * r_ref.abs().max().item()
+    assert (mb - m2_ref).abs().max().item() < 1e-5 and (rb - r2_ref).abs().max().item() < 1e-4 * r2_ref.abs().max().item()
+
+
 @pytest.mark.parametrize("D", [32, 64, 192, 256, 768])
 def test_layernorm_fwd_bwd(D):
     from chadavit_b200 import ops
