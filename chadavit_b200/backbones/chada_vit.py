@@ -242,8 +242,12 @@ class ChAdaViT(nn.Module):
         att, lse = ops.attn_fwd(qkv, lay, self.num_heads, need_lse=save)
         z1 = ops.gemm(att, a.v16(pre + "self_attn.out_proj.weight"), bias=a.v32(pre + "self_attn.out_proj.bias"), aux=x, flags=R)
         y, y32, m1b, r1b = ops.layernorm_fwd(z1, g1, b1, eps, out_f32=True, save_stats=save)
-        hid = ops.gemm(y, a.v16(pre + "linear1.weight"), bias=a.v32(pre + "linear1.bias"), flags=ops.EPI_RELU)
-        z2 = ops.gemm(hid, a.v16(pre + "linear2.weight"), bias=a.v32(pre + "linear2.bias"), aux=y32, flags=R)
+        if ops.ffn_fused_ok(x.shape[1], FFN_DIM):   # linear1 -> ReLU -> linear2 -> +residual in one kernel; hidden stored only if saved
+            z2, hid = ops.ffn_fwd(y, a.v16(pre + "linear1.weight"), a.v32(pre + "linear1.bias"), a.v16(pre + "linear2.weight"),
+                                  a.v32(pre + "linear2.bias"), y32, save_hidden=save)
+        else:
+            hid = ops.gemm(y, a.v16(pre + "linear1.weight"), bias=a.v32(pre + "linear1.bias"), flags=ops.EPI_RELU)
+            z2 = ops.gemm(hid, a.v16(pre + "linear2.weight"), bias=a.v32(pre + "linear2.bias"), aux=y32, flags=R)
         nxt = None
         if i + 1 < self.depth and x.shape[1] in (64, 128, 192, 256):
             npre = f"blocks.{i + 1}."

@@ -1,0 +1,310 @@
+// Fused feed-forward block of the encoder layer (chada_vit.py:113-116 _ff_block, with the residual of :100):
+//     z2 = resid + relu(y W1^T + b1) W2^T + b2            y bf16 [T, D], W1 [F, D], W2 [D, F], resid / z2 fp32 [T, D]
+// in ONE kernel: the [T, F] hidden activations never go through HBM between the two GEMMs (separately, linear1 writes
+// 2F bytes per token — it sits on the HBM write roofline — and linear2 reads them back).  Optionally the hidden
+// activations are ALSO stored (bf16) for the backward pass of the student; the teacher / local-crop passes skip that.
+//
+// Structure = the attention forward with the softmax replaced by bias + ReLU.  A work item is a PAIR of 128-row tiles
+// (A, B); the hidden dimension is walked in chunks of 64 units:
+//     H_t(c)  = y_t · W1[c]^T          SS MMA, M = 128, N = 64, K = D      -> TMEM (64 fp32 columns)
+//     P_t(c)  = bf16(relu(H_t(c) + b1[c]))   by 128 threads (1 thread = 1 row), written over H_t in TMEM
+//     Z_t    += P_t(c) · W2[:, c]^T    TS MMA (A from TMEM), M = 128, N = D, K = 64     -> TMEM (D fp32 columns)
+// TMEM (D = 192): H_A 64 | H_B 64 | Z_A 192 | Z_B 192 = 512 columns.  Each weight chunk (W1[c]: 64 x D, W2[:, c]: D x 64,
+// 48 KB) is fetched once per PAIR of row tiles — with one tile per CTA the weight stream alone (96 KB per 1536 MMA clocks and
+// SM) would exceed what L2 delivers.  Warps 0-3 / 4-7: bias + ReLU (+ hidden store) and final epilogue of tile A / B;
+// warp 8: MMA issuer (convergent warp, elected lane) serving A, B, A, B ...; warp 9: TMA.  While the epilogue warps turn
+// H_A(c) into P_A(c), the tensor pipe runs Z_B += P_B(c) W2 and H_B(c+1), and vice versa.
+#include "common.cuh"
+#include "chadavit_b200.h"
+#include "internal.h"
+
+namespace cb {
+
+#ifdef CB_TIMELINE
+static __device__ unsigned long long g_cb_timeline[CB_TL_ROLES][CB_TL_LEN];
+#endif
+
+constexpr int FF_D = 192;          // model width handled by this kernel (TMEM: 2 x 64 + 2 x D <= 512)
+constexpr int FF_C = 64;           // hidden units per chunk
+constexpr int FF_KB = FF_D / 64;   // 64-wide k-blocks of D
+constexpr int FF_Y_BYTES = 128 * FF_D * 2;          // one row tile of y: FF_KB blocks of [128 x 64] (128B swizzle)
+constexpr int FF_W1_BYTES = FF_C * FF_D * 2;        // W1 chunk: FF_KB blocks of [64 x 64]
+constexpr int FF_W2_BYTES = FF_D * FF_C * 2;        // W2 chunk: [D x 64]
+constexpr int FF_S1 = 3, FF_S2 = 2;                 // ring depths of the W1 / W2 chunk slots (separate rings: a W1 slot is free as soon
+                                                    // as H(c) has retired, long before the W2 slot of the same chunk)
+constexpr int FF_MAX_F = 2048;                      // b1 is staged in shared memory
+constexpr int FF_SMEM_BYTES = 2 * FF_Y_BYTES + FF_S1 * FF_W1_BYTES + FF_S2 * FF_W2_BYTES + FF_MAX_F * 4 + 1024 /*align*/ + 512 /*barriers*/;
+constexpr int FF_COL_Z = 128;      // H_t at 64 t, Z_t at 128 + 192 t
+
+struct FfnArgs {
+  const float* b1;     // [F]
+  const float* b2;     // [D]
+  const float* resid;  // [T, D] fp32 (norm1 output, the residual of chada_vit.py:100)
+  float* z2;           // [T, D] fp32
+  __nv_bfloat16* hid;  // [T, F] bf16 or null
+  int T, F;
+};
+
+__global__ void __launch_bounds__(320, 1)
+ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
+               const FfnArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sY = smem;                                   // [2] row tiles
+  uint8_t* sW1 = sY + 2 * FF_Y_BYTES;                   // [S1] W1 chunks
+  uint8_t* sW2 = sW1 + FF_S1 * FF_W1_BYTES;             // [S2] W2 chunks
+  float* sB1 = reinterpret_cast<float*>(sW2 + FF_S2 * FF_W2_BYTES);   // [F]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB1 + FF_MAX_F);
+  uint64_t* y_full = bars + 0;              // [2]
+  uint64_t* y_empty = bars + 2;             // [2] every H_t MMA of the item has retired
+  uint64_t* w1_full = bars + 4;             // [S1]
+  uint64_t* w1_empty = w1_full + FF_S1;     // [S1] 2 arrivals (both MMA warps)
+  uint64_t* w2_full = w1_empty + FF_S1;     // [S2]
+  uint64_t* w2_empty = w2_full + FF_S2;     // [S2] 2 arrivals
+  uint64_t* h_full = w2_empty + FF_S2;      // [2] H_t(c) complete
+  uint64_t* p_full = h_full + 2;            // [2] 128 arrivals: P_t(c) written
+  uint64_t* z_full = p_full + 2;            // [2]
+  uint64_t* z_empty = z_full + 2;           // [2] 128 arrivals: Z_t read out by the epilogue
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(z_empty + 2);
+
+  constexpr int W_MMA = 8, W_TMA = 9;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = (a.T + 127) / 128, n_items = (n_tiles + 1) / 2, n_chunks = a.F / FF_C;
+  if (warp == W_TMA && lane == 0) {
+    tma_prefetch_desc(&tmY); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&y_full[i], 1); mbar_init(&y_empty[i], 1); mbar_init(&h_full[i], 1); mbar_init(&p_full[i], 128);
+      mbar_init(&z_full[i], 1); mbar_init(&z_empty[i], 128);
+    }
+    for (int i = 0; i < FF_S1; ++i) { mbar_init(&w1_full[i], 1); mbar_init(&w1_empty[i], 1); }
+    for (int i = 0; i < FF_S2; ++i) { mbar_init(&w2_full[i], 1); mbar_init(&w2_empty[i], 1); }
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < a.F; i += blockDim.x) sB1[i] = __ldg(a.b1 + i);
+  if (warp == W_MMA) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == W_TMA) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int s1 = 0, s2 = 0; uint32_t p1 = 0, p2 = 0, ni = 0, nib = 0;
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++ni) {
+        const int nt = (2 * it + 1 < n_tiles) ? 2 : 1;
+        for (int t = 0; t < nt; ++t) {
+          mbar_wait(&y_empty[t], ((t ? nib : ni) & 1) ^ 1);
+          mbar_expect_tx(&y_full[t], FF_Y_BYTES);
+#pragma unroll
+          for (int kb = 0; kb < FF_KB; ++kb) tma_load_2d(sY + t * FF_Y_BYTES + kb * (128 * 128), &tmY, &y_full[t], kb * 64, (2 * it + t) * 128);
+        }
+        if (nt == 2) ++nib;
+        for (int c = 0; c < n_chunks; ++c) {
+          mbar_wait(&w1_empty[s1], p1 ^ 1);
+          mbar_expect_tx(&w1_full[s1], FF_W1_BYTES);
+#pragma unroll
+          for (int kb = 0; kb < FF_KB; ++kb) tma_load_2d(sW1 + s1 * FF_W1_BYTES + kb * (FF_C * 128), &tmW1, &w1_full[s1], kb * 64, c * FF_C);
+          if (++s1 == FF_S1) { s1 = 0; p1 ^= 1; }
+          mbar_wait(&w2_empty[s2], p2 ^ 1);
+          mbar_expect_tx(&w2_full[s2], FF_W2_BYTES);
+          tma_load_2d(sW2 + s2 * FF_W2_BYTES, &tmW2, &w2_full[s2], c * FF_C, 0);
+          if (++s2 == FF_S2) { s2 = 0; p2 ^= 1; }
+        }
+      }
+    }
+  } else if (warp == W_MMA) {
+    // ------------------------------------------------------------------ MMA issuer (convergent warp, elected lane)
+    // ONE issuing warp serving both tiles in strict A, B, A, B order: the groups are large here (16 MMAs = 960 clk), so the
+    // ~160 clk per group on the issuing warp is amortised, and exclusive back-to-back groups keep the ping-pong tight (with
+    // one issuer per tile the two streams interleaved MMA by MMA and every group took twice as long to retire).
+    constexpr uint32_t idesc_h = umma_idesc_bf16(128, FF_C, false, false);
+    constexpr uint32_t idesc_z = umma_idesc_bf16(128, FF_D, false, false);
+    const uint64_t y_desc0 = umma_smem_desc(smem_u32(sY), 16, 1024, 3);
+    const uint64_t w1_desc0 = umma_smem_desc(smem_u32(sW1), 16, 1024, 3), w2_desc0 = umma_smem_desc(smem_u32(sW2), 16, 1024, 3);
+    int s1 = 0, s2 = 0; uint32_t p1 = 0, p2 = 0, ni = 0, nib = 0, np = 0, npb = 0;   // rings; items / p_full uses of tile A, tile B
+    CB_TL_DECL(tl);
+    auto mma_h = [&](int t, int slot) {                // H_t = y_t · W1[c]^T ; caller is the elected lane
+      const uint64_t wd = umma_desc_add(w1_desc0, slot * FF_W1_BYTES), yd = umma_desc_add(y_desc0, t * FF_Y_BYTES);
+#pragma unroll
+      for (int kb = 0; kb < FF_KB; ++kb)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_ss(tmem_base + t * FF_C, umma_desc_add(yd, kb * (128 * 128) + k * 32), umma_desc_add(wd, kb * (FF_C * 128) + k * 32), idesc_h, (kb > 0 || k > 0) ? 1u : 0u);
+      tc_commit(&h_full[t]);
+    };
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++ni) {
+      const int nt = (2 * it + 1 < n_tiles) ? 2 : 1;
+      mbar_wait(&y_full[0], ni & 1);
+      if (nt == 2) mbar_wait(&y_full[1], nib & 1);
+      mbar_wait(&w1_full[s1], p1);
+      tc_fence_after();
+      if (elect_one()) {
+        mma_h(0, s1);
+        if (nt == 2) mma_h(1, s1);
+        tc_commit(&w1_empty[s1]);
+      }
+      __syncwarp();
+      if (++s1 == FF_S1) { s1 = 0; p1 ^= 1; }
+      for (int c = 0; c < n_chunks; ++c) {
+        const bool more = c + 1 < n_chunks;
+        CB_TL(0, tl, 1);
+        mbar_wait(&w2_full[s2], p2);
+        if (more) mbar_wait(&w1_full[s1], p1);
+        CB_TL(0, tl, 2);
+        for (int t = 0; t < nt; ++t) {
+          const uint32_t npt = t ? npb : np, nit = t ? nib : ni;
+          mbar_wait(&p_full[t], npt & 1);
+          if (c == 0 && nit > 0) mbar_wait(&z_empty[t], (nit - 1) & 1);   // the previous item's Z_t has been read out (overwritten below)
+          tc_fence_after();
+          CB_TL(0, tl, 3 + t);
+          if (elect_one()) {
+            const uint64_t w2d = umma_desc_add(w2_desc0, s2 * FF_W2_BYTES);
+#pragma unroll
+            for (int kk = 0; kk < FF_C / 16; ++kk)     // Z_t += P_t(c) · W2[:, c]^T
+              umma_ts(tmem_base + FF_COL_Z + t * FF_D, tmem_base + t * FF_C + kk * 8, umma_desc_add(w2d, kk * 32), idesc_z, (c > 0 || kk > 0) ? 1u : 0u);
+            if (more) mma_h(t, s1);                    // H_t(c+1) over P_t(c): the in-order pipe has retired its reader by then
+            else { tc_commit(&y_empty[t]); tc_commit(&z_full[t]); }
+          }
+          __syncwarp();
+          if (t) ++npb; else ++np;
+        }
+        if (elect_one()) { tc_commit(&w2_empty[s2]); if (more) tc_commit(&w1_empty[s1]); }
+        __syncwarp();
+        CB_TL(0, tl, 5);
+        if (more && ++s1 == FF_S1) { s1 = 0; p1 ^= 1; }
+        if (++s2 == FF_S2) { s2 = 0; p2 ^= 1; }
+      }
+      if (nt == 2) ++nib;
+    }
+  } else {
+    // ------------------------------------------------------------------ bias + ReLU warps (tile t = 0: warps 0-3, 1: warps 4-7)
+    const int t = warp >> 2, q = warp & 3;
+    const int r_in_tile = q * 32 + lane;
+    const uint32_t lane_addr = tmem_base + (uint32_t(q * 32) << 16);
+    const uint32_t h_addr = lane_addr + t * FF_C, z_addr = lane_addr + FF_COL_Z + t * FF_D;
+    uint32_t nh = 0, ni = 0;   // h_full uses so far, items of this tile so far
+    CB_TL_DECL(tl);
+    const bool tl_on = (warp == 0 || warp == 4) && lane == 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      if (2 * it + t >= n_tiles) continue;
+      const long row = (long)(2 * it + t) * 128 + r_in_tile;
+      const bool row_ok = row < a.T;
+      for (int c = 0; c < n_chunks; ++c, ++nh) {
+        if (tl_on) CB_TL(1 + t, tl, 1);
+        mbar_wait(&h_full[t], nh & 1);
+        tc_fence_after();
+        if (tl_on) CB_TL(1 + t, tl, 2);
+        uint32_t r0[32], r1[32];
+        tmem_ld32(h_addr, r0);
+        tmem_ld32(h_addr + 32, r1);
+        tmem_ld_wait();
+        uint32_t pk[32];
+        const float* bp = sB1 + c * FF_C;                // bias of this chunk: broadcast 16-byte smem loads
+#pragma unroll
+        for (int e = 0; e < 32; e += 4) {
+          const float4 ba = *reinterpret_cast<const float4*>(bp + e), bb = *reinterpret_cast<const float4*>(bp + 32 + e);
+          pk[e >> 1] = pack_bf16(fmaxf(__uint_as_float(r0[e]) + ba.x, 0.f), fmaxf(__uint_as_float(r0[e + 1]) + ba.y, 0.f));
+          pk[(e >> 1) + 1] = pack_bf16(fmaxf(__uint_as_float(r0[e + 2]) + ba.z, 0.f), fmaxf(__uint_as_float(r0[e + 3]) + ba.w, 0.f));
+          pk[16 + (e >> 1)] = pack_bf16(fmaxf(__uint_as_float(r1[e]) + bb.x, 0.f), fmaxf(__uint_as_float(r1[e + 1]) + bb.y, 0.f));
+          pk[16 + (e >> 1) + 1] = pack_bf16(fmaxf(__uint_as_float(r1[e + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(r1[e + 3]) + bb.w, 0.f));
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {                  // P (bf16) over the first 32 columns of H_t
+          uint32_t t16[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) t16[k] = pk[h * 16 + k];
+          tmem_st16(h_addr + h * 16, t16);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&p_full[t]);
+        if (tl_on) CB_TL(1 + t, tl, 3);
+        if (a.hid && row_ok) {                         // hidden activations kept for the backward pass: 128 contiguous bytes per row
+          __nv_bfloat16* dst = a.hid + row * a.F + c * FF_C;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            stg256(dst + 16 * k, pk[8 * k], pk[8 * k + 1], pk[8 * k + 2], pk[8 * k + 3], pk[8 * k + 4], pk[8 * k + 5], pk[8 * k + 6], pk[8 * k + 7]);
+        }
+      }
+      // ---- final epilogue: z2 = Z + b2 + resid (fp32); a thread owns a row: 6 x 128 contiguous bytes
+      mbar_wait(&z_full[t], ni & 1);
+      ++ni;
+      tc_fence_after();
+#pragma unroll 1
+      for (int s = 0; s < FF_D / 32; ++s) {
+        uint32_t res[4][8];
+        if (row_ok) {
+          const float* rp = a.resid + row * FF_D + s * 32;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) ldg256(rp + 8 * k, res[k]);
+        }
+        uint32_t x[32];
+        tmem_ld32(z_addr + s * 32, x);
+        tmem_ld_wait();
+        if (row_ok) {
+          float* dst = a.z2 + row * FF_D + s * 32;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.b2 + s * 32 + 8 * k)), b1 = __ldg(reinterpret_cast<const float4*>(a.b2 + s * 32 + 8 * k + 4));
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            uint32_t o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = __float_as_uint(__uint_as_float(x[8 * k + e]) + bb[e] + __uint_as_float(res[k][e]));
+            stg256(dst + 8 * k, o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&z_empty[t]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == W_MMA) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace cb
+
+#ifdef CB_TIMELINE
+extern "C" int cb_debug_timeline_ffn(void* dst) {
+  CB_CUDA(cudaDeviceSynchronize());
+  CB_CUDA(cudaMemcpyFromSymbol(dst, cb::g_cb_timeline, sizeof(cb::g_cb_timeline)));
+  static unsigned long long zeros[CB_TL_ROLES][CB_TL_LEN];
+  CB_CUDA(cudaMemcpyToSymbol(cb::g_cb_timeline, zeros, sizeof(zeros)));
+  return 0;
+}
+#endif
+
+extern "C" int cb_ffn_fwd(const void* y, const void* w1, const float* b1, const void* w2, const float* b2, const float* resid, float* z2,
+                          void* hid, int T, int D, int F, void* stream) {
+  using namespace cb;
+  CB_CHECK(T > 0 && D == FF_D && F % FF_C == 0 && F >= FF_C && F <= FF_MAX_F, "ffn_fwd: T=%d D=%d F=%d (this kernel handles D = %d, F a multiple of %d up to %d)", T, D, F, FF_D, FF_C, FF_MAX_F);
+  CB_CHECK(((reinterpret_cast<uintptr_t>(resid) | reinterpret_cast<uintptr_t>(z2) | reinterpret_cast<uintptr_t>(hid) | reinterpret_cast<uintptr_t>(b1) |
+             reinterpret_cast<uintptr_t>(b2)) & 31) == 0, "ffn_fwd: resid / z2 / hid / biases must be 32-byte aligned");
+  static bool attr_set = false;
+  if (!attr_set) {
+    CB_CUDA(cudaFuncSetAttribute(ffn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM_BYTES));
+    attr_set = true;
+  }
+  CUtensorMap ty, t1, t2;
+  {
+    uint64_t dims[2] = {(uint64_t)D, (uint64_t)T}; uint64_t strides[1] = {(uint64_t)D * 2}; uint32_t box[2] = {64, 128};
+    if (make_tmap(&ty, y, 2, dims, strides, box, 3)) return 1;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)D, (uint64_t)F}; uint64_t strides[1] = {(uint64_t)D * 2}; uint32_t box[2] = {64, (uint32_t)FF_C};
+    if (make_tmap(&t1, w1, 2, dims, strides, box, 3)) return 1;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)F, (uint64_t)D}; uint64_t strides[1] = {(uint64_t)F * 2}; uint32_t box[2] = {64, (uint32_t)FF_D};
+    if (make_tmap(&t2, w2, 2, dims, strides, box, 3)) return 1;
+  }
+  FfnArgs a{};
+  a.b1 = b1; a.b2 = b2; a.resid = resid; a.z2 = z2; a.hid = reinterpret_cast<__nv_bfloat16*>(hid); a.T = T; a.F = F;
+  const int n_items = ((T + 127) / 128 + 1) / 2;
+  const int grid = n_items < num_sms() ? n_items : num_sms();
+  ffn_fwd_kernel<<<grid, 320, FF_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(ty, t1, t2, a);
+  CB_CUDA(cudaGetLastError());
+  return 0;
+}

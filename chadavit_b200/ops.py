@@ -76,6 +76,23 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     return out
 
 
+def ffn_fused_ok(D: int, F: int) -> bool:
+    return D == 192 and F % 64 == 0 and F <= 2048
+
+
+def ffn_fwd(y: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor, resid: torch.Tensor, *,
+            save_hidden: bool) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """z2 = resid + relu(y W1^T + b1) W2^T + b2 in one kernel (D = 192).  Returns (z2 fp32, hidden bf16 | None)."""
+    T, D = y.shape
+    F = w1.shape[0]
+    assert y.dtype == bf16 and w1.dtype == bf16 and w2.dtype == bf16 and resid.dtype == torch.float32
+    assert y.is_contiguous() and w1.is_contiguous() and w2.is_contiguous() and resid.is_contiguous() and w2.shape == (D, F)
+    z2 = torch.empty(T, D, device=y.device, dtype=torch.float32)
+    hid = torch.empty(T, F, device=y.device, dtype=bf16) if save_hidden else None
+    _call("cb_ffn_fwd", _p(y), _p(w1), _p(b1), _p(w2), _p(b2), _p(resid), _p(z2), _p(hid), T, D, F, _stream())
+    return z2, hid
+
+
 def splitk_for(K: int, tiles: int, target_ctas: int = 148) -> int:
     """Number of K splits so that a weight-gradient GEMM with `tiles` output tiles fills the GPU."""
     kb = (K + 63) // 64

@@ -126,6 +126,17 @@ int cb_attn_varlen_fwd(const void* qkv, const int* work, int n_work, int q_tile,
 int cb_attn_varlen_bwd(const void* dout, const void* qkv, const void* out, const float* lse, const int* work, int n_work,
                        float* delta_ws, float* dq_acc_ws, void* dqkv, int T, int D, int H, float softmax_scale, void* stream);
 
+/*
+ * Fused feed-forward block + residual of the encoder layer (chada_vit.py:113-116 _ff_block and the add of :100):
+ *   z2 = resid + relu(y W1^T + b1) W2^T + b2
+ * y bf16 [T, D] (norm1 output), w1 bf16 [F, D] (linear1.weight), w2 bf16 [D, F] (linear2.weight), b1 fp32 [F], b2 fp32 [D],
+ * resid / z2 fp32 [T, D].  hid bf16 [T, F] receives relu(y W1^T + b1) when not NULL (saved for the backward pass); with
+ * hid == NULL the hidden activations never leave the SM.  D must be 192 (tensor-memory budget), F a multiple of 64; other
+ * shapes use two cb_gemm_bf16 calls.
+ */
+int cb_ffn_fwd(const void* y, const void* w1, const float* b1, const void* w2, const float* b2, const float* resid, float* z2,
+               void* hid, int T, int D, int F, void* stream);
+
 /* ---------------- DINOHead pieces (src/methods/dino.py:61-111); the Linear layers themselves are cb_gemm_bf16 ---------------- */
 /* nn.GELU (exact erf): out bf16 = gelu(pre fp32);  backward: dpre bf16 = dact fp32 * gelu'(pre) */
 int cb_gelu_fwd(const float* pre, void* out, long n, void* stream);

@@ -90,3 +90,25 @@ def test_gemm_weight_grad_splitk():
     err = (dW - ref).abs().max().item()
     print(f"dW split-K: max err {err:.3e} (ref max {ref.abs().max().item():.2f})")
     assert err <= 2e-3 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("T,F", [(1000, 2048), (128, 64), (129, 128), (257, 2048), (40000, 2048), (128 * 148 * 2 + 5, 512)])
+@pytest.mark.parametrize("save_hidden", [True, False])
+def test_ffn_fused(T, F, save_hidden):
+    """cb_ffn_fwd == linear1 -> ReLU -> (bf16 rounding of the hidden activations) -> linear2 + residual (chada_vit.py:113-116, :100)."""
+    from chadavit_b200 import ops
+    D = 192
+    g = torch.Generator(device="cpu").manual_seed(T + F)
+    r = lambda *s: torch.randn(*s, generator=g)  # noqa: E731
+    y = r(T, D).to(torch.bfloat16).cuda()
+    w1, w2 = (r(F, D) / D ** 0.5).to(torch.bfloat16).cuda(), (r(D, F) / F ** 0.5).to(torch.bfloat16).cuda()
+    b1, b2, resid = r(F).cuda(), r(D).cuda(), r(T, D).cuda()
+    z2, hid = ops.ffn_fwd(y, w1, b1, w2, b2, resid, save_hidden=save_hidden)
+    ops.sync_check()
+    h_ref = torch.relu(y.float() @ w1.float().t() + b1).to(torch.bfloat16)
+    z_ref = h_ref.float() @ w2.float().t() + b2 + resid
+    assert (z2 - z_ref).abs().max().item() < 2e-2 * max(1.0, z_ref.abs().max().item())
+    if save_hidden:
+        assert (hid.float() - h_ref.float()).abs().max().item() < 2e-2 * max(1.0, h_ref.float().abs().max().item())
+    else:
+        assert hid is None

@@ -57,6 +57,9 @@ def main():
     report("fc1   [T,192]x[192,2048] +bias relu -> bf16", timeit(lambda: ops.gemm(x16, w1, bias=b1, flags=ops.EPI_RELU, out=o)), 2.0 * T * D * F, T * (D + F) * 2)
     o = torch.empty(T, D, device=dev)
     report("fc2   [T,2048]x[2048,192] +bias +res32 -> f32", timeit(lambda: ops.gemm(hid, w2, bias=b2, aux=x32, flags=R, out=o)), 2.0 * T * D * F, T * (F * 2 + D * 8))
+    zz = torch.empty(T, D, device=dev)
+    report("ffn fused fc1+relu+fc2+res (no hidden store)", timeit(lambda: ops.ffn_fwd(x16, w1, b1, w2, b2, x32, save_hidden=False)), 4.0 * T * D * F, T * (D * 2 + D * 8))
+    report("ffn fused fc1+relu+fc2+res (+ hidden store)", timeit(lambda: ops.ffn_fwd(x16, w1, b1, w2, b2, x32, save_hidden=True)), 4.0 * T * D * F, T * (D * 2 + D * 8 + F * 2))
     # ---- backward GEMMs
     o = torch.empty(T, F, device=dev, dtype=bf16)
     report("dh    [T,192]x[192,2048] (W2 MN) relu-mask", timeit(lambda: ops.gemm(x16, w2, b_mn=True, aux=hid, flags=ops.EPI_RELU_MASK, out=o)), 2.0 * T * D * F, T * (D + 2 * F) * 2)

@@ -33,6 +33,7 @@ out, lse = ops.attn_fwd(qkv, lay, 2)
 T, F = 68664, 2048
 x16, w1, b1 = r(T, D), r(F, D), torch.randn(F, device=dev)
 hid_out = torch.empty(T, F, device=dev, dtype=bf16)
+w2f, b2f, x32f = r(D, F), torch.randn(D, device=dev), torch.randn(T, D, device=dev)
 
 
 def run():
@@ -40,6 +41,8 @@ def run():
         ops.attn_fwd(qkv, lay, 2)
     elif which == "bwd":
         ops.attn_bwd(do, qkv, out, lse, lay, 2)
+    elif which == "ffn":
+        ops.ffn_fwd(x16, w1, b1, w2f, b2f, x32f, save_hidden=False)
     else:   # gemm: fc1
         ops.gemm(x16, w1, bias=b1, flags=ops.EPI_RELU, out=hid_out)
 
