@@ -212,7 +212,8 @@ def main():
     launches = launches_per_step * args.steps
     # ---- instrumented eager pass of the same step: CUDA-event duration of every attention / GEMM launch (roofline)
     model.use_cuda_graph, keep = False, model.use_cuda_graph
-    ops.PROFILE = {"cb_attn_varlen_fwd": [0, 0.0, [], 0.0], "cb_attn_varlen_bwd": [0, 0.0, [], 0.0], "cb_gemm_bf16": [0, 0.0, [], 0.0]}
+    ops.PROFILE = {"cb_attn_varlen_fwd": [0, 0.0, [], 0.0], "cb_attn_varlen_bwd": [0, 0.0, [], 0.0], "cb_gemm_bf16": [0, 0.0, [], 0.0],
+                   "cb_ffn_fwd": [0, 0.0, [], 0.0]}
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):

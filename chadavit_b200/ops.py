@@ -89,7 +89,8 @@ def ffn_fwd(y: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tenso
     assert y.is_contiguous() and w1.is_contiguous() and w2.is_contiguous() and resid.is_contiguous() and w2.shape == (D, F)
     z2 = torch.empty(T, D, device=y.device, dtype=torch.float32)
     hid = torch.empty(T, F, device=y.device, dtype=bf16) if save_hidden else None
-    _call("cb_ffn_fwd", _p(y), _p(w1), _p(b1), _p(w2), _p(b2), _p(resid), _p(z2), _p(hid), T, D, F, _stream())
+    _call("cb_ffn_fwd", _p(y), _p(w1), _p(b1), _p(w2), _p(b2), _p(resid), _p(z2), _p(hid), T, D, F, _stream(), work=4.0 * T * D * F,
+          nbytes=float(T) * (D * 2 + D * 8 + (F * 2 if save_hidden else 0)) + 4.0 * D * F)
     return z2, hid
 
 
