@@ -62,10 +62,11 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
   uint64_t* w2_full = w1_empty + FF_S1;     // [S2]
   uint64_t* w2_empty = w2_full + FF_S2;     // [S2] 2 arrivals
   uint64_t* h_full = w2_empty + FF_S2;      // [2] H_t(c) complete
-  uint64_t* p_full = h_full + 2;            // [2] 128 arrivals: P_t(c) written
+  uint64_t* p_full = h_full + 2;            // [2] 256 arrivals: P_t(c) written
   uint64_t* z_full = p_full + 2;            // [2]
-  uint64_t* z_empty = z_full + 2;           // [2] 128 arrivals: Z_t read out by the epilogue
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(z_empty + 2);
+  uint64_t* z_empty = z_full + 2;           // [2] 256 arrivals: Z_t read out by the epilogue
+  uint64_t* p_half = z_empty + 2;           // [2] 128 arrivals: column half 0 of H_t(c) has been read (half 1 may overwrite its P columns)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_half + 2);
 
   constexpr int W_MMA = 8, W_TMA = 9;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -73,8 +74,8 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
   if (warp == W_TMA && lane == 0) {
     tma_prefetch_desc(&tmY); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&y_full[i], 1); mbar_init(&y_empty[i], 1); mbar_init(&h_full[i], 1); mbar_init(&p_full[i], 128);
-      mbar_init(&z_full[i], 1); mbar_init(&z_empty[i], 128);
+      mbar_init(&y_full[i], 1); mbar_init(&y_empty[i], 1); mbar_init(&h_full[i], 1); mbar_init(&p_full[i], 256); mbar_init(&p_half[i], 128);
+      mbar_init(&z_full[i], 1); mbar_init(&z_empty[i], 256);
     }
     for (int i = 0; i < FF_S1; ++i) { mbar_init(&w1_full[i], 1); mbar_init(&w1_empty[i], 1); }
     for (int i = 0; i < FF_S2; ++i) { mbar_init(&w2_full[i], 1); mbar_init(&w2_empty[i], 1); }
@@ -178,85 +179,92 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
       if (nt == 2) ++nib;
     }
   } else {
-    // ------------------------------------------------------------------ bias + ReLU warps (tile t = 0: warps 0-3, 1: warps 4-7)
-    const int t = warp >> 2, q = warp & 3;
+    // ------------------------------------------------------------------ bias + ReLU warps
+    // ALL eight warps serve every tile: warp w owns TMEM lanes 32 (w & 3) .. (rows) and the column half hf = w >> 2 of the
+    // 64-wide chunk (bias + ReLU is element-wise: no exchange between the halves).  That halves the H -> P latency on the
+    // critical chain  H_t(c) -> P_t(c) -> Z_t += / H_t(c+1)  compared with one warpgroup per tile.
+    const int hf = warp >> 2, q = warp & 3;
     const int r_in_tile = q * 32 + lane;
     const uint32_t lane_addr = tmem_base + (uint32_t(q * 32) << 16);
-    const uint32_t h_addr = lane_addr + t * FF_C, z_addr = lane_addr + FF_COL_Z + t * FF_D;
-    uint32_t nh = 0, ni = 0;   // h_full uses so far, items of this tile so far
+    uint32_t nh0 = 0, nh1 = 0, ni0 = 0, ni1 = 0;   // h_full uses / items so far of tile A, tile B
     CB_TL_DECL(tl);
     const bool tl_on = (warp == 0 || warp == 4) && lane == 0;
     for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-      if (2 * it + t >= n_tiles) continue;
-      const long row = (long)(2 * it + t) * 128 + r_in_tile;
-      const bool row_ok = row < a.T;
-      for (int c = 0; c < n_chunks; ++c, ++nh) {
-        if (tl_on) CB_TL(1 + t, tl, 1);
-        mbar_wait(&h_full[t], nh & 1);
-        tc_fence_after();
-        if (tl_on) CB_TL(1 + t, tl, 2);
-        uint32_t r0[32], r1[32];
-        tmem_ld32(h_addr, r0);
-        tmem_ld32(h_addr + 32, r1);
-        tmem_ld_wait();
-        uint32_t pk[32];
-        const float* bp = sB1 + c * FF_C;                // bias of this chunk: broadcast 16-byte smem loads
-#pragma unroll
-        for (int e = 0; e < 32; e += 4) {
-          const float4 ba = *reinterpret_cast<const float4*>(bp + e), bb = *reinterpret_cast<const float4*>(bp + 32 + e);
-          pk[e >> 1] = pack_bf16(fmaxf(__uint_as_float(r0[e]) + ba.x, 0.f), fmaxf(__uint_as_float(r0[e + 1]) + ba.y, 0.f));
-          pk[(e >> 1) + 1] = pack_bf16(fmaxf(__uint_as_float(r0[e + 2]) + ba.z, 0.f), fmaxf(__uint_as_float(r0[e + 3]) + ba.w, 0.f));
-          pk[16 + (e >> 1)] = pack_bf16(fmaxf(__uint_as_float(r1[e]) + bb.x, 0.f), fmaxf(__uint_as_float(r1[e + 1]) + bb.y, 0.f));
-          pk[16 + (e >> 1) + 1] = pack_bf16(fmaxf(__uint_as_float(r1[e + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(r1[e + 3]) + bb.w, 0.f));
-        }
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {                  // P (bf16) over the first 32 columns of H_t
-          uint32_t t16[16];
-#pragma unroll
-          for (int k = 0; k < 16; ++k) t16[k] = pk[h * 16 + k];
-          tmem_st16(h_addr + h * 16, t16);
-        }
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(&p_full[t]);
-        if (tl_on) CB_TL(1 + t, tl, 3);
-        if (a.hid && row_ok) {                         // hidden activations kept for the backward pass: 128 contiguous bytes per row
-          __nv_bfloat16* dst = a.hid + row * a.F + c * FF_C;
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            stg256(dst + 16 * k, pk[8 * k], pk[8 * k + 1], pk[8 * k + 2], pk[8 * k + 3], pk[8 * k + 4], pk[8 * k + 5], pk[8 * k + 6], pk[8 * k + 7]);
-        }
-      }
-      // ---- final epilogue: z2 = Z + b2 + resid (fp32); a thread owns a row: 6 x 128 contiguous bytes
-      mbar_wait(&z_full[t], ni & 1);
-      ++ni;
-      tc_fence_after();
+      const int nt = (2 * it + 1 < n_tiles) ? 2 : 1;
+      for (int c = 0; c < n_chunks; ++c) {
 #pragma unroll 1
-      for (int s = 0; s < FF_D / 32; ++s) {
-        uint32_t res[4][8];
-        if (row_ok) {
-          const float* rp = a.resid + row * FF_D + s * 32;
+        for (int t = 0; t < nt; ++t) {
+          const long row = (long)(2 * it + t) * 128 + r_in_tile;
+          const uint32_t h_addr = lane_addr + t * FF_C + hf * 32;
+          if (tl_on) CB_TL(1 + hf, tl, 1 + 4 * t);
+          mbar_wait(&h_full[t], (t ? nh1 : nh0) & 1);
+          if (t) ++nh1; else ++nh0;
+          tc_fence_after();
+          if (tl_on) CB_TL(1 + hf, tl, 2 + 4 * t);
+          uint32_t r0[32];
+          tmem_ld32(h_addr, r0);
+          tmem_ld_wait();
+          uint32_t pk[16];
+          const float* bp = sB1 + c * FF_C + hf * 32;    // bias of this half chunk: broadcast 16-byte smem loads
 #pragma unroll
-          for (int k = 0; k < 4; ++k) ldg256(rp + 8 * k, res[k]);
-        }
-        uint32_t x[32];
-        tmem_ld32(z_addr + s * 32, x);
-        tmem_ld_wait();
-        if (row_ok) {
-          float* dst = a.z2 + row * FF_D + s * 32;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.b2 + s * 32 + 8 * k)), b1 = __ldg(reinterpret_cast<const float4*>(a.b2 + s * 32 + 8 * k + 4));
-            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-            uint32_t o[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) o[e] = __float_as_uint(__uint_as_float(x[8 * k + e]) + bb[e] + __uint_as_float(res[k][e]));
-            stg256(dst + 8 * k, o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]);
+          for (int e = 0; e < 32; e += 4) {
+            const float4 ba = *reinterpret_cast<const float4*>(bp + e);
+            pk[e >> 1] = pack_bf16(fmaxf(__uint_as_float(r0[e]) + ba.x, 0.f), fmaxf(__uint_as_float(r0[e + 1]) + ba.y, 0.f));
+            pk[(e >> 1) + 1] = pack_bf16(fmaxf(__uint_as_float(r0[e + 2]) + ba.z, 0.f), fmaxf(__uint_as_float(r0[e + 3]) + ba.w, 0.f));
+          }
+          // P (bf16): hidden units 32 hf .. 32 hf + 31 of the chunk -> TMEM columns 16 hf .. 16 hf + 15 of H_t.  Half 1 writes
+          // columns 16..31, which belong to half 0's fp32 input range: wait until half 0 has read its columns (it arrives on
+          // p_half after its tcgen05.ld) — half 0 itself only overwrites columns it has already read.
+          if (hf == 1) { mbar_wait(&p_half[t], (t ? nh1 : nh0) & 1 ^ 1); tc_fence_after(); }
+          else { tc_fence_before(); mbar_arrive(&p_half[t]); }
+          tmem_st16(lane_addr + t * FF_C + hf * 16, pk);
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&p_full[t]);
+          if (tl_on) CB_TL(1 + hf, tl, 3 + 4 * t);
+          if (a.hid && row < a.T) {                      // hidden activations kept for the backward pass: 64 contiguous bytes per row
+            __nv_bfloat16* dst = a.hid + row * a.F + c * FF_C + hf * 32;
+            stg256(dst, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
+            stg256(dst + 16, pk[8], pk[9], pk[10], pk[11], pk[12], pk[13], pk[14], pk[15]);
           }
         }
       }
-      tc_fence_before();
-      mbar_arrive(&z_empty[t]);
+      // ---- final epilogue: z2 = Z + b2 + resid (fp32); this warp's half: 32-column slabs hf, hf + 2, hf + 4 (128 contiguous bytes each)
+#pragma unroll 1
+      for (int t = 0; t < nt; ++t) {
+        const long row = (long)(2 * it + t) * 128 + r_in_tile;
+        const bool row_ok = row < a.T;
+        const uint32_t z_addr = lane_addr + FF_COL_Z + t * FF_D;
+        mbar_wait(&z_full[t], (t ? ni1 : ni0) & 1);
+        if (t) ++ni1; else ++ni0;
+        tc_fence_after();
+#pragma unroll 1
+        for (int s = hf; s < FF_D / 32; s += 2) {
+          uint32_t res[4][8];
+          if (row_ok) {
+            const float* rp = a.resid + row * FF_D + s * 32;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) ldg256(rp + 8 * k, res[k]);
+          }
+          uint32_t x[32];
+          tmem_ld32(z_addr + s * 32, x);
+          tmem_ld_wait();
+          if (row_ok) {
+            float* dst = a.z2 + row * FF_D + s * 32;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.b2 + s * 32 + 8 * k)), b1 = __ldg(reinterpret_cast<const float4*>(a.b2 + s * 32 + 8 * k + 4));
+              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+              uint32_t o[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) o[e] = __float_as_uint(__uint_as_float(x[8 * k + e]) + bb[e] + __uint_as_float(res[k][e]));
+              stg256(dst + 8 * k, o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]);
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&z_empty[t]);
+      }
     }
   }
   tc_fence_before();
