@@ -81,6 +81,18 @@ class ParamArena:
         off, n, shape = self.offsets[name]
         return grad_flat[off:off + n].view(shape)
 
+    def segment_maps(self):
+        """(seg_start_block int32 [P+1], seg_of_block int32 [numel/64]) on the arena's device: which parameter owns each
+        64-element block (alignment padding belongs to the parameter in front of it) — for the per-parameter norm kernels."""
+        m = getattr(self, "_segmaps", None)
+        if m is None or m[0].device != self.fp32.device:
+            starts = [self.offsets[n][0] // ALIGN for n in self.names] + [self.numel // ALIGN]
+            start = torch.tensor(starts, dtype=torch.int32)
+            counts = start[1:] - start[:-1]
+            of = torch.repeat_interleave(torch.arange(len(self.names), dtype=torch.int32), counts.long())
+            m = self._segmaps = (start.to(self.fp32.device), of.to(self.fp32.device))
+        return m
+
     def ensure_grad(self) -> torch.Tensor:
         if self.grad is None or self.grad.device != self.fp32.device:
             self.grad = torch.zeros_like(self.fp32)

@@ -191,11 +191,31 @@ class ChAdaViT(nn.Module):
             return _BackboneFn.apply(self, x, counts, *self.arena.params)
         return self._forward_impl(x, counts, save=False)[0]
 
-    def get_last_selfattention(self, x):
-        raise NotImplementedError("get_last_selfattention (main_attn.py) is outside the accelerated path in this round")
+    @torch.no_grad()
+    def get_last_selfattention(self, x: torch.Tensor) -> torch.Tensor:
+        """Attention probabilities of the last block, (ΣC, num_heads, 1+N, 1+N) fp32 (chada_vit.py:313-320; main_attn.py reads
+        ``attentions[0, :, 0, 1:]``).  The reference tokenises with ``list_num_channels=[1], max_channels=1``: every channel image
+        is a sequence of its own, and the channel token is added only by a model built with ``max_number_channels == 1``."""
+        if not x.is_cuda:
+            raise RuntimeError("chadavit_b200.ChAdaViT needs CUDA inputs (no CPU fallback)")
+        a = self._ready()
+        counts = (1,) * x.shape[0]
+        h, lay, _, _ = self._tokenize(x, counts, chan_rule=1)
+        pre = None
+        for i in range(self.depth - 1):
+            h, _, pre = self._block_fwd(i, h, lay, False, pre)
+        p = f"blocks.{self.depth - 1}."
+        if pre is not None:
+            u = pre[0]
+        else:
+            u, _, _, _ = ops.layernorm_fwd(h, a.v32(p + "norm1.weight"), a.v32(p + "norm1.bias"), self.blocks[-1].norm1.eps, save_stats=False)
+        qkv = ops.gemm(u, a.v16(p + "self_attn.in_proj_weight"), bias=a.v32(p + "self_attn.in_proj_bias"))
+        return ops.attn_probs(qkv, lay, self.num_heads)
 
-    # ------------------------------------------------------------------ forward on the packed layout
-    def _forward_impl(self, x: torch.Tensor, counts: Sequence[int], save: bool):
+    def _tokenize(self, x: torch.Tensor, counts: Sequence[int], chan_rule: int = PAD_CHANNELS):
+        """Packed tokens of a ragged batch: (tokens fp32 [T,D], layout, bf16 patches, interp map or None).  The channel token is
+        added iff ``self.max_channels == chan_rule`` (chada_vit.py:248: ``max_channels == self.max_channels`` with the
+        ``max_channels`` argument 10 in forward and 1 in get_last_selfattention)."""
         a = self.arena
         D, P = self.embed_dim, self.token_learner.patch_size
         G, _, H, W = x.shape
@@ -209,9 +229,16 @@ class ChAdaViT(nn.Module):
         else:
             interp = self._interp_matrix(hp, wp, H, W, x.device)
             pos_patch = ops.small_matmul_f32(interp, pos[1:])
-        chan = a.v32("channel_token").view(self.max_channels, D) if self.max_channels == PAD_CHANNELS else None  # chada_vit.py:248
+        chan = a.v32("channel_token").view(self.max_channels, D) if self.max_channels == chan_rule else None
         tok, patches = ops.tokenize_fwd(x, lay, P, a.v16("token_learner.proj.weight").view(D, P * P), a.v32("token_learner.proj.bias"),
                                         pos_patch, pos[0], a.v32("cls_token").view(D), chan)
+        return tok, lay, patches, interp
+
+    # ------------------------------------------------------------------ forward on the packed layout
+    def _forward_impl(self, x: torch.Tensor, counts: Sequence[int], save: bool):
+        a = self.arena
+        H, W = x.shape[2], x.shape[3]
+        tok, lay, patches, interp = self._tokenize(x, counts)
         blocks = []
         h, pre = tok, None          # pre = (u, mean, rstd) of this block's norm1(x) when the previous block already produced it
         for i in range(self.depth):

@@ -168,6 +168,15 @@ def _cfg(cfg, path: str, default=None):
     return default if cur is None else cur
 
 
+class StagedBatch(tuple):
+    """``(crops on the device, targets, num_channels_lists)`` whose crops are still being copied (``DINO.stage_batch``)."""
+
+    def __new__(cls, items, buffer_set):
+        self = super().__new__(cls, items)
+        self.set = buffer_set
+        return self
+
+
 class DINO(nn.Module):
     """DINO method without the Lightning shell: same sub-module names as the reference LightningModule
     (``backbone``, ``momentum_backbone``, ``head``, ``momentum_head``, ``dino_loss_func``, ``momentum_updater``) so
@@ -218,6 +227,16 @@ class DINO(nn.Module):
         self.betas = tuple(_cfg(cfg, "optimizer.kwargs.betas", (0.9, 0.999)))
         self.adam_eps = _cfg(cfg, "optimizer.kwargs.eps", 1e-8)
         self.exclude_bias_n_norm_wd = bool(_cfg(cfg, "optimizer.exclude_bias_n_norm_wd", False))
+        # base.py:67-72 offers sgd / lars / adam / adamw; the ChAda-ViT pre-training configs use LARS
+        # (scripts/*/dino_chada_vit_moyen.yaml: lr 0.3, eta 0.02, clip_lr, exclude_bias_n_norm; momentum 0.9 from
+        # src/args/pretrain.py:220-221).  The engine path implements adamw (default here) and lars.
+        self.optimizer = str(_cfg(cfg, "optimizer.name", "adamw")).lower()
+        if self.optimizer not in ("adamw", "lars"):
+            raise NotImplementedError(f"optimizer '{self.optimizer}': the fused engine implements 'adamw' and 'lars'")
+        self.lars = {"momentum": float(_cfg(cfg, "optimizer.kwargs.momentum", 0.9)), "dampening": float(_cfg(cfg, "optimizer.kwargs.dampening", 0.0)),
+                     "nesterov": bool(_cfg(cfg, "optimizer.kwargs.nesterov", False)), "eta": float(_cfg(cfg, "optimizer.kwargs.eta", 1e-3)),
+                     "eps": float(_cfg(cfg, "optimizer.kwargs.eps", 1e-8)), "clip_lr": bool(_cfg(cfg, "optimizer.kwargs.clip_lr", False)),
+                     "exclude_bias_n_norm": bool(_cfg(cfg, "optimizer.kwargs.exclude_bias_n_norm", False))}
         self.current_epoch = 0
         self.global_step = 0
         self.max_steps = _cfg(cfg, "max_steps", 100000)
@@ -225,8 +244,7 @@ class DINO(nn.Module):
         self._opt: Dict[str, Dict[str, torch.Tensor]] = {}
         self.use_cuda_graph = bool(_cfg(cfg, "engine.cuda_graph", False))
         self._graphs: Dict[tuple, dict] = {}
-        if self.clip_grad:
-            raise NotImplementedError("clip_grad > 0 (per-parameter clipping, dino.py:249-261) is not implemented in this round")
+        self._staging: Optional[dict] = None
 
     # ------------------------------------------------------------------ reference-shaped pieces
     @property
@@ -264,7 +282,29 @@ class DINO(nn.Module):
         mz = [self.momentum_forward(x, i)["z"] for i, x in enumerate(X[:nl])]
         return self.dino_loss_func(torch.cat(z), torch.cat(mz))
 
+    def dino_clip_gradients(self, clip: float):
+        """Per-parameter clipping of the backbone gradients (dino.py:249-261): one norm pass + one scaling pass over the flat
+        gradient arena instead of a host-synchronising ``.norm()`` per tensor.  Works on the ``.grad`` tensors autograd left."""
+        a = self.backbone._ready()
+        g = a.ensure_grad()
+        g.zero_()
+        have = torch.zeros(len(a.names), dtype=torch.uint8)
+        for i, (n, p) in enumerate(zip(a.names, a.params)):
+            if p.grad is not None:
+                a.g32(n, g).copy_(p.grad)
+                have[i] = 1
+        start, of = a.segment_maps()
+        partial = torch.empty(a.numel // 32, device=g.device, dtype=torch.float32)
+        norms = torch.empty(len(a.names) * 3, device=g.device, dtype=torch.float32)
+        ops.param_norms(a.fp32, g, start, have.to(g.device), partial, norms, grad_scale=1.0, clip=float(clip))
+        ops.scale_grads(g, of, norms)
+        for n, p in zip(a.names, a.params):
+            if p.grad is not None:
+                p.grad.copy_(a.g32(n, g))
+
     def on_after_backward(self):
+        if self.clip_grad:                                                           # dino.py:371-372
+            self.dino_clip_gradients(self.clip_grad)
         if self.current_epoch < self.freeze_last_layer:                              # dino.py:374-376
             for p in self.head.last_layer.parameters():
                 p.grad = None
@@ -278,6 +318,9 @@ class DINO(nn.Module):
         self.momentum_updater.update_tau(cur_step=self.global_step, max_steps=self.max_steps)
 
     def configure_optimizers(self):
+        """A stock torch optimizer for the autograd drop-in path (AdamW only; LARS lives in the fused engine step)."""
+        if self.optimizer != "adamw":
+            raise NotImplementedError("configure_optimizers: only AdamW has a stock torch counterpart; use fused_train_step for LARS")
         params = [{"params": list(self.backbone.parameters())}, {"params": list(self.head.parameters())}]
         return torch.optim.AdamW(params, lr=self.lr, weight_decay=self.weight_decay, betas=self.betas, eps=self.adam_eps)
 
@@ -292,21 +335,50 @@ class DINO(nn.Module):
                 flags[off:off + cnt] = (1 if decay else 0) | (0 if p.requires_grad else 2)
             # alignment padding between parameters: frozen
             used = torch.zeros(arena.numel, dtype=torch.bool)
-            for n in arena.names:
+            for n, p in zip(arena.names, arena.params):
                 off, cnt, _ = arena.offsets[n]
                 used[off:off + cnt] = True
+                if p.dim() != 1 or not self.lars["exclude_bias_n_norm"]:
+                    flags[off:off + cnt] |= 4                                  # LARS layer-wise adaptation (lars.py:136)
             flags[~used] = 2
-            st = {"m": torch.zeros_like(arena.fp32), "v": torch.zeros_like(arena.fp32), "flags": flags.to(arena.fp32.device),
-                  "flags_frozen_last": None}
+            dev = arena.fp32.device
+            st = {"m": torch.zeros_like(arena.fp32), "flags": flags.to(dev), "flags_frozen_last": None, "variants": {}, "stepped": set()}
+            if self.optimizer == "adamw":
+                st["v"] = torch.zeros_like(arena.fp32)
+            if self.optimizer == "lars" or (self.clip_grad and name == "backbone"):
+                st["partial"] = torch.empty(arena.numel // 32, device=dev, dtype=torch.float32)
+                st["norms"] = torch.zeros(len(arena.names) * 3, device=dev, dtype=torch.float32)
+                st["seg_clip"] = torch.tensor([1 if p.requires_grad else 0 for p in arena.params], dtype=torch.uint8, device=dev)
             if name == "head":
                 fl = flags.clone()
                 for n in arena.names:
                     if n.startswith("last_layer."):
                         off, cnt, _ = arena.offsets[n]
                         fl[off:off + cnt] = 2
-                st["flags_frozen_last"] = fl.to(arena.fp32.device)
+                st["flags_frozen_last"] = fl.to(dev)
             self._opt[name] = st
         return st
+
+    def _lars_first_flags(self, name: str, arena: ParamArena, st: dict, frozen_last: bool) -> torch.Tensor:
+        """LARS creates a parameter's momentum buffer as a copy of its first update (lars.py:151-152); with dampening == 0 that
+        equals the zero-initialised buffer the kernel starts from, otherwise the first update carries flag bit3."""
+        base = st["flags_frozen_last"] if frozen_last else st["flags"]
+        if self.lars["dampening"] == 0.0 or self.lars["momentum"] == 0.0:
+            return base
+        first = tuple(n for n, p in zip(arena.names, arena.params)
+                      if p.requires_grad and n not in st["stepped"] and not (frozen_last and n.startswith("last_layer.")))
+        for n in first:
+            st["stepped"].add(n)
+        if not first:
+            return base
+        key = (frozen_last, first)
+        if key not in st["variants"]:
+            fl = (st["flags_frozen_last"] if frozen_last else st["flags"]).clone()
+            for n in first:
+                off, cnt, _ = arena.offsets[n]
+                fl[off:off + cnt] |= 8
+            st["variants"][key] = fl
+        return st["variants"][key]
 
     @torch.no_grad()
     def _step_device_work(self, X, list_num_channels, *, lr: float, tau: float, step: int, world: int, dev_hyper=None) -> torch.Tensor:
@@ -357,13 +429,63 @@ class DINO(nn.Module):
         # AdamW + teacher EMA + bf16 refresh of student and teacher, one launch per network
         for name, on, mo, g in (("backbone", bb, tb, gb), ("head", hd, th, gh)):
             st = self._opt_state(name, on.arena)
-            flags = st["flags"]
-            if name == "head" and self.current_epoch < self.freeze_last_layer:
-                flags = st["flags_frozen_last"]
+            frozen_last = name == "head" and self.current_epoch < self.freeze_last_layer
+            flags = st["flags_frozen_last"] if frozen_last else st["flags"]
+            clip = float(self.clip_grad) if (self.clip_grad and name == "backbone") else 0.0
+            if "norms" in st:       # per-parameter ||p||, ||g|| and the DINO clip coefficient (deterministic, no host sync)
+                start, seg_of = on.arena.segment_maps()
+                ops.param_norms(on.arena.fp32, g, start, st["seg_clip"], st["partial"], st["norms"], grad_scale=1.0 / world, clip=clip)
+            if self.optimizer == "lars":
+                o = self.lars
+                ops.lars_step(on.arena.fp32, g, st["m"], self._lars_first_flags(name, on.arena, st, frozen_last), seg_of, st["norms"],
+                              lr=lr, momentum=o["momentum"], dampening=o["dampening"], nesterov=o["nesterov"],
+                              weight_decay=self.weight_decay, eta=o["eta"], eps=o["eps"], clip_lr=o["clip_lr"], p_bf16=on.arena.bf16,
+                              teacher=mo.arena.fp32, teacher_bf16=mo.arena.bf16, grad_scale=1.0 / world, tau=tau, dev_hyper=dev_hyper)
+                continue
+            if clip:
+                ops.scale_grads(g, seg_of, st["norms"])
             ops.adamw_step(on.arena.fp32, g, st["m"], st["v"], lr=lr, beta1=self.betas[0], beta2=self.betas[1], eps=self.adam_eps,
                            weight_decay=self.weight_decay, step=step, flags=flags, p_bf16=on.arena.bf16,
                            teacher=mo.arena.fp32, teacher_bf16=mo.arena.bf16, grad_scale=1.0 / world, tau=tau, dev_hyper=dev_hyper)
         return loss
+
+    def stage_batch(self, batch: Sequence[Any]) -> "StagedBatch":
+        """Start the host->device copy of a collated batch ``(crops, targets, num_channels_lists)`` (pinned host crops,
+        channels_strategies.py:31-85 contract) on the engine's copy stream and return at once.  The result is passed to
+        ``fused_train_step`` in place of the batch; the step waits for the copy on the device, never on the host.  Two
+        device buffer sets alternate, so the copy of batch i+1 runs under the compute of batch i:
+
+            nxt = model.stage_batch(next(it))
+            while nxt is not None:
+                cur, nxt = nxt, None
+                loss = model.fused_train_step(cur)          # asynchronous
+                nxt = model.stage_batch(next(it, None))     # H2D of the next batch overlaps the step just launched
+                loss.item()
+        """
+        X, targets, list_num_channels = batch
+        X = [X] if isinstance(X, torch.Tensor) else list(X)
+        self.backbone._ready()
+        dev = self.backbone.arena.fp32.device
+        st = self._staging
+        if st is None or st["device"] != dev:
+            st = self._staging = {"device": dev, "stream": torch.cuda.Stream(device=dev), "sets": [{}, {}], "next": 0}
+        s = st["sets"][st["next"]]
+        st["next"] ^= 1
+        shapes = tuple(tuple(x.shape) for x in X)
+        cs: torch.cuda.Stream = st["stream"]
+        if s.get("shapes") != shapes:
+            s["shapes"] = shapes
+            s["x"] = [torch.empty(sh, device=dev, dtype=torch.float32) for sh in shapes]
+            s["consumed"] = None
+            cs.wait_stream(torch.cuda.current_stream(dev))     # fresh blocks may still be in use by queued work of this stream
+        elif s["consumed"] is not None:
+            cs.wait_event(s["consumed"])                       # the step that read this set two batches ago has finished with it
+        with torch.cuda.stream(cs):
+            for d, x in zip(s["x"], X):
+                d.copy_(x, non_blocking=True)
+            s["ready"] = torch.cuda.Event()
+            s["ready"].record(cs)
+        return StagedBatch((s["x"], targets, list_num_channels), s)
 
     @torch.no_grad()
     def fused_train_step(self, batch: Sequence[Any], lr: Optional[float] = None) -> torch.Tensor:
@@ -373,12 +495,15 @@ class DINO(nn.Module):
         With ``self.use_cuda_graph`` the device work of a batch *signature* (channel counts per crop + shapes) is captured
         into a CUDA graph the second time that signature is seen and replayed afterwards (inputs are copied into static
         buffers; lr / bias corrections / tau are read from device memory), which removes the per-launch host overhead."""
+        staged = batch.set if isinstance(batch, StagedBatch) else None
         X, _targets, list_num_channels = batch
         X = [X] if isinstance(X, torch.Tensor) else list(X)
         assert len(X) == self.num_crops
         bb, tb, hd, th = self.backbone, self.momentum_backbone, self.head, self.momentum_head
         for m in (bb, tb, hd, th):
             m._ready()
+        if staged is not None:
+            torch.cuda.current_stream().wait_event(staged["ready"])
         world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
         self.global_step += 1
         lr = self.lr if lr is None else lr
@@ -391,6 +516,9 @@ class DINO(nn.Module):
             dev = bb.arena.fp32.device
             X = [x if x.is_cuda else x.to(dev, non_blocking=True) for x in X]    # host (pinned) crops are accepted
             loss = self._step_device_work(X, list_num_channels, lr=lr, tau=tau, step=step, world=world)
+        if staged is not None:
+            staged["consumed"] = torch.cuda.Event()
+            staged["consumed"].record()
         for ar in (bb.arena, tb.arena, hd.arena, th.arena):
             ar.mark_dirty()
             ar._bf16_key = (ar.manual_version, sum(p._version for p in ar.params))   # shadows were refreshed by the kernel
@@ -413,7 +541,6 @@ class DINO(nn.Module):
             try:
                 dev = self.backbone.arena.fp32.device
                 ent["x"] = [torch.empty(x.shape, device=dev, dtype=torch.float32) for x in X]
-                ent["hyper_host"] = torch.zeros(4, dtype=torch.float32).pin_memory()
                 ent["hyper"] = torch.zeros(4, dtype=torch.float32, device=dev)
                 for d, x in zip(ent["x"], X):
                     d.copy_(x, non_blocking=True)
@@ -433,7 +560,8 @@ class DINO(nn.Module):
             for d, x in zip(ent["x"], X):          # H2D (pinned host crops) or D2D into the graph's static input buffers
                 if d.data_ptr() != x.data_ptr():
                     d.copy_(x, non_blocking=True)
-        ent["hyper_host"].copy_(torch.tensor(hyper, dtype=torch.float32))
-        ent["hyper"].copy_(ent["hyper_host"], non_blocking=True)
+        # 16 bytes from PAGEABLE memory: the driver copies them into the command stream at call time, so the host may queue many
+        # steps ahead without a later step's scalars overwriting an earlier step's (a reused pinned buffer would race)
+        ent["hyper"].copy_(torch.tensor(hyper, dtype=torch.float32), non_blocking=True)
         ent["graph"].replay()
         return ent["loss"]

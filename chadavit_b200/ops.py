@@ -7,6 +7,8 @@ from __future__ import annotations
 
 from typing import List, Optional, Sequence, Tuple
 
+import math
+
 import numpy as np
 import torch
 
@@ -29,7 +31,7 @@ def _stream():
 
 
 # kernels launched per C-ABI call (for bench.py's gpu_launches claim; memsets are not counted)
-_KERNELS_PER_CALL = {"cb_tokenize_fwd": 2, "cb_tokenize_bwd": 2, "cb_attn_varlen_bwd": 3, "cb_sync_check": 0}
+_KERNELS_PER_CALL = {"cb_tokenize_fwd": 2, "cb_tokenize_bwd": 2, "cb_attn_varlen_bwd": 3, "cb_sync_check": 0, "cb_param_norms": 2}
 
 # Optional per-kernel-class device timing (bench.py): PROFILE[name] = [n_launches, flops, [(start_evt, end_evt), ...], bytes]
 PROFILE = None
@@ -389,3 +391,35 @@ def adamw_step(p, g, m, v, *, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay
     """dev_hyper: optional device fp32[4] {lr, 1-beta1^step, sqrt(1-beta2^step), tau} read by the kernel (CUDA-graph replay)."""
     _call("cb_adamw_step", _p(p), _p(g), _p(m), _p(v), _p(flags), _p(p_bf16), _p(teacher), _p(teacher_bf16), p.numel(), float(lr),
           float(beta1), float(beta2), float(eps), float(weight_decay), int(step), float(grad_scale), float(tau), _p(dev_hyper), _stream())
+
+
+def param_norms(p, g, seg_start_block, seg_clip, partial, norms, *, grad_scale=1.0, clip=0.0) -> None:
+    """norms[s] = (||p_s||, ||g_s*grad_scale*coef_s||, coef_s) per parameter of a flat arena (deterministic two-pass reduction);
+    coef_s is the dino_clip_gradients coefficient (dino.py:249-261) where seg_clip[s] != 0 and clip > 0, else 1."""
+    _call("cb_param_norms", _p(p), _p(g), _p(seg_start_block), _p(seg_clip), _p(partial), _p(norms), p.numel(),
+          seg_start_block.numel() - 1, float(grad_scale), float(clip), _stream())
+
+
+def scale_grads(g, seg_of_block, norms) -> None:
+    """g *= coef of the owning parameter, in place (the clip coefficients computed by ``param_norms``)."""
+    _call("cb_scale_grads", _p(g), _p(seg_of_block), _p(norms), g.numel(), _stream())
+
+
+def lars_step(p, g, buf, flags, seg_of_block, norms, *, lr, momentum=0.0, dampening=0.0, nesterov=False, weight_decay=0.0, eta=1e-3,
+              eps=1e-8, clip_lr=False, p_bf16=None, teacher=None, teacher_bf16=None, grad_scale=1.0, tau=1.0, dev_hyper=None) -> None:
+    """LARS.step (src/utils/lars.py:113-167) over a flat arena + teacher EMA + bf16 shadows, one launch."""
+    _call("cb_lars_step", _p(p), _p(g), _p(buf), _p(flags), _p(seg_of_block), _p(norms), _p(p_bf16), _p(teacher), _p(teacher_bf16),
+          p.numel(), float(lr), float(momentum), float(dampening), int(bool(nesterov)), float(weight_decay), float(eta), float(eps),
+          int(bool(clip_lr)), float(grad_scale), float(tau), _p(dev_hyper), _stream())
+
+
+def attn_probs(qkv: torch.Tensor, lay: "PackedLayout", num_heads: int) -> torch.Tensor:
+    """softmax(q k^T / sqrt(d)) per sequence and head as a dense fp32 (nseq, H, S_max, S_max) tensor (zero beyond a sequence's
+    length) — the last block's attention map for get_last_selfattention (chada_vit.py:313-320)."""
+    D = qkv.shape[1] // 3
+    d = D // num_heads
+    nseq = lay.cu.numel() - 1
+    s_max = int(lay.max_seqlen)
+    out = torch.empty(nseq, num_heads, s_max, s_max, device=qkv.device, dtype=torch.float32)
+    _call("cb_attn_probs", _p(qkv), _p(lay.cu), nseq, num_heads, d, s_max, 1.0 / math.sqrt(d), _p(out), _stream())
+    return out

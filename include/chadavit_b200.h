@@ -173,6 +173,34 @@ int cb_adamw_step(float* p, const float* g, float* m, float* v, const unsigned c
                   void* teacher_bf16, long n, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
                   float grad_scale, float tau, const float* dev_hyper, void* stream);
 
+/* Attention probabilities of one block for ChAdaViT.get_last_selfattention (src/backbones/vit/chada_vit.py:313-320, read by
+ * main_attn.py:200-207): out[b, h, i, j] = softmax_j(q_i . k_j * scale) over the tokens of packed sequence b; qkv is the
+ * packed bf16 [T, 3*H*d] projection (rows q | k | v, head h = columns h*d..), out is fp32 [nseq, H, max_seqlen, max_seqlen],
+ * entries beyond a sequence's length are zero. */
+int cb_attn_probs(const void* qkv, const int* cu_seqlens, int nseq, int num_heads, int head_dim, int max_seqlen, float scale,
+                  float* out, void* stream);
+
+/* Per-parameter L2 norms over a flat arena whose parameters start at 64-element aligned offsets.
+ * seg_start_block[nseg+1]: first 64-element block of every parameter (int32, ascending; padding belongs to the parameter
+ * in front of it and holds zeros).  partial: workspace of (n/64)*2 floats.  Output norms[3*s + {0,1,2}] =
+ * { ||p_s||, ||g_s * grad_scale * coef_s||, coef_s } with coef_s = min(1, clip / (||g_s * grad_scale|| + 1e-6)) where
+ * seg_clip[s] != 0 and clip > 0 — DINO.dino_clip_gradients (src/methods/dino.py:249-261), else 1.  Two launches, no atomics:
+ * the result is bit-reproducible, so data-parallel replicas stay identical. */
+int cb_param_norms(const float* p, const float* g, const int* seg_start_block, const unsigned char* seg_clip, float* partial,
+                   float* norms, long n, int nseg, float grad_scale, float clip, void* stream);
+/* g[i] *= coef of the parameter that owns element i (seg_of_block: int32 per 64-element block; norms from cb_param_norms):
+ * the in-place form of dino_clip_gradients, for optimizers that do not take the coefficient themselves (cb_adamw_step). */
+int cb_scale_grads(float* g, const int* seg_of_block, const float* norms, long n, void* stream);
+/* LARS.step over a flat arena (src/utils/lars.py:113-167), fused with the teacher EMA and the bf16 shadow refresh like
+ * cb_adamw_step.  flags[i]: bit0 = the group's weight decay applies (0 otherwise: base.py:426-427), bit1 = frozen / no
+ * gradient, bit2 = layer-wise adaptation applies (p.ndim != 1 or not exclude_bias_n_norm), bit3 = first update of this
+ * parameter (momentum buffer := d_p).  The gradient used is g * grad_scale * coef_s.  dev_hyper (optional, device fp32[4];
+ * slots 0 = lr and 3 = tau are read) serves CUDA-graph replay. */
+int cb_lars_step(float* p, const float* g, float* buf, const unsigned char* flags, const int* seg_of_block, const float* norms,
+                 void* p_bf16, float* teacher, void* teacher_bf16, long n, float lr, float momentum, float dampening,
+                 int nesterov, float weight_decay, float eta, float eps, int clip_lr, float grad_scale, float tau,
+                 const float* dev_hyper, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

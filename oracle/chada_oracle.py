@@ -13,6 +13,10 @@ path uses), every function of SURVEY.md §8(a):
   dino_loss             src/losses/dino.py:69-118
   ema_update / cosine_tau   src/utils/momentum.py:63-87
   dino_step             src/methods/base.py:695-707,1216-1218 + src/methods/dino.py:279,296,313-317
+  last_selfattention    src/backbones/vit/chada_vit.py:313-320 (+ :90-97 return_attention, :105-111 need_weights)
+  clip_gradients        src/methods/dino.py:249-261
+  lars_step             src/utils/lars.py:113-167
+  one_channel_collate   src/data/channels_strategies.py:31-85
 
 Parameters are dicts keyed by the reference's state-dict names.  All functions are
 differentiable through torch autograd, which is how the tests obtain reference gradients.
@@ -279,3 +283,92 @@ def packed_index(counts: Sequence[int], npatch: int) -> Tuple[List[int], List[in
         rows.extend(b * S_pad + r for r in range(n))
         cu.append(cu[-1] + n)
     return cu, rows
+
+
+# --------------------------------------------------------------------------- §8(f) rows: attention maps, clip, LARS, collate
+def last_selfattention(x: Tensor, P: Dict[str, Tensor], *, nhead: int, patch: int = 16, depth: int = 12) -> Tensor:
+    """ChAdaViT.get_last_selfattention (chada_vit.py:313-320): every channel image is its own single-channel sequence
+    (``list_num_channels=[1]`` makes ``torch.split`` cut chunks of one; ``max_channels=1`` means no padding and — because
+    1 != self.max_channels — no channel token); blocks 0..depth-2 run normally; the last block returns the attention
+    probabilities of ``self_attn(norm1(x))`` per head (``average_attn_weights=False``): (ΣC, nhead, 1+N, 1+N)."""
+    _, _, w, h = x.shape
+    tok = patch_embed(x, P["token_learner.proj.weight"], P["token_learner.proj.bias"], patch)     # (G, N, D)
+    G, N, D = tok.shape
+    mask = torch.cat([tok.new_zeros(G, 1, dtype=torch.bool), (tok == 0).all(-1)], 1)              # :239,267 (all False in practice)
+    emb = tok + interp_pos_embed(P["pos_embed"], N, w, h, patch)[:, 0]
+    cls = (P["cls_token"] + P["pos_embed"][:, :, 0]).expand(G, -1, -1)
+    hcur = torch.cat([cls, emb], 1)
+    for i in range(depth - 1):
+        hcur = encoder_layer(hcur, mask, P, f"blocks.{i}.", nhead)
+    pre = f"blocks.{depth - 1}."
+    u = F.layer_norm(hcur, (D,), P[pre + "norm1.weight"], P[pre + "norm1.bias"], 1e-5)
+    S, d = u.shape[1], D // nhead
+    qkv = _q(_q(u) @ _q(P[pre + "self_attn.in_proj_weight"]).t() + P[pre + "self_attn.in_proj_bias"])
+    q, k, _v = qkv.split(D, dim=-1)
+    q = q.reshape(G, S, nhead, d).transpose(1, 2)
+    k = k.reshape(G, S, nhead, d).transpose(1, 2)
+    s_ = (q @ k.transpose(-1, -2)) / math.sqrt(d)
+    s_ = s_.masked_fill(mask[:, None, None, :], float("-inf"))
+    return torch.softmax(s_, -1)
+
+
+def clip_gradients(grads: Sequence[Tensor], clip: float) -> List[Tensor]:
+    """DINO.dino_clip_gradients (dino.py:249-261): per-parameter clip_coef = clip / (||g||_2 + 1e-6), applied when < 1."""
+    out = []
+    for g in grads:
+        if g is None:
+            out.append(None)
+            continue
+        coef = clip / (g.norm(2) + 1e-6)
+        out.append(g * coef if coef < 1 else g.clone())
+    return out
+
+
+def lars_step(params: Sequence[Tensor], grads: Sequence[Tensor], bufs: List, *, lr: float, weight_decays: Sequence[float],
+              momentum: float = 0.0, dampening: float = 0.0, nesterov: bool = False, eta: float = 1e-3, eps: float = 1e-8,
+              clip_lr: bool = False, exclude_bias_n_norm: bool = False) -> Tuple[List[Tensor], List]:
+    """LARS.step (src/utils/lars.py:113-167) for a flat list of parameters; ``weight_decays[i]`` is the weight decay of the
+    group parameter i sits in (base.py:426-427 puts ndim <= 1 parameters into a weight_decay = 0 group when
+    exclude_bias_n_norm_wd).  ``grads[i] is None`` skips the parameter (:128-129).  Returns (new params, new buffers)."""
+    new_p, new_b = [], []
+    for p, g, buf, wd in zip(params, grads, bufs, weight_decays):
+        if g is None:
+            new_p.append(p.clone())
+            new_b.append(buf)
+            continue
+        d_p = g
+        p_norm, g_norm = torch.norm(p), torch.norm(g)
+        if p.ndim != 1 or not exclude_bias_n_norm:                       # :136
+            if p_norm != 0 and g_norm != 0:
+                lars_lr = p_norm / (g_norm + p_norm * wd + eps)          # :138
+                lars_lr = lars_lr * eta
+                if clip_lr:
+                    lars_lr = min(lars_lr / lr, 1)                       # :143
+                d_p = d_p.add(p, alpha=wd)
+                d_p = d_p * lars_lr
+        if momentum != 0:                                                # :149-159
+            buf = d_p.clone() if buf is None else buf * momentum + (1 - dampening) * d_p
+            d_p = d_p.add(buf, alpha=momentum) if nesterov else buf
+        new_p.append(p - lr * d_p)
+        new_b.append(buf)
+    return new_p, new_b
+
+
+def one_channel_collate(batch):
+    """one_channel_collate_fn (channels_strategies.py:31-85): (crop_lists, labels, num_channels_lists)."""
+    first = batch[0][-2:][0]
+    num_crops = len(first) if isinstance(first, list) else 1
+    crop_lists = [[] for _ in range(num_crops)]
+    counts = [[] for _ in range(num_crops)]
+    labels = []
+    for item in batch:
+        image_list, label = item[-2:]
+        if isinstance(image_list, torch.Tensor):
+            image_list = [image_list]
+        for i, crop in enumerate(image_list):
+            counts[i].append(crop.shape[0])
+            for c in range(crop.shape[0]):
+                crop_lists[i].append(crop[c, :, :].unsqueeze(0))
+        labels.append(label)
+    crop_lists = [torch.cat(c, 0).unsqueeze(1) for c in crop_lists]
+    return (crop_lists[0] if len(crop_lists) == 1 else crop_lists), torch.tensor(labels), counts

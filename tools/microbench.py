@@ -35,10 +35,31 @@ def report(name, us, flops=0.0, bytes_=0.0):
     print(f"{name:46s} {us:9.1f} us  {flops / us / 1e6:8.1f} TFLOP/s  {bytes_ / us / 1e3:8.1f} GB/s")
 
 
+def optim_section(dev):
+    """LARS path of the fused step at the size of backbone + head (17.5 M parameters): norms (8 B/param) + step (40 B/param)."""
+    n = 17_510_464
+    p, gr, buf, t = (torch.randn(n, device=dev) for _ in range(4))
+    p16, t16 = torch.empty(n, device=dev, dtype=bf16), torch.empty(n, device=dev, dtype=bf16)
+    nseg = 160
+    start = torch.linspace(0, n // 64, nseg + 1).to(torch.int32).to(dev)
+    seg_of = torch.repeat_interleave(torch.arange(nseg, dtype=torch.int32), (start[1:] - start[:-1]).long().cpu()).to(dev)
+    flags = torch.full((n,), 5, dtype=torch.uint8, device=dev)
+    partial, norms = torch.empty(n // 32, device=dev), torch.empty(3 * nseg, device=dev)
+    clipf = torch.ones(nseg, dtype=torch.uint8, device=dev)
+    report("param_norms 17.5M params (8 B/param), 160 segs", timeit(lambda: ops.param_norms(p, gr, start, clipf, partial, norms, clip=3.0)), 0, n * 8.0)
+    report("lars+ema+bf16 shadows 17.5M params (40 B/param)",
+           timeit(lambda: ops.lars_step(p, gr, buf, flags, seg_of, norms, lr=1e-3, momentum=0.9, weight_decay=1e-6, eta=0.02, clip_lr=True,
+                                        p_bf16=p16, teacher=t, teacher_bf16=t16, tau=0.99)), 0, n * 40.0)
+    report("scale_grads 17.5M params (8 B/param)", timeit(lambda: ops.scale_grads(gr, seg_of, norms)), 0, n * 8.0)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--tokens", type=int, default=68664)
+    ap.add_argument("--only", default="", help="comma list of sections: optim")
     a = ap.parse_args()
+    if a.only == "optim":
+        return optim_section("cuda")
     T, D, F = a.tokens, 192, 2048
     dev = "cuda"
     r = lambda *s: (torch.randn(*s, device=dev) * 0.5).to(bf16)  # noqa: E731
