@@ -423,3 +423,23 @@ def attn_probs(qkv: torch.Tensor, lay: "PackedLayout", num_heads: int) -> torch.
     out = torch.empty(nseq, num_heads, s_max, s_max, device=qkv.device, dtype=torch.float32)
     _call("cb_attn_probs", _p(qkv), _p(lay.cu), nseq, num_heads, d, s_max, 1.0 / math.sqrt(d), _p(out), _stream())
     return out
+
+
+def split_bf16x3(x: torch.Tensor, role_b: bool, normalize: bool, want_sqnorm: bool = False, pad_rows_to: int = 1):
+    """fp32 [R, D] -> bf16 [R', 3D] operand ([hi|hi|lo] or, for the B side, [hi|lo|hi]) for an fp32-accurate tensor-core product;
+    R' = R rounded up to ``pad_rows_to`` (extra rows zero).  Optionally L2-normalises rows first and returns ||row||^2."""
+    assert x.dtype == torch.float32 and x.dim() == 2 and x.is_contiguous()
+    R, D = x.shape
+    Rp = (R + pad_rows_to - 1) // pad_rows_to * pad_rows_to
+    out = torch.empty(Rp, 3 * D, device=x.device, dtype=bf16)
+    if Rp > R:
+        out[R:].zero_()
+    sq = torch.zeros(Rp, device=x.device, dtype=torch.float32) if want_sqnorm else None
+    _call("cb_split_bf16x3", _p(x), _p(out), _p(sq), R, D, int(role_b), int(normalize), _stream())
+    return out, sq
+
+
+def inv_euclid_(dots: torch.Tensor, sq_a: torch.Tensor, sq_b: torch.Tensor, n_cols: int, eps: float) -> torch.Tensor:
+    """dots[i, j] <- 1 / (sqrt(max(|a_i|^2 + |b_j|^2 - 2 dots[i, j], 0)) + eps) for the first n_cols columns, in place."""
+    _call("cb_inv_euclid", _p(dots), _p(sq_a), _p(sq_b), dots.shape[0], n_cols, dots.stride(0), float(eps), _stream())
+    return dots

@@ -180,6 +180,14 @@ int cb_adamw_step(float* p, const float* g, float* m, float* v, const unsigned c
 int cb_attn_probs(const void* qkv, const int* cu_seqlens, int nseq, int num_heads, int head_dim, int max_seqlen, float scale,
                   float* out, void* stream);
 
+/* Weighted k-NN evaluation (src/utils/knn.py:96-177): operand preparation for an fp32-accurate similarity matrix on the bf16
+ * tensor cores.  Row r of x (fp32 [rows, D]) is optionally L2-normalised (F.normalize, knn.py:114-116) and written as bf16
+ * [hi | hi | lo] (role_b = 0) or [hi | lo | hi] (role_b = 1) of length 3*D, so that ONE cb_gemm_bf16 over K = 3*D yields
+ * a.b up to a 2^-16 relative term.  sqnorm (optional) receives ||row||^2.  cb_inv_euclid turns such dot products in place into
+ * 1 / (cdist + eps) (knn.py:141). */
+int cb_split_bf16x3(const float* x, void* out, float* sqnorm, int rows, int D, int role_b, int normalize, void* stream);
+int cb_inv_euclid(float* dots, const float* sqnorm_a, const float* sqnorm_b, int M, int N, int ld, float eps, void* stream);
+
 /* Per-parameter L2 norms over a flat arena whose parameters start at 64-element aligned offsets.
  * seg_start_block[nseg+1]: first 64-element block of every parameter (int32, ascending; padding belongs to the parameter
  * in front of it and holds zeros).  partial: workspace of (n/64)*2 floats.  Output norms[3*s + {0,1,2}] =

@@ -17,6 +17,9 @@ path uses), every function of SURVEY.md §8(a):
   clip_gradients        src/methods/dino.py:249-261
   lars_step             src/utils/lars.py:113-167
   one_channel_collate   src/data/channels_strategies.py:31-85
+  knn_compute           src/utils/knn.py:96-177
+  extract_features      src/methods/base.py:941-981 (multi_channels strategy)
+  rewrite_checkpoint_keys   main_linear.py:103-110
 
 Parameters are dicts keyed by the reference's state-dict names.  All functions are
 differentiable through torch autograd, which is how the tests obtain reference gradients.
@@ -372,3 +375,65 @@ def one_channel_collate(batch):
         labels.append(label)
     crop_lists = [torch.cat(c, 0).unsqueeze(1) for c in crop_lists]
     return (crop_lists[0] if len(crop_lists) == 1 else crop_lists), torch.tensor(labels), counts
+
+
+def knn_compute(train_features: Tensor, train_targets: Tensor, test_features: Tensor, test_targets: Tensor, *, k: int = 20,
+                T: float = 0.07, max_distance_matrix_size: int = int(5e6), distance_fx: str = "cosine",
+                epsilon: float = 0.00001) -> Tuple[float, float, Tensor]:
+    """WeightedKNNClassifier.compute (knn.py:96-177) -> (top1 %, top5 %, predicted class per test sample)."""
+    if distance_fx == "cosine":
+        train_features = F.normalize(train_features)
+        test_features = F.normalize(test_features)
+    num_classes = torch.unique(test_targets).numel()
+    n_train, n_test = train_targets.size(0), test_targets.size(0)
+    chunk = min(max(1, max_distance_matrix_size // n_train), n_test)
+    k = min(k, n_train)
+    top1 = top5 = total = 0.0
+    preds = []
+    for idx in range(0, n_test, chunk):
+        feats = test_features[idx:min(idx + chunk, n_test)]
+        targets = test_targets[idx:min(idx + chunk, n_test)]
+        b = targets.size(0)
+        if distance_fx == "cosine":
+            sim = feats @ train_features.t()
+        elif distance_fx == "euclidean":
+            sim = 1 / (torch.cdist(feats, train_features) + epsilon)
+        else:
+            raise NotImplementedError
+        sim, ind = sim.topk(k, largest=True, sorted=True)
+        neigh = torch.gather(train_targets.view(1, -1).expand(b, -1), 1, ind)
+        one_hot = torch.zeros(b * k, num_classes)
+        one_hot.scatter_(1, neigh.view(-1, 1).long(), 1)
+        if distance_fx == "cosine":
+            sim = (sim / T).exp()
+        probs = (one_hot.view(b, -1, num_classes) * sim.view(b, -1, 1)).sum(1)
+        _, pred = probs.sort(1, True)
+        correct = pred.eq(targets.view(-1, 1))
+        top1 += correct[:, :1].sum().item()
+        top5 += correct[:, :min(5, k, correct.size(-1))].sum().item()
+        total += b
+        preds.append(pred[:, 0])
+    return top1 * 100.0 / total, top5 * 100.0 / total, torch.cat(preds)
+
+
+def extract_features(feats: Tensor, counts: Sequence[int], *, return_all_tokens: bool, mixed_channels: bool = False) -> Tensor:
+    """Tail of BaseMethod._base_extract_step for the multi_channels strategy (base.py:958-981): with return_all_tokens the
+    (ΣC·N, D) token matrix becomes one row per image (needs equal channel counts: torch.stack); CLS features pass through."""
+    if mixed_channels or not return_all_tokens:
+        return feats
+    chunks = feats.view(sum(counts), -1, feats.shape[-1])
+    chunks = torch.split(chunks, list(counts), dim=0)
+    return torch.stack(chunks, dim=0).flatten(start_dim=1)
+
+
+def rewrite_checkpoint_keys(state: Dict[str, Tensor]) -> Dict[str, Tensor]:
+    """Key rewriting of main_linear.py:103-110 applied to a Lightning ``state_dict``: 'encoder' -> 'backbone', then the
+    'backbone.' prefix is stripped; every original key is deleted (so only backbone entries survive)."""
+    state = dict(state)
+    for k in list(state.keys()):
+        if "encoder" in k:
+            state[k.replace("encoder", "backbone")] = state[k]
+        if "backbone" in k:
+            state[k.replace("backbone.", "")] = state[k]
+        del state[k]
+    return state

@@ -88,3 +88,46 @@ def test_collate_rejects_mixed_sizes():
         one_channel_collate_fn(bad)
     with pytest.raises(RuntimeError):
         O.one_channel_collate(bad)
+
+
+@pytest.mark.parametrize("name", list(MG.KNN_CASES))
+def test_oracle_knn(name):
+    xtr, ytr, xte, yte = MG.knn_data()
+    t1, t5, _ = O.knn_compute(xtr, ytr, xte, yte, **MG.KNN_CASES[name])
+    assert [t1, t5] == pytest.approx(G[f"knn.{name}"].tolist(), abs=1e-9)
+
+
+def test_checkpoint_key_rewriting_and_load():
+    """A Lightning-style DINO state_dict (backbone.*, momentum_backbone.*, head.* ...) loads into the backbone the way
+    main_linear.py:103-110 does it: same surviving keys as the restated rule, nothing missing, values bit-equal."""
+    from chadavit_b200.backbones import chada_vit
+    from chadavit_b200.utils.checkpoint import load_pretrained_backbone, rewrite_backbone_keys
+    P = {k: torch.from_numpy(v) for k, v in det.det_state_dict(O.backbone_shapes(32), 3).items()}
+    H = {k: torch.from_numpy(v) for k, v in det.det_state_dict(O.head_shapes(32, 64), 4).items()}
+    state = {f"backbone.{k}": v for k, v in P.items()}
+    state.update({f"head.{k}": v for k, v in H.items()})
+    state.update({f"momentum_head.{k}": v + 1 for k, v in H.items()})
+    state["dino_loss_func.center"] = torch.zeros(1, 64)
+    want = O.rewrite_checkpoint_keys(state)
+    got = rewrite_backbone_keys(state)
+    assert list(got.keys()) == list(want.keys()) and set(P.keys()) <= set(got.keys())
+    m = chada_vit(patch_size=16, embed_dim=32, return_all_tokens=False, max_number_channels=10)
+    res = load_pretrained_backbone(m, {"state_dict": state})
+    assert not res.missing_keys and not res.unexpected_keys
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, P[k]), k
+    enc = {k.replace("backbone.", "encoder."): v for k, v in state.items() if k.startswith("backbone.")}
+    # quirk kept on purpose: 'encoder.*' keys are renamed to 'backbone.*' AFTER the key snapshot was taken, so the prefix is never
+    # stripped from them and strict=False then loads nothing (main_linear.py:103-110 behaves exactly like this)
+    assert list(rewrite_backbone_keys(enc).keys()) == list(O.rewrite_checkpoint_keys(enc).keys()) == list(state.keys())[:len(enc)]
+    res = load_pretrained_backbone(chada_vit(patch_size=16, embed_dim=32, return_all_tokens=False, max_number_channels=10), enc)
+    assert len(res.missing_keys) == len(P) and len(res.unexpected_keys) == len(P)
+
+
+def test_oracle_extract_features_shapes():
+    toks = torch.arange(6 * 4 * 2, dtype=torch.float32).view(6 * 4, 2)        # ΣC = 6 channel images, N = 4, D = 2
+    out = O.extract_features(toks, [3, 3], return_all_tokens=True)
+    assert out.shape == (2, 3 * 4 * 2) and torch.equal(out[1], toks[12:].reshape(-1))
+    assert O.extract_features(toks, [2, 4], return_all_tokens=True, mixed_channels=True) is toks
+    with pytest.raises(RuntimeError):
+        O.extract_features(toks, [2, 4], return_all_tokens=True)              # torch.stack of unequal chunks (base.py:975)
