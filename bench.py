@@ -284,17 +284,25 @@ def main():
         roof[name] = {"launches_per_step": p["launches"] / args.steps, "ms_per_step": p["ms_total"] / args.steps,
                       "share_of_step": p["ms_total"] / ms_eager, "achieved_tflops": ach, "frac": ach / tf_peak,
                       "achieved_gbs": gbs, "frac_hbm": gbs / hbm_peak}
-    # The dominant SINGLE kernel of the step is the attention backward (profiles/r01_launches_bench_step.txt: 13.4 % of the
-    # kernel time; the GEMM class is larger in total but is 14 instantiations over a dozen shapes, most of them HBM-bound:
-    # see "all" for its aggregate TFLOP/s and GB/s).  `traffic` = dram read + write bytes of one launch from the committed
-    # `ncu --set full` capture of the same kernel on the same ragged batch (profiles/r01_ncu_attn_bwd.txt).
-    top = "cb_attn_varlen_bwd"
+    # The dominant SINGLE kernel of the step (profiles/r01_launches_bench_step.txt: ffn_fwd_kernel 25 % of the kernel time, then
+    # attention forward 14 % and backward 12 %; the GEMM class is larger in total but is 14 instantiations over a dozen shapes,
+    # most of them HBM-bound: see "all" for its aggregate TFLOP/s and GB/s) is picked live among the single-kernel classes.
+    # `traffic` = dram read + write bytes of ONE launch from the committed `ncu --set full` capture of that kernel on the
+    # ragged global-crop batch of 64 images (T = 68 664 tokens; the bench launches it on 2x that for the packed global crops).
+    NCU = {"cb_ffn_fwd": ("ffn_fwd_kernel (cb_ffn_fwd)", 366.2e6, "profiles/r01_ncu_ffn_fwd.txt",
+                          "capture: T = 68664, hidden activations stored; algorithmic bytes of that launch 414.7e6 (the tail of the "
+                          "hidden store is still in L2 when the kernel ends)"),
+           "cb_attn_varlen_bwd": ("attn_bwd_kernel<96> (cb_attn_varlen_bwd)", 223.1e6, "profiles/r01_ncu_attn_bwd.txt",
+                                  "capture: T = 68664, H = 2, d = 96; algorithmic bytes of that launch 237.3e6"),
+           "cb_attn_varlen_fwd": ("attn_fwd2_kernel<96> (cb_attn_varlen_fwd)", 87.5e6, "profiles/r01_ncu_attn_fwd.txt",
+                                  "capture: T = 68664, H = 2, d = 96")}
+    top = max(NCU, key=lambda k: prof[k]["ms_total"])
     tp = prof[top]
-    roofline = {"kernel": "attn_bwd_kernel<96> (cb_attn_varlen_bwd)", "bound": "tensor", "achieved": roof[top]["achieved_tflops"], "peak": tf_peak,
-                "unit": "TFLOP/s", "frac": roof[top]["frac"], "traffic": 223.1e6, "traffic_source": "profiles/r01_ncu_attn_bwd.txt",
+    roofline = {"kernel": NCU[top][0], "bound": "tensor", "achieved": roof[top]["achieved_tflops"], "peak": tf_peak,
+                "unit": "TFLOP/s", "frac": roof[top]["frac"], "traffic": NCU[top][1], "traffic_source": NCU[top][2], "traffic_note": NCU[top][3],
                 "peak_source": peak_src, "algorithmic_flops_per_launch": tp["work"] / max(1, tp["launches"]),
                 "algorithmic_bytes_per_launch": tp["bytes"] / max(1, tp["launches"]),
-                "avg_launch_ms": tp["ms_total"] / max(1, tp["launches"]), "all": roof,
+                "avg_launch_ms": tp["ms_total"] / max(1, tp["launches"]), "share_of_step": roof[top]["share_of_step"], "all": roof,
                 "hbm_note": "a one-directional HBM stream tops out near 3.9 TB/s (write) / 4.3 TB/s (read) on this part; only mixed "
                             "traffic reaches the 6.55 TB/s copy figure (tools/membw.py, profiles/r01_hw_probes.txt)",
                 "timing": "CUDA events around every launch of the class in an instrumented eager pass of the same step "

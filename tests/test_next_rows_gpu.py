@@ -32,7 +32,7 @@ def test_get_last_selfattention_vs_reference(name):
     got = A[:, :, MG.ATTN_ROWS, :].cpu()
     err, rel = (got - ref).abs().max().item(), rel_err(got, ref)
     print(f"attention map {name}: max abs err {err:.2e} (max prob {ref.max().item():.3f}), rel L2 {rel:.2e}")
-    assert err < 5e-3 and rel < 4e-2                       # bf16 q/k: ~1e-2 relative on the probabilities
+    assert err < 2.5e-2 * ref.max().item() and rel < 4e-2  # bf16 q/k/u operands: ~1e-2 relative on the probabilities
     assert (A.sum(-1) - 1).abs().max().item() < 1e-4
     # what main_attn.py:202-207 reads
     cls_map = A[0, :, 0, 1:].reshape(A.shape[1], -1)

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Launch ONE kernel class a few times so that `ncu --set full` can capture it in isolation.
-    python tools/prof_one.py fc1|qkv|dh|fc2|attn_fwd|attn_bwd|ln_fwd|ln_bwd"""
+    python tools/prof_one.py fc1|qkv|dh|fc2|attn_fwd|attn_bwd|ffn|ffn_save"""
 import os
 import sys
 
@@ -27,6 +27,8 @@ fns = {
     "dh": lambda: ops.gemm(x16, w2, b_mn=True, aux=hid, flags=ops.EPI_RELU_MASK),
     "fc2": lambda: ops.gemm(hid, w2, bias=b2, aux=x32, flags=R),
     "attn_fwd": lambda: ops.attn_fwd(qkv, lay, 2),
+    "ffn": lambda: ops.ffn_fwd(x16, w1, b1, w2, b2, x32, save_hidden=False),
+    "ffn_save": lambda: ops.ffn_fwd(x16, w1, b1, w2, b2, x32, save_hidden=True),
 }
 if which == "attn_bwd":
     out, lse = ops.attn_fwd(qkv, lay, 2)
