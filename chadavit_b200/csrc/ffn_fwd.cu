@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "chadavit_b200.h"
 #include "internal.h"
+#include <stdlib.h>
 
 namespace cb {
 
@@ -290,6 +291,9 @@ extern "C" int cb_ffn_fwd(const void* y, const void* w1, const float* b1, const 
   CB_CHECK(T > 0 && D == FF_D && F % FF_C == 0 && F >= FF_C && F <= FF_MAX_F, "ffn_fwd: T=%d D=%d F=%d (this kernel handles D = %d, F a multiple of %d up to %d)", T, D, F, FF_D, FF_C, FF_MAX_F);
   CB_CHECK(((reinterpret_cast<uintptr_t>(resid) | reinterpret_cast<uintptr_t>(z2) | reinterpret_cast<uintptr_t>(hid) | reinterpret_cast<uintptr_t>(b1) |
              reinterpret_cast<uintptr_t>(b2)) & 31) == 0, "ffn_fwd: resid / z2 / hid / biases must be 32-byte aligned");
+  static int use_v2 = -1;
+  if (use_v2 < 0) { const char* e = getenv("CB_FFN_V2"); use_v2 = (e && e[0] == '1') ? 1 : 0; }
+  if (use_v2) return ffn_fwd2_run(y, w1, b1, w2, b2, resid, z2, hid, T, F, reinterpret_cast<cudaStream_t>(stream));
   static bool attr_set = false;
   if (!attr_set) {
     CB_CUDA(cudaFuncSetAttribute(ffn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM_BYTES));

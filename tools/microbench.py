@@ -53,6 +53,18 @@ def optim_section(dev):
     report("scale_grads 17.5M params (8 B/param)", timeit(lambda: ops.scale_grads(gr, seg_of, norms)), 0, n * 8.0)
 
 
+def ffn_section(dev, T):
+    D, F = 192, 2048
+    r = lambda *s: (torch.randn(*s, device=dev) * 0.5).to(bf16)  # noqa: E731
+    x16, w1, w2 = r(T, D), r(F, D), r(D, F)
+    x32 = torch.randn(T, D, device=dev)
+    b1, b2 = torch.randn(F, device=dev), torch.randn(D, device=dev)
+    for TT in (T, 2 * T):
+        xa, xr = (x16, x32) if TT == T else (torch.cat([x16, x16]), torch.cat([x32, x32]))
+        report(f"ffn fused T={TT} (no hidden store)", timeit(lambda: ops.ffn_fwd(xa, w1, b1, w2, b2, xr, save_hidden=False)), 4.0 * TT * D * F, TT * (D * 2 + D * 8))
+        report(f"ffn fused T={TT} (+ hidden store)", timeit(lambda: ops.ffn_fwd(xa, w1, b1, w2, b2, xr, save_hidden=True)), 4.0 * TT * D * F, TT * (D * 2 + D * 8 + F * 2))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--tokens", type=int, default=68664)
@@ -60,6 +72,8 @@ def main():
     a = ap.parse_args()
     if a.only == "optim":
         return optim_section("cuda")
+    if a.only == "ffn":
+        return ffn_section("cuda", a.tokens)
     T, D, F = a.tokens, 192, 2048
     dev = "cuda"
     r = lambda *s: (torch.randn(*s, device=dev) * 0.5).to(bf16)  # noqa: E731
