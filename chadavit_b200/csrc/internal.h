@@ -35,4 +35,8 @@ int gemm_run(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn,
 int ffn_fwd2_run(const void* y, const void* w1, const float* b1, const void* w2, const float* b2, const float* resid, float* z2, void* hid,
                  int T, int F, cudaStream_t stream);
 
+// third generation (ffn_fwd3.cu): 128-unit hidden chunks, y tile in shared memory; needs F % 128 == 0
+int ffn_fwd3_run(const void* y, const void* w1, const float* b1, const void* w2, const float* b2, const float* resid, float* z2, void* hid,
+                 int T, int F, cudaStream_t stream);
+
 }  // namespace cb

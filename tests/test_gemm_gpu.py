@@ -94,9 +94,15 @@ def test_gemm_weight_grad_splitk():
 
 @pytest.mark.parametrize("T,F", [(1000, 2048), (128, 64), (129, 128), (257, 2048), (40000, 2048), (128 * 148 * 2 + 5, 512)])
 @pytest.mark.parametrize("save_hidden", [True, False])
-def test_ffn_fused(T, F, save_hidden):
-    """cb_ffn_fwd == linear1 -> ReLU -> (bf16 rounding of the hidden activations) -> linear2 + residual (chada_vit.py:113-116, :100)."""
+@pytest.mark.parametrize("gen", ["", "1", "2", "3"])
+def test_ffn_fused(T, F, save_hidden, gen, monkeypatch):
+    """cb_ffn_fwd == linear1 -> ReLU -> (bf16 rounding of the hidden activations) -> linear2 + residual (chada_vit.py:113-116, :100).
+    gen: the kernel generation forced through CB_FFN_V ("" = the library's own choice: 3 without / 1 with the hidden store)."""
     from chadavit_b200 import ops
+    if gen:
+        monkeypatch.setenv("CB_FFN_V", gen)
+    else:
+        monkeypatch.delenv("CB_FFN_V", raising=False)
     D = 192
     g = torch.Generator(device="cpu").manual_seed(T + F)
     r = lambda *s: torch.randn(*s, generator=g)  # noqa: E731

@@ -41,7 +41,7 @@ def run():
         ops.attn_fwd(qkv, lay, 2)
     elif which == "bwd":
         ops.attn_bwd(do, qkv, out, lse, lay, 2)
-    elif which in ("ffn", "ffn2"):
+    elif which in ("ffn", "ffn2", "ffn3"):
         ops.ffn_fwd(x16, w1, b1, w2f, b2f, x32f, save_hidden=False)
     else:   # gemm: fc1
         ops.gemm(x16, w1, bias=b1, flags=ops.EPI_RELU, out=hid_out)
