@@ -124,3 +124,41 @@ def test_weighted_knn_matches_reference(name):
     err = (sim - ref).abs().max().item()
     print(f"split-bf16 similarity: max abs err {err:.2e}")
     assert err < 5e-5
+
+
+def test_moyen_lars_clip_graph_steps():
+    """configs[2] shape (moyen/16, 2 global + 6 local crops) at a small batch with the pre-training yaml's optimizer (LARS,
+    clip_lr, exclude_bias_n_norm) + clip_grad, through CUDA-graph replay: finite, parameters and teacher move, the frozen
+    prototypes do not (epoch 0 < freeze_last_layer), weight_g stays 1."""
+    from chadavit_b200.methods import DINO
+    cfg = {"method": "dino", "backbone": {"kwargs": {"patch_size": 16, "embed_dim": 192, "return_all_tokens": False}},
+           "data": {"max_img_channels": 10, "num_large_crops": 2, "num_small_crops": 6},
+           "method_kwargs": {"num_prototypes": 4096, "clip_grad": 3.0, "freeze_last_layer": 1},
+           "max_epochs": 100, "max_steps": 1000, "momentum": {"base_tau": 0.99, "final_tau": 1.0},
+           "optimizer": {"name": "lars", "lr": 0.3, "weight_decay": 1e-6, "exclude_bias_n_norm_wd": True,
+                         "kwargs": {"clip_lr": True, "eta": 0.02, "exclude_bias_n_norm": True, "momentum": 0.9}},
+           "engine": {"cuda_graph": True}}
+    torch.manual_seed(0)
+    m = DINO(cfg).cuda()
+    counts = [3, 1, 10, 5, 2, 7]
+    g = torch.Generator(device="cuda").manual_seed(3)
+    crops = [torch.randn(sum(counts), 1, 224, 224, device="cuda", generator=g) for _ in range(2)] + \
+            [torch.randn(sum(counts), 1, 96, 96, device="cuda", generator=g) for _ in range(6)]
+    batch = (crops, None, [counts] * 8)
+    p0 = m.backbone.arena.fp32.clone() if m.backbone._arena is not None else None
+    w0 = {k: v.detach().clone() for k, v in m.backbone.state_dict().items()}
+    t0 = {k: v.detach().clone() for k, v in m.momentum_backbone.state_dict().items()}
+    v0 = m.head.last_layer.weight_v.detach().clone()
+    losses = [m.fused_train_step(batch).item() for _ in range(5)]        # eager, capture, 3 replays
+    torch.cuda.synchronize()
+    assert all(np.isfinite(l) for l in losses), losses
+    assert m.use_cuda_graph, "graph capture fell back to eager"
+    moved = sum(int(not torch.equal(v, w0[k])) for k, v in m.backbone.state_dict().items())
+    assert moved == len(w0), (moved, len(w0))
+    assert all(torch.isfinite(v).all() for v in m.backbone.state_dict().values())
+    assert any(not torch.equal(v, t0[k]) for k, v in m.momentum_backbone.state_dict().items())
+    assert torch.equal(m.head.last_layer.weight_v.detach(), v0)           # frozen in epoch 0
+    assert torch.equal(m.head.last_layer.weight_g.detach(), torch.ones_like(m.head.last_layer.weight_g))
+    # clip_lr bounds every LARS update: |dp| <= lr * |momentum-averaged (g + wd p)| with lars_lr <= 1
+    step = max((v - w0[k]).abs().max().item() for k, v in m.backbone.state_dict().items())
+    assert step < 10.0, step
