@@ -270,9 +270,10 @@ class ChAdaViT(nn.Module):
         z1 = ops.gemm(att, a.v16(pre + "self_attn.out_proj.weight"), bias=a.v32(pre + "self_attn.out_proj.bias"), aux=x, flags=R)
         y, y32, m1b, r1b = ops.layernorm_fwd(z1, g1, b1, eps, out_f32=True, save_stats=save)
         if ops.ffn_fused_ok(x.shape[1], FFN_DIM):   # linear1 -> ReLU -> linear2 -> +residual in one kernel; hidden stored only if saved
-            z2, hid = ops.ffn_fwd(y, a.v16(pre + "linear1.weight"), a.v32(pre + "linear1.bias"), a.v16(pre + "linear2.weight"),
-                                  a.v32(pre + "linear2.bias"), y32, save_hidden=save)
+            z2, hid, bits = ops.ffn_fwd(y, a.v16(pre + "linear1.weight"), a.v32(pre + "linear1.bias"), a.v16(pre + "linear2.weight"),
+                                        a.v32(pre + "linear2.bias"), y32, save_hidden=save, save_mask_bits=save)
         else:
+            bits = None
             hid = ops.gemm(y, a.v16(pre + "linear1.weight"), bias=a.v32(pre + "linear1.bias"), flags=ops.EPI_RELU)
             z2 = ops.gemm(hid, a.v16(pre + "linear2.weight"), bias=a.v32(pre + "linear2.bias"), aux=y32, flags=R)
         nxt = None
@@ -287,7 +288,7 @@ class ChAdaViT(nn.Module):
                                                out_bf16=False, out_f32=True, save_stats=save)
         if not save:
             return out, None, nxt
-        return out, (x, u, m1a, r1a, qkv, att, lse, z1, m1b, r1b, y, hid, z2, m2, r2), nxt
+        return out, (x, u, m1a, r1a, qkv, att, lse, z1, m1b, r1b, y, hid, z2, m2, r2, bits), nxt
 
     # ------------------------------------------------------------------ backward on the packed layout
     def _backward_impl(self, s: _Saved, dout: torch.Tensor, gflat: torch.Tensor) -> None:
@@ -316,7 +317,7 @@ class ChAdaViT(nn.Module):
         """dxo fp32 [T,D] -> (dx fp32, dx bf16 if last).  Gradient residual stream fp32; bf16 only for MMA operands."""
         a, pre = self.arena, f"blocks.{i}."
         g = lambda n: a.g32(pre + n, gflat)  # noqa: E731
-        x, u, m1a, r1a, qkv, att, lse, z1, m1b, r1b, y, hid, z2, m2, r2 = sv
+        x, u, m1a, r1a, qkv, att, lse, z1, m1b, r1b, y, hid, z2, m2, r2, bits = sv
         T, D = x.shape
         A = ops.EPI_ATOMIC
         sk = lambda tiles: ops.splitk_for(T, tiles)  # noqa: E731
@@ -325,7 +326,9 @@ class ChAdaViT(nn.Module):
         dz2, dz2h = ops.layernorm_bwd(dxo, z2, a.v32(pre + "norm2.weight"), m2, r2, dgamma=g("norm2.weight"), dbeta=g("norm2.bias"),
                                       dcolsum=g("linear2.bias"), want_bf16=True)
         ops.gemm(dz2h, hid, a_mn=True, b_mn=True, flags=A, out=g("linear2.weight"), k_splits=sk(mt(D) * (FFN_DIM // 256)))
-        dh = ops.gemm(dz2h, a.v16(pre + "linear2.weight"), b_mn=True, aux=hid, flags=ops.EPI_RELU_MASK, colsum=g("linear1.bias"))
+        # d(hidden) = (dz2 W2) o (hidden > 0): the mask comes as 1 bit per unit from the fused forward (hid itself: 16x the bytes)
+        dh = ops.gemm(dz2h, a.v16(pre + "linear2.weight"), b_mn=True, aux=hid if bits is None else bits,
+                      flags=ops.EPI_RELU_MASK | (0 if bits is None else ops.EPI_MASK_BITS), colsum=g("linear1.bias"))
         ops.gemm(dh, y, a_mn=True, b_mn=True, flags=A, out=g("linear1.weight"), k_splits=sk(mt(FFN_DIM) * mt(D)))
         dy = ops.gemm(dh, a.v16(pre + "linear1.weight"), b_mn=True, aux=dz2, flags=ops.EPI_RESIDUAL_F32 | ops.EPI_OUT_F32)
         # y = LN1(z1), z1 = x + att Wo^T + bo      (second use of norm1: gradients accumulate)

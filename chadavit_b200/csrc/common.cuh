@@ -291,6 +291,16 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
   __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(v);
 }
+// ReLU mask of 32 hidden units as bits: bit 2i / 2i+1 <=> the low / high bf16 of pk[i] is > 0 (same test as the masked epilogue of
+// the backward product: a bf16 is > 0 iff its bit pattern read as a signed 16-bit integer is > 0)
+__device__ __forceinline__ uint32_t relu_bits16(const uint32_t* pk) {
+  uint32_t w = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+    w |= (((short)(pk[i] & 0xffffu) > 0) ? (1u << (2 * i)) : 0u) | (((int)pk[i] >= 0x10000) ? (2u << (2 * i)) : 0u);
+  return w;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

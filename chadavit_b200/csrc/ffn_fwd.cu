@@ -43,6 +43,8 @@ struct FfnArgs {
   const float* resid;  // [T, D] fp32 (norm1 output, the residual of chada_vit.py:100)
   float* z2;           // [T, D] fp32
   __nv_bfloat16* hid;  // [T, F] bf16 or null
+  uint32_t* mask_bits; // [F/32, ld_bits] ReLU mask as bits, or null
+  int ld_bits;
   int T, F;
 };
 
@@ -228,6 +230,7 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
             stg256(dst, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
             stg256(dst + 16, pk[8], pk[9], pk[10], pk[11], pk[12], pk[13], pk[14], pk[15]);
           }
+          if (a.mask_bits && row < a.T) a.mask_bits[(long)(2 * c + hf) * a.ld_bits + row] = relu_bits16(pk);   // a warp = 32 consecutive rows: one line
         }
       }
       // ---- final epilogue: z2 = Z + b2 + resid (fp32); this warp's half: 32-column slabs hf, hf + 2, hf + 4 (128 contiguous bytes each)
@@ -286,9 +289,11 @@ extern "C" int cb_debug_timeline_ffn(void* dst) {
 #endif
 
 extern "C" int cb_ffn_fwd(const void* y, const void* w1, const float* b1, const void* w2, const float* b2, const float* resid, float* z2,
-                          void* hid, int T, int D, int F, void* stream) {
+                          void* hid, unsigned int* mask_bits, int ld_bits, int T, int D, int F, void* stream) {
   using namespace cb;
   CB_CHECK(T > 0 && D == FF_D && F % FF_C == 0 && F >= FF_C && F <= FF_MAX_F, "ffn_fwd: T=%d D=%d F=%d (this kernel handles D = %d, F a multiple of %d up to %d)", T, D, F, FF_D, FF_C, FF_MAX_F);
+  CB_CHECK(!mask_bits || (ld_bits >= T && ld_bits % 32 == 0 && (reinterpret_cast<uintptr_t>(mask_bits) & 127) == 0),
+           "ffn_fwd: mask_bits needs ld_bits >= T (a multiple of 32) and a 128-byte aligned buffer");
   CB_CHECK(((reinterpret_cast<uintptr_t>(resid) | reinterpret_cast<uintptr_t>(z2) | reinterpret_cast<uintptr_t>(hid) | reinterpret_cast<uintptr_t>(b1) |
              reinterpret_cast<uintptr_t>(b2)) & 31) == 0, "ffn_fwd: resid / z2 / hid / biases must be 32-byte aligned");
   // Kernel generations (measured at T = 68664 / 137328, F = 2048: profiles/r01_microbench_kernels.txt):
@@ -300,8 +305,8 @@ extern "C" int cb_ffn_fwd(const void* y, const void* w1, const float* b1, const 
   const char* env = getenv("CB_FFN_V");
   const int ver = (env && env[0] >= '1' && env[0] <= '3') ? env[0] - '0' : 0;
   const int use = ver ? ver : (hid == nullptr ? 3 : 1);
-  if (use == 3 && F % 128 == 0) return ffn_fwd3_run(y, w1, b1, w2, b2, resid, z2, hid, T, F, reinterpret_cast<cudaStream_t>(stream));
-  if (use == 2 || (use == 3 && ver)) return ffn_fwd2_run(y, w1, b1, w2, b2, resid, z2, hid, T, F, reinterpret_cast<cudaStream_t>(stream));
+  if (use == 3 && F % 128 == 0) return ffn_fwd3_run(y, w1, b1, w2, b2, resid, z2, hid, mask_bits, ld_bits, T, F, reinterpret_cast<cudaStream_t>(stream));
+  if (use == 2 || (use == 3 && ver)) return ffn_fwd2_run(y, w1, b1, w2, b2, resid, z2, hid, mask_bits, ld_bits, T, F, reinterpret_cast<cudaStream_t>(stream));
   static bool attr_set = false;
   if (!attr_set) {
     CB_CUDA(cudaFuncSetAttribute(ffn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM_BYTES));
@@ -321,7 +326,7 @@ extern "C" int cb_ffn_fwd(const void* y, const void* w1, const float* b1, const 
     if (make_tmap(&t2, w2, 2, dims, strides, box, 3)) return 1;
   }
   FfnArgs a{};
-  a.b1 = b1; a.b2 = b2; a.resid = resid; a.z2 = z2; a.hid = reinterpret_cast<__nv_bfloat16*>(hid); a.T = T; a.F = F;
+  a.b1 = b1; a.b2 = b2; a.resid = resid; a.z2 = z2; a.hid = reinterpret_cast<__nv_bfloat16*>(hid); a.mask_bits = mask_bits; a.ld_bits = ld_bits; a.T = T; a.F = F;
   const int n_items = ((T + 127) / 128 + 1) / 2;
   const int grid = n_items < num_sms() ? n_items : num_sms();
   ffn_fwd_kernel<<<grid, 320, FF_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(ty, t1, t2, a);

@@ -39,6 +39,8 @@ struct Ffn2Args {
   const float* resid;      // [T, D] fp32
   float* z2;               // [T, D] fp32
   __nv_bfloat16* hid;      // [T, F] bf16 or null
+  uint32_t* mask_bits;     // [F/32, ld_bits] ReLU mask as bits, or null
+  int ld_bits;
   int T, F;
 };
 
@@ -231,6 +233,7 @@ ffn_fwd2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant_
           stg256(dst, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
           stg256(dst + 16, pk[8], pk[9], pk[10], pk[11], pk[12], pk[13], pk[14], pk[15]);
         }
+        if (a.mask_bits && row_ok) a.mask_bits[(long)(2 * c + hf) * a.ld_bits + row] = relu_bits16(pk);
       }
       g += n_chunks;
       // every H product of this item has completed (h_full of its last chunk was seen): the y columns may take the next tile,
@@ -288,7 +291,7 @@ extern "C" int cb_debug_timeline_ffn2(void* dst) {
 namespace cb {
 
 int ffn_fwd2_run(const void* y, const void* w1, const float* b1, const void* w2, const float* b2, const float* resid, float* z2, void* hid,
-                 int T, int F, cudaStream_t stream) {
+                 unsigned int* mask_bits, int ld_bits, int T, int F, cudaStream_t stream) {
   using namespace f2;
   static bool attr_set = false;
   if (!attr_set) {
@@ -306,7 +309,7 @@ int ffn_fwd2_run(const void* y, const void* w1, const float* b1, const void* w2,
   }
   Ffn2Args a{};
   a.y = reinterpret_cast<const __nv_bfloat16*>(y); a.b1 = b1; a.b2 = b2; a.resid = resid; a.z2 = z2;
-  a.hid = reinterpret_cast<__nv_bfloat16*>(hid); a.T = T; a.F = F;
+  a.hid = reinterpret_cast<__nv_bfloat16*>(hid); a.mask_bits = mask_bits; a.ld_bits = ld_bits; a.T = T; a.F = F;
   const int n_items = ((T + 127) / 128 + 1) / 2;
   const int max_clusters = num_sms() / 2;
   const int clusters = n_items < max_clusters ? n_items : max_clusters;

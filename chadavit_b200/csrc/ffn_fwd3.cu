@@ -39,6 +39,8 @@ struct Ffn3Args {
   const float* resid;      // [T, D] fp32
   float* z2;               // [T, D] fp32
   __nv_bfloat16* hid;      // [T, F] bf16 or null
+  uint32_t* mask_bits;     // [F/32, ld_bits] ReLU mask as bits, or null
+  int ld_bits;
   int T, F;
 };
 
@@ -231,6 +233,10 @@ ffn_fwd3_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
           for (int k = 0; k < 4; ++k)
             stg256(dst + 16 * k, pk[8 * k], pk[8 * k + 1], pk[8 * k + 2], pk[8 * k + 3], pk[8 * k + 4], pk[8 * k + 5], pk[8 * k + 6], pk[8 * k + 7]);
         }
+        if (a.mask_bits && row_ok) {
+          a.mask_bits[(long)(4 * c + 2 * hf) * a.ld_bits + row] = relu_bits16(pk);
+          a.mask_bits[(long)(4 * c + 2 * hf + 1) * a.ld_bits + row] = relu_bits16(pk + 16);
+        }
       }
       g += n_chunks;
       // ---- final epilogue: z2 = Z + b2 + resid (fp32); this warp's half: 32-column slabs hf, hf + 2, hf + 4
@@ -285,7 +291,7 @@ extern "C" int cb_debug_timeline_ffn3(void* dst) {
 namespace cb {
 
 int ffn_fwd3_run(const void* y, const void* w1, const float* b1, const void* w2, const float* b2, const float* resid, float* z2, void* hid,
-                 int T, int F, cudaStream_t stream) {
+                 unsigned int* mask_bits, int ld_bits, int T, int F, cudaStream_t stream) {
   using namespace f3;
   static bool attr_set = false;
   if (!attr_set) {
@@ -306,7 +312,7 @@ int ffn_fwd3_run(const void* y, const void* w1, const float* b1, const void* w2,
     if (make_tmap(&t2, w2, 2, dims, strides, box, 3)) return 1;
   }
   Ffn3Args a{};
-  a.b1 = b1; a.b2 = b2; a.resid = resid; a.z2 = z2; a.hid = reinterpret_cast<__nv_bfloat16*>(hid); a.T = T; a.F = F;
+  a.b1 = b1; a.b2 = b2; a.resid = resid; a.z2 = z2; a.hid = reinterpret_cast<__nv_bfloat16*>(hid); a.mask_bits = mask_bits; a.ld_bits = ld_bits; a.T = T; a.F = F;
   const int n_items = ((T + 127) / 128 + 1) / 2;
   const int max_clusters = num_sms() / 2;
   const int clusters = n_items < max_clusters ? n_items : max_clusters;

@@ -241,6 +241,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             for (int k = 0; k < 4; ++k)
               if (c + 8 * k + 8 <= n_lim) ldg256(rp + 8 * k, *reinterpret_cast<uint32_t(*)[8]>(&m[8 * k]));
           } else if (mode == EM_BF16_MASK) {
+            if (g.flags & CB_EPI_MASK_BITS) {   // one coalesced word per slab: bit j <=> hidden[row, n0 + c + j] > 0
+              m[0] = __ldg(reinterpret_cast<const uint32_t*>(g.aux) + (long)((n0 + c) >> 5) * g.ld_aux + row);
+              return;
+            }
             const __nv_bfloat16* mp = g.aux + row * g.ld_aux + n0 + c;
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
@@ -260,10 +264,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             // d(hidden) = (dz2 . W2) where hidden > 0.  bf16 > 0  <=>  its bit pattern, read as a signed 16-bit integer, is > 0.
             uint32_t pk[16];
             float f[32];
+            const bool bits = (g.flags & CB_EPI_MASK_BITS) != 0;
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
               const uint32_t mm = m[e];
-              const uint32_t sel = ((short)(mm & 0xffffu) > 0 ? 0xffffu : 0u) | ((int)mm >= 0x10000 ? 0xffff0000u : 0u);
+              const uint32_t b2 = m[0] >> (2 * e);
+              const uint32_t sel = bits ? (((b2 & 1u) ? 0xffffu : 0u) | ((b2 & 2u) ? 0xffff0000u : 0u))
+                                        : (((short)(mm & 0xffffu) > 0 ? 0xffffu : 0u) | ((int)mm >= 0x10000 ? 0xffff0000u : 0u));
               pk[e] = pack_bf16(__uint_as_float(x[2 * e]) * g.alpha, __uint_as_float(x[2 * e + 1]) * g.alpha) & sel;   // rows past M: mask = 0
               const float2 u = unpack_bf16(pk[e]);
               f[2 * e] = u.x; f[2 * e + 1] = u.y;
@@ -404,7 +411,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const long grow = (long)m0 + q * 32 + i * 8 + (lane >> 2);
-            mk[i] = (grow < g.M && gc8 < g.N) ? __ldg(reinterpret_cast<const uint4*>(g.aux + grow * g.ld_aux + gc8)) : make_uint4(0u, 0u, 0u, 0u);
+            if (g.flags & CB_EPI_MASK_BITS) {   // expand this lane's 8 mask bits into the bf16 pattern the read-back tests (1.0 / 0)
+              const uint32_t w = (grow < g.M && gc8 < g.N) ? __ldg(reinterpret_cast<const uint32_t*>(g.aux) + (long)(gc8 >> 5) * g.ld_aux + grow) >> (gc8 & 31) : 0u;
+              uint32_t* mw = &mk[i].x;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) mw[k] = ((w >> (2 * k)) & 1u ? 0x3f80u : 0u) | ((w >> (2 * k + 1)) & 1u ? 0x3f800000u : 0u);
+            } else {
+              mk[i] = (grow < g.M && gc8 < g.N) ? __ldg(reinterpret_cast<const uint4*>(g.aux + grow * g.ld_aux + gc8)) : make_uint4(0u, 0u, 0u, 0u);
+            }
           }
         }
         if (mode == EM_F32) {
@@ -668,7 +682,8 @@ int gemm_run(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn,
     const int esz = (g.flags & (CB_EPI_OUT_F32 | CB_EPI_ATOMIC)) ? 4 : 2;
     const bool c_ok = (reinterpret_cast<uintptr_t>(g.C) & 31) == 0 && ((long)g.ldc * esz) % 32 == 0 && g.N % 8 == 0;
     const int asz = (g.flags & CB_EPI_RESIDUAL_F32) ? 4 : 2;
-    const bool aux_ok = !(g.flags & (CB_EPI_RESIDUAL_F32 | CB_EPI_RELU_MASK)) || ((reinterpret_cast<uintptr_t>(g.aux) & 31) == 0 && ((long)g.ld_aux * asz) % 32 == 0);
+    const bool aux_ok = !(g.flags & (CB_EPI_RESIDUAL_F32 | CB_EPI_RELU_MASK)) || (g.flags & CB_EPI_MASK_BITS) ||
+                        ((reinterpret_cast<uintptr_t>(g.aux) & 31) == 0 && ((long)g.ld_aux * asz) % 32 == 0);
     g.direct = (c_ok && aux_ok) ? 1 : 0;
   }
   CUtensorMap tmA, tmB;
@@ -705,5 +720,7 @@ extern "C" int cb_gemm_bf16(const void* A, int lda, int a_mn, const void* B, int
   CB_CHECK(!(flags & CB_EPI_RESIDUAL), "cb_gemm_bf16: bf16 residual epilogue was removed (the residual stream is fp32: use CB_EPI_RESIDUAL_F32)");
   CB_CHECK(!(flags & CB_EPI_RESIDUAL_F32) || (flags & CB_EPI_OUT_F32), "cb_gemm_bf16: CB_EPI_RESIDUAL_F32 requires CB_EPI_OUT_F32");
   CB_CHECK(!(flags & (CB_EPI_RELU_MASK | CB_EPI_RESIDUAL_F32)) || aux, "cb_gemm_bf16: aux pointer required by flags");
+  CB_CHECK(!(flags & CB_EPI_MASK_BITS) || ((flags & CB_EPI_RELU_MASK) && ld_aux >= M && (reinterpret_cast<uintptr_t>(aux) & 3) == 0),
+           "cb_gemm_bf16: CB_EPI_MASK_BITS needs CB_EPI_RELU_MASK and a uint32 [N/32, ld_aux >= M] bit mask");
   return cb::gemm_run(A, lda, a_mn, B, ldb, b_mn, g, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -14,7 +14,7 @@ import torch
 
 from . import _lib
 
-EPI_RELU, EPI_RESIDUAL, EPI_RELU_MASK, EPI_OUT_F32, EPI_ATOMIC, EPI_RESIDUAL_F32 = 1, 2, 4, 8, 16, 64
+EPI_RELU, EPI_RESIDUAL, EPI_RELU_MASK, EPI_OUT_F32, EPI_ATOMIC, EPI_RESIDUAL_F32, EPI_MASK_BITS = 1, 2, 4, 8, 16, 64, 128
 bf16 = torch.bfloat16
 
 
@@ -74,7 +74,8 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     assert out.shape == (M, N) and out.stride(1) == 1
     _call("cb_gemm_bf16", _p(A), A.stride(0), int(a_mn), _p(B), B.stride(0), int(b_mn), _p(out), out.stride(0), M, N, K,
           _p(bias), _p(aux), aux.stride(0) if aux is not None else 0, flags, float(alpha), k_splits, _p(colsum), _stream(), work=2.0 * M * N * K,
-          nbytes=2.0 * (M * K + N * K) + float(M) * N * out.element_size() + (float(M) * N * aux.element_size() if aux is not None else 0.0))
+          nbytes=2.0 * (M * K + N * K) + float(M) * N * out.element_size() +
+          (0.0 if aux is None else float(M) * N / 8 if flags & EPI_MASK_BITS else float(M) * N * aux.element_size()))
     return out
 
 
@@ -83,17 +84,21 @@ def ffn_fused_ok(D: int, F: int) -> bool:
 
 
 def ffn_fwd(y: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor, resid: torch.Tensor, *,
-            save_hidden: bool) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
-    """z2 = resid + relu(y W1^T + b1) W2^T + b2 in one kernel (D = 192).  Returns (z2 fp32, hidden bf16 | None)."""
+            save_hidden: bool, save_mask_bits: Optional[bool] = None):
+    """z2 = resid + relu(y W1^T + b1) W2^T + b2 in one kernel (D = 192).  Returns (z2 fp32, hidden bf16 | None), or — when the
+    ``save_mask_bits`` keyword is given at all — (z2, hidden | None, bits | None): the ReLU mask as bits, uint32 [F/32, ld]
+    (for gemm(..., flags=EPI_RELU_MASK | EPI_MASK_BITS))."""
     T, D = y.shape
     F = w1.shape[0]
     assert y.dtype == bf16 and w1.dtype == bf16 and w2.dtype == bf16 and resid.dtype == torch.float32
     assert y.is_contiguous() and w1.is_contiguous() and w2.is_contiguous() and resid.is_contiguous() and w2.shape == (D, F)
     z2 = torch.empty(T, D, device=y.device, dtype=torch.float32)
     hid = torch.empty(T, F, device=y.device, dtype=bf16) if save_hidden else None
-    _call("cb_ffn_fwd", _p(y), _p(w1), _p(b1), _p(w2), _p(b2), _p(resid), _p(z2), _p(hid), T, D, F, _stream(), work=4.0 * T * D * F,
-          nbytes=float(T) * (D * 2 + D * 8 + (F * 2 if save_hidden else 0)) + 4.0 * D * F)
-    return z2, hid
+    bits = torch.empty(F // 32, (T + 31) // 32 * 32, device=y.device, dtype=torch.int32) if save_mask_bits else None
+    _call("cb_ffn_fwd", _p(y), _p(w1), _p(b1), _p(w2), _p(b2), _p(resid), _p(z2), _p(hid), _p(bits), bits.shape[1] if bits is not None else 0,
+          T, D, F, _stream(), work=4.0 * T * D * F,
+          nbytes=float(T) * (D * 2 + D * 8 + (F * 2 if save_hidden else 0) + (F / 8 if save_mask_bits else 0)) + 4.0 * D * F)
+    return (z2, hid) if save_mask_bits is None else (z2, hid, bits)
 
 
 def splitk_for(K: int, tiles: int, target_ctas: int = 148) -> int:

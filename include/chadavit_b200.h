@@ -35,6 +35,9 @@ extern "C" {
 #define CB_EPI_ATOMIC 16    /* fp32 atomic accumulate into C (split-K weight gradients)                               */
 #define CB_EPI_TOKENIZE 32  /* internal: tokenizer scatter epilogue (use cb_tokenize_fwd)                             */
 #define CB_EPI_RESIDUAL_F32 64 /* C += aux, aux fp32 [M,N], needs CB_EPI_OUT_F32      (x + attn / x + ff, chada_vit.py:99-100) */
+#define CB_EPI_MASK_BITS 128 /* with CB_EPI_RELU_MASK: aux is a BIT mask, uint32 [N/32, ld_aux] (ld_aux >= M, in words): bit j of
+                                aux[n/32][m] set <=> keep C[m, 32*(n/32) + j] — the layout cb_ffn_fwd writes (1 bit instead of 16
+                                per hidden unit, and consecutive rows are consecutive words: coalesced)                          */
 
 const char* cb_last_error(void);
 int cb_version(void);
@@ -131,11 +134,13 @@ int cb_attn_varlen_bwd(const void* dout, const void* qkv, const void* out, const
  *   z2 = resid + relu(y W1^T + b1) W2^T + b2
  * y bf16 [T, D] (norm1 output), w1 bf16 [F, D] (linear1.weight), w2 bf16 [D, F] (linear2.weight), b1 fp32 [F], b2 fp32 [D],
  * resid / z2 fp32 [T, D].  hid bf16 [T, F] receives relu(y W1^T + b1) when not NULL (saved for the backward pass); with
- * hid == NULL the hidden activations never leave the SM.  D must be 192 (tensor-memory budget), F a multiple of 64; other
- * shapes use two cb_gemm_bf16 calls.
+ * hid == NULL the hidden activations never leave the SM.  mask_bits (optional) receives the ReLU mask as bits, uint32
+ * [F/32, ld_bits] (ld_bits >= T, a multiple of 32): bit j of mask_bits[w][t] <=> hid[t, 32 w + j] > 0 — what the backward
+ * product d(hidden) = (dz2 W2) o (hidden > 0) reads through CB_EPI_MASK_BITS instead of the 16x larger hid.
+ * D must be 192 (tensor-memory budget), F a multiple of 64; other shapes use two cb_gemm_bf16 calls.
  */
 int cb_ffn_fwd(const void* y, const void* w1, const float* b1, const void* w2, const float* b2, const float* resid, float* z2,
-               void* hid, int T, int D, int F, void* stream);
+               void* hid, unsigned int* mask_bits, int ld_bits, int T, int D, int F, void* stream);
 
 /* ---------------- DINOHead pieces (src/methods/dino.py:61-111); the Linear layers themselves are cb_gemm_bf16 ---------------- */
 /* nn.GELU (exact erf): out bf16 = gelu(pre fp32);  backward: dpre bf16 = dact fp32 * gelu'(pre) */

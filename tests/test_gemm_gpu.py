@@ -109,12 +109,45 @@ def test_ffn_fused(T, F, save_hidden, gen, monkeypatch):
     y = r(T, D).to(torch.bfloat16).cuda()
     w1, w2 = (r(F, D) / D ** 0.5).to(torch.bfloat16).cuda(), (r(D, F) / F ** 0.5).to(torch.bfloat16).cuda()
     b1, b2, resid = r(F).cuda(), r(D).cuda(), r(T, D).cuda()
-    z2, hid = ops.ffn_fwd(y, w1, b1, w2, b2, resid, save_hidden=save_hidden)
+    z2, hid, bits = ops.ffn_fwd(y, w1, b1, w2, b2, resid, save_hidden=save_hidden, save_mask_bits=True)
     ops.sync_check()
     h_ref = torch.relu(y.float() @ w1.float().t() + b1).to(torch.bfloat16)
     z_ref = h_ref.float() @ w2.float().t() + b2 + resid
     assert (z2 - z_ref).abs().max().item() < 2e-2 * max(1.0, z_ref.abs().max().item())
+    # the ReLU mask as bits: bit j of bits[w, t] <=> hidden[t, 32 w + j] > 0
+    assert bits.shape == (F // 32, (T + 31) // 32 * 32) and bits.dtype == torch.int32
+    unpacked = ((bits[:, :T].t().unsqueeze(-1) >> torch.arange(32, device="cuda", dtype=torch.int32)) & 1).reshape(T, F).bool()
     if save_hidden:
         assert (hid.float() - h_ref.float()).abs().max().item() < 2e-2 * max(1.0, h_ref.float().abs().max().item())
+        assert torch.equal(unpacked, hid > 0)                                   # exactly the stored activations' mask
     else:
+        # against the fp32 reference the two can only differ where the pre-activation is at rounding distance from 0
+        pre = y.float() @ w1.float().t() + b1
+        assert (pre[unpacked != (h_ref > 0)].abs() < 1e-2).all()
         assert hid is None
+
+
+@pytest.mark.parametrize("T", [200, 128 * 9 + 7, 40000])
+def test_relu_mask_bits_equals_bf16_mask(T):
+    """d(hidden) = (dz2 . W2) o (hidden > 0) with the mask as 1 bit per unit (CB_EPI_MASK_BITS, the layout cb_ffn_fwd writes) is
+    bit-identical to the same product masked by the bf16 hidden activations, in the staged (small M) and the weights-resident
+    row-direct epilogue, including the fused bias-gradient column sums."""
+    from chadavit_b200 import ops
+    D, F = 192, 2048
+    g = torch.Generator(device="cpu").manual_seed(T)
+    dz = (torch.randn(T, D, generator=g) * 0.1).to(torch.bfloat16).cuda()
+    w2 = (torch.randn(D, F, generator=g) / F ** 0.5).to(torch.bfloat16).cuda()
+    hid = torch.relu(torch.randn(T, F, generator=g)).to(torch.bfloat16).cuda()
+    ld = (T + 31) // 32 * 32
+    pos = torch.zeros(ld, F, dtype=torch.int64, device="cuda")
+    pos[:T] = (hid > 0).long()
+    words = (pos.view(ld, F // 32, 32) << torch.arange(32, device="cuda")).sum(-1)            # [ld, F/32], bit j = column 32 w + j
+    bits = torch.where(words >= 2 ** 31, words - 2 ** 32, words).to(torch.int32).t().contiguous()
+    cs_a, cs_b = torch.zeros(F, device="cuda"), torch.zeros(F, device="cuda")
+    ref = ops.gemm(dz, w2, b_mn=True, aux=hid, flags=ops.EPI_RELU_MASK, colsum=cs_a)
+    got = ops.gemm(dz, w2, b_mn=True, aux=bits, flags=ops.EPI_RELU_MASK | ops.EPI_MASK_BITS, colsum=cs_b)
+    ops.sync_check()
+    assert torch.equal(ref, got)
+    assert (cs_a - cs_b).abs().max().item() <= 1e-3 * max(1.0, cs_a.abs().max().item())       # fp32 atomics: order differs
+    full = (dz.float() @ w2.float()) * (hid > 0)
+    assert (got.float() - full).abs().max().item() < 2e-2 * max(1.0, full.abs().max().item())

@@ -65,6 +65,20 @@ def ffn_section(dev, T):
         report(f"ffn fused T={TT} (+ hidden store)", timeit(lambda: ops.ffn_fwd(xa, w1, b1, w2, b2, xr, save_hidden=True)), 4.0 * TT * D * F, TT * (D * 2 + D * 8 + F * 2))
 
 
+def dh_section(dev, T):
+    """d(hidden) = (dz2 W2) o (hidden > 0): mask read from the bf16 hidden activations vs from the 1-bit mask of cb_ffn_fwd."""
+    D, F = 192, 2048
+    r = lambda *s: (torch.randn(*s, device=dev) * 0.5).to(bf16)  # noqa: E731
+    for TT in (T, 2 * T):
+        dz, w2, hid = r(TT, D), r(D, F), torch.relu(r(TT, F))
+        bits = torch.randint(-2 ** 31, 2 ** 31 - 1, (F // 32, (TT + 31) // 32 * 32), device=dev, dtype=torch.int32)
+        o, cs = torch.empty(TT, F, device=dev, dtype=bf16), torch.zeros(F, device=dev)
+        report(f"dh T={TT} mask = bf16 hidden", timeit(lambda: ops.gemm(dz, w2, b_mn=True, aux=hid, flags=ops.EPI_RELU_MASK, out=o, colsum=cs)),
+               2.0 * TT * D * F, TT * (D + 2 * F) * 2)
+        report(f"dh T={TT} mask = bits", timeit(lambda: ops.gemm(dz, w2, b_mn=True, aux=bits, flags=ops.EPI_RELU_MASK | ops.EPI_MASK_BITS, out=o, colsum=cs)),
+               2.0 * TT * D * F, TT * (D * 2 + F * 2 + F / 8))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--tokens", type=int, default=68664)
@@ -74,6 +88,8 @@ def main():
         return optim_section("cuda")
     if a.only == "ffn":
         return ffn_section("cuda", a.tokens)
+    if a.only == "dh":
+        return dh_section("cuda", a.tokens)
     T, D, F = a.tokens, 192, 2048
     dev = "cuda"
     r = lambda *s: (torch.randn(*s, device=dev) * 0.5).to(bf16)  # noqa: E731
