@@ -12,6 +12,7 @@ Block semantics reproduced exactly: ``a = MHA(norm1(x)); x = n
 from __future__ import annotations
 
 import math
+import os
 from functools import partial
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -23,6 +24,7 @@ from .. import ops
 from ..arena import ParamArena
 
 FFN_DIM = 2048      # chada_vit.py:160 (dim_feedforward hard-coded)
+_MASK_BITS = os.environ.get("CB_NO_MASK_BITS", "") != "1"   # A/B switch: d(hidden) masked by the 1-bit mask (default) or by the bf16 activations
 PAD_CHANNELS = 10   # chada_vit.py:219 (forward always pads to 10; here: the upper bound on channels per image)
 
 
@@ -271,7 +273,7 @@ class ChAdaViT(nn.Module):
         y, y32, m1b, r1b = ops.layernorm_fwd(z1, g1, b1, eps, out_f32=True, save_stats=save)
         if ops.ffn_fused_ok(x.shape[1], FFN_DIM):   # linear1 -> ReLU -> linear2 -> +residual in one kernel; hidden stored only if saved
             z2, hid, bits = ops.ffn_fwd(y, a.v16(pre + "linear1.weight"), a.v32(pre + "linear1.bias"), a.v16(pre + "linear2.weight"),
-                                        a.v32(pre + "linear2.bias"), y32, save_hidden=save, save_mask_bits=save)
+                                        a.v32(pre + "linear2.bias"), y32, save_hidden=save, save_mask_bits=save and _MASK_BITS)
         else:
             bits = None
             hid = ops.gemm(y, a.v16(pre + "linear1.weight"), bias=a.v32(pre + "linear1.bias"), flags=ops.EPI_RELU)
