@@ -30,6 +30,7 @@ sys.path.insert(0, ROOT)
 
 D_MODEL, N_PROTO, BATCH, N_GLOBAL, N_LOCAL = 192, 4096, 64, 2, 6
 METRIC = "DINO pretrain imgs/s at 1/2/4/8 B200; varlen attn TFLOPS vs BF16 peak"
+FFN3_TRAFFIC = None      # dram bytes of one ffn_fwd3_kernel launch (ncu --set full, profiles/r01_ncu_ffn_fwd3.txt)
 
 
 def channel_counts(batch: int, seed: int = 1234):
@@ -213,7 +214,7 @@ def main():
     # ---- instrumented eager pass of the same step: CUDA-event duration of every attention / GEMM launch (roofline)
     model.use_cuda_graph, keep = False, model.use_cuda_graph
     ops.PROFILE = {"cb_attn_varlen_fwd": [0, 0.0, [], 0.0], "cb_attn_varlen_bwd": [0, 0.0, [], 0.0], "cb_gemm_bf16": [0, 0.0, [], 0.0],
-                   "cb_ffn_fwd": [0, 0.0, [], 0.0]}
+                   "cb_ffn_fwd": [0, 0.0, [], 0.0], "cb_ffn_fwd:nostore": [0, 0.0, [], 0.0]}
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
@@ -284,18 +285,20 @@ def main():
         roof[name] = {"launches_per_step": p["launches"] / args.steps, "ms_per_step": p["ms_total"] / args.steps,
                       "share_of_step": p["ms_total"] / ms_eager, "achieved_tflops": ach, "frac": ach / tf_peak,
                       "achieved_gbs": gbs, "frac_hbm": gbs / hbm_peak}
-    # The dominant SINGLE kernel of the step (profiles/r01_launches_bench_step.txt: ffn_fwd_kernel 25 % of the kernel time, then
-    # attention forward 14 % and backward 12 %; the GEMM class is larger in total but is 14 instantiations over a dozen shapes,
-    # most of them HBM-bound: see "all" for its aggregate TFLOP/s and GB/s) is picked live among the single-kernel classes.
+    # The dominant SINGLE kernel of the step is picked live among the single-kernel classes (profiles/r01_launches_bench_step.txt:
+    # attention backward, attention forward, the two fused feed-forward kernels; the GEMM class is larger in total but is 14
+    # instantiations over a dozen shapes, most of them HBM-bound: see "all" for its aggregate TFLOP/s and GB/s).
     # `traffic` = dram read + write bytes of ONE launch from the committed `ncu --set full` capture of that kernel on the
     # ragged global-crop batch of 64 images (T = 68 664 tokens; the bench launches it on 2x that for the packed global crops).
-    NCU = {"cb_ffn_fwd": ("ffn_fwd_kernel (cb_ffn_fwd)", 366.2e6, "profiles/r01_ncu_ffn_fwd.txt",
-                          "capture: T = 68664, hidden activations stored; algorithmic bytes of that launch 414.7e6 (the tail of the "
-                          "hidden store is still in L2 when the kernel ends)"),
-           "cb_attn_varlen_bwd": ("attn_bwd_kernel<96> (cb_attn_varlen_bwd)", 223.1e6, "profiles/r01_ncu_attn_bwd.txt",
+    NCU = {"cb_attn_varlen_bwd": ("attn_bwd_kernel<96> (cb_attn_varlen_bwd)", 223.1e6, "profiles/r01_ncu_attn_bwd.txt",
                                   "capture: T = 68664, H = 2, d = 96; algorithmic bytes of that launch 237.3e6"),
            "cb_attn_varlen_fwd": ("attn_fwd2_kernel<96> (cb_attn_varlen_fwd)", 87.5e6, "profiles/r01_ncu_attn_fwd.txt",
-                                  "capture: T = 68664, H = 2, d = 96")}
+                                  "capture: T = 68664, H = 2, d = 96"),
+           "cb_ffn_fwd": ("ffn_fwd_kernel (cb_ffn_fwd, hidden activations stored: student pass)", 366.2e6, "profiles/r01_ncu_ffn_fwd.txt",
+                          "capture: T = 68664; algorithmic bytes of that launch 414.7e6 (the tail of the hidden store is still in L2 "
+                          "when the kernel ends)"),
+           "cb_ffn_fwd:nostore": ("ffn_fwd3_kernel (cb_ffn_fwd, hidden activations not stored: teacher / local crops)", FFN3_TRAFFIC,
+                                  "profiles/r01_ncu_ffn_fwd3.txt", "capture: T = 68664; algorithmic bytes of that launch 133.4e6")}
     top = max(NCU, key=lambda k: prof[k]["ms_total"])
     tp = prof[top]
     roofline = {"kernel": NCU[top][0], "bound": "tensor", "achieved": roof[top]["achieved_tflops"], "peak": tf_peak,

@@ -37,11 +37,12 @@ _KERNELS_PER_CALL = {"cb_tokenize_fwd": 2, "cb_tokenize_bwd": 2, "cb_attn_varlen
 PROFILE = None
 
 
-def _call(name: str, *args, work: float = 0.0, nbytes: float = 0.0) -> None:
+def _call(name: str, *args, work: float = 0.0, nbytes: float = 0.0, pkey: Optional[str] = None) -> None:
+    """pkey: profiling class when one entry point dispatches to different kernels (cb_ffn_fwd with / without the hidden store)."""
     lib = _lib.load()
     _lib.launch_count += _KERNELS_PER_CALL.get(name, 1)
-    if PROFILE is not None and name in PROFILE:
-        rec = PROFILE[name]
+    if PROFILE is not None and (pkey or name) in PROFILE:
+        rec = PROFILE[pkey or name]
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         _lib.check(getattr(lib, name)(*args), name)
@@ -96,7 +97,7 @@ def ffn_fwd(y: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tenso
     hid = torch.empty(T, F, device=y.device, dtype=bf16) if save_hidden else None
     bits = torch.empty(F // 32, (T + 31) // 32 * 32, device=y.device, dtype=torch.int32) if save_mask_bits else None
     _call("cb_ffn_fwd", _p(y), _p(w1), _p(b1), _p(w2), _p(b2), _p(resid), _p(z2), _p(hid), _p(bits), bits.shape[1] if bits is not None else 0,
-          T, D, F, _stream(), work=4.0 * T * D * F,
+          T, D, F, _stream(), work=4.0 * T * D * F, pkey="cb_ffn_fwd" if save_hidden else "cb_ffn_fwd:nostore",
           nbytes=float(T) * (D * 2 + D * 8 + (F * 2 if save_hidden else 0) + (F / 8 if save_mask_bits else 0)) + 4.0 * D * F)
     return (z2, hid) if save_mask_bits is None else (z2, hid, bits)
 
