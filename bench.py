@@ -30,7 +30,7 @@ sys.path.insert(0, ROOT)
 
 D_MODEL, N_PROTO, BATCH, N_GLOBAL, N_LOCAL = 192, 4096, 64, 2, 6
 METRIC = "DINO pretrain imgs/s at 1/2/4/8 B200; varlen attn TFLOPS vs BF16 peak"
-FFN3_TRAFFIC = None      # dram bytes of one ffn_fwd3_kernel launch (ncu --set full, profiles/r01_ncu_ffn_fwd3.txt)
+FFN3_TRAFFIC = 100.8e6     # dram bytes of one ffn_fwd3_kernel launch (ncu --set full, profiles/r01_ncu_ffn_fwd3.txt)
 
 
 def channel_counts(batch: int, seed: int = 1234):
