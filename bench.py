@@ -62,8 +62,10 @@ class ClockSampler:
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, index: int):
-        self.index, self.samples, self.stop = index, [], threading.Event()
+    def __init__(self, index: int, enabled: bool = True):
+        """enabled = False (ranks > 0 of a multi-GPU run): no polling — eight concurrent nvidia-smi pollers would contend for the
+        driver and the host cores inside the timed region; rank 0's GPU stands for the box (the line is printed by rank 0)."""
+        self.index, self.samples, self.stop, self.enabled = index, [], threading.Event(), enabled
         self.t = threading.Thread(target=self._run, daemon=True)
 
     def _run(self):
@@ -78,12 +80,14 @@ class ClockSampler:
             self.stop.wait(0.1)
 
     def __enter__(self):
-        self.t.start()
+        if self.enabled:
+            self.t.start()
         return self
 
     def __exit__(self, *a):
         self.stop.set()
-        self.t.join(timeout=6)
+        if self.enabled:
+            self.t.join(timeout=6)
 
     def summary(self):
         if not self.samples:
@@ -201,7 +205,7 @@ def main():
     model.use_cuda_graph = keep
     launches_per_step = _lib.launch_count - launches_eager0
     sync()
-    with ClockSampler(local_rank) as clk:
+    with ClockSampler(local_rank, enabled=(rank == 0)) as clk:
         sync()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
