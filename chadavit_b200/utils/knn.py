@@ -32,16 +32,17 @@ class WeightedKNNClassifier:
 
     def update(self, train_features: Optional[torch.Tensor] = None, train_targets: Optional[torch.Tensor] = None,
                test_features: Optional[torch.Tensor] = None, test_targets: Optional[torch.Tensor] = None) -> None:
-        assert (train_features is None) == (train_targets is None)
-        assert (test_features is None) == (test_targets is None)
-        if train_features is not None:
-            assert train_features.size(0) == train_targets.size(0)
-            self.train_features.append(train_features.detach())
-            self.train_targets.append(train_targets.detach())
-        if test_features is not None:
-            assert test_features.size(0) == test_targets.size(0)
-            self.test_features.append(test_features.detach())
-            self.test_targets.append(test_targets.detach())
+        """Appends a batch to the train and / or test bank; features and targets of a bank come together (knn.py:62-94)."""
+        for feats, targets, bank_f, bank_t in ((train_features, train_targets, self.train_features, self.train_targets),
+                                               (test_features, test_targets, self.test_features, self.test_targets)):
+            if (feats is None) != (targets is None):
+                raise AssertionError("features and targets of a bank must be passed together")
+            if feats is None:
+                continue
+            if feats.size(0) != targets.size(0):
+                raise AssertionError(f"{feats.size(0)} feature rows for {targets.size(0)} targets")
+            bank_f.append(feats.detach())
+            bank_t.append(targets.detach())
 
     __call__ = update
 
