@@ -131,3 +131,55 @@ def test_oracle_extract_features_shapes():
     assert O.extract_features(toks, [2, 4], return_all_tokens=True, mixed_channels=True) is toks
     with pytest.raises(RuntimeError):
         O.extract_features(toks, [2, 4], return_all_tokens=True)              # torch.stack of unequal chunks (base.py:975)
+
+
+def test_knn_bank_bookkeeping_and_no_cpu_fallback():
+    from chadavit_b200.utils.knn import WeightedKNNClassifier
+    knn = WeightedKNNClassifier(k=3, T=0.1, distance_fx="cosine")
+    assert knn.compute() == (-1, -1)                                   # knn.py:109-110
+    knn(train_features=torch.zeros(4, 8), train_targets=torch.zeros(4, dtype=torch.long))
+    knn.update(test_features=torch.zeros(2, 8), test_targets=torch.zeros(2, dtype=torch.long))
+    assert len(knn.train_features) == len(knn.test_features) == 1
+    with pytest.raises(AssertionError):
+        knn.update(train_features=torch.zeros(1, 8))                   # features without targets (knn.py:78)
+    with pytest.raises(AssertionError):
+        knn.update(test_features=torch.zeros(3, 8), test_targets=torch.zeros(2))
+    with pytest.raises(RuntimeError):
+        knn.compute()                                                  # CPU features: the product path has no fallback
+
+
+def test_engine_optimizer_flags_host_logic():
+    """Per-element flag bytes the fused optimizers read: bit0 weight decay (base.py:426-427 via exclude_bias_n_norm_wd), bit1
+    frozen (weight_g under norm_last_layer, alignment padding, last_layer while epoch < freeze_last_layer), bit2 LARS layer-wise
+    adaptation (lars.py:136)."""
+    from chadavit_b200.methods import DINO
+    cfg = {"method": "dino", "backbone": {"kwargs": {"patch_size": 16, "embed_dim": 32, "return_all_tokens": False}},
+           "data": {"max_img_channels": 10, "num_large_crops": 2, "num_small_crops": 0},
+           "method_kwargs": {"num_prototypes": 64, "clip_grad": 3.0},
+           "optimizer": {"name": "lars", "lr": 0.3, "weight_decay": 1e-6, "exclude_bias_n_norm_wd": True,
+                         "kwargs": {"clip_lr": True, "eta": 0.02, "exclude_bias_n_norm": True}}}
+    m = DINO(cfg)
+    assert m.optimizer == "lars" and m.lars["momentum"] == 0.9 and m.clip_grad == 3.0       # src/args/pretrain.py:221 default
+    for name, net in (("backbone", m.backbone), ("head", m.head)):
+        ar = net.arena
+        st = m._opt_state(name, ar)
+        fl = st["flags"]
+        assert "v" not in st and st["norms"].numel() == 3 * len(ar.names)                   # LARS: one momentum buffer, norms workspace
+        used = torch.zeros(ar.numel, dtype=torch.bool)
+        for n, p in zip(ar.names, ar.params):
+            off, cnt, _ = ar.offsets[n]
+            used[off:off + cnt] = True
+            want = (0 if p.dim() <= 1 else 1) | (0 if p.requires_grad else 2) | (4 if p.dim() != 1 else 0)
+            assert (fl[off:off + cnt] == want).all(), (n, want, fl[off].item())
+        assert (fl[~used] == 2).all()                                                        # padding never moves
+        start, seg_of = ar.segment_maps()
+        assert seg_of.numel() == ar.numel // 64 and start[-1].item() == ar.numel // 64
+        assert all(seg_of[ar.offsets[n][0] // 64].item() == i for i, n in enumerate(ar.names))
+    hd = m._opt_state("head", m.head.arena)
+    off, cnt, _ = m.head.arena.offsets["last_layer.weight_v"]
+    assert (hd["flags_frozen_last"][off:off + cnt] == 2).all() and (hd["flags"][off:off + cnt] & 2 == 0).all()
+    assert m.head.last_layer.weight_g.requires_grad is False
+    with pytest.raises(NotImplementedError):
+        DINO({**cfg, "optimizer": {"name": "sgd"}})
+    with pytest.raises(NotImplementedError):
+        m.configure_optimizers()                                                             # stock torch counterpart exists for AdamW only
