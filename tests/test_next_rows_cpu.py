@@ -183,3 +183,23 @@ def test_engine_optimizer_flags_host_logic():
         DINO({**cfg, "optimizer": {"name": "sgd"}})
     with pytest.raises(NotImplementedError):
         m.configure_optimizers()                                                             # stock torch counterpart exists for AdamW only
+
+
+def test_non_square_images_oracle_and_position_grid():
+    """A 96 x 224 image (6 x 14 patches): the oracle reproduces the reference's output, and the product's precomputed linear map
+    of the bicubic position-grid resize (ChAdaViT._interp_matrix, host code) equals the reference interpolation."""
+    from chadavit_b200.backbones import chada_vit
+    c = MG.NONSQ
+    P = {k: torch.from_numpy(v) for k, v in det.det_state_dict(O.backbone_shapes(c["D"]), c["seed"]).items()}
+    x = torch.from_numpy(det.det_pixels(sum(c["counts"]), c["H"], c["W"], c["seed"]))
+    with torch.no_grad():
+        y = O.backbone_forward(x, 0, [c["counts"]], P, nhead=2, final_eps=1e-6)
+    assert (y - torch.from_numpy(G["nonsq.out"])).abs().max().item() < 2e-5
+    m = chada_vit(patch_size=16, embed_dim=c["D"], return_all_tokens=False, max_number_channels=10)
+    m.load_state_dict(P)
+    for (H, W) in ((96, 224), (96, 96), (224, 96)):
+        hp, wp = H // 16, W // 16
+        M = m._interp_matrix(hp, wp, H, W, "cpu")
+        assert M.shape == (hp * wp, 196)
+        ref = O.interp_pos_embed(P["pos_embed"], hp * wp, H, W, 16)[0, 0]
+        assert (M @ P["pos_embed"][0, 0, 1:] - ref).abs().max().item() < 1e-6

@@ -292,3 +292,18 @@ def test_staged_batches_equal_resident_batches(graph):
     for (k, p), (_, q) in zip(a.named_parameters(), b.named_parameters()):
         assert torch.equal(p.detach(), q.detach()), k
     assert torch.equal(a.dino_loss_func.center, b.dino_loss_func.center)
+
+
+@pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent: first hardware run pending (a pass shows up as XPASS)")
+def test_non_square_images_vs_reference():
+    """96 x 224 images (6 x 14 patches): packed tokenizer + bicubic position-grid resize against the reference's output."""
+    from chadavit_b200.backbones import chada_vit
+    c = MG.NONSQ
+    m = chada_vit(patch_size=16, embed_dim=c["D"], return_all_tokens=False, max_number_channels=10)
+    m.load_state_dict(det_params(O.backbone_shapes(c["D"]), c["seed"]))
+    m = m.cuda()
+    x = torch.from_numpy(det.det_pixels(sum(c["counts"]), c["H"], c["W"], c["seed"])).cuda()
+    with torch.no_grad():
+        y = m(x, 0, [c["counts"]]).cpu()
+    ref = torch.from_numpy(G["nonsq.out"])
+    assert y.shape == ref.shape and rel_err(y, ref) < 1e-2
