@@ -149,3 +149,35 @@ def test_bench_sharding_is_token_balanced():
     import bench
     c0, c1 = bench.channel_counts(64), bench.channel_counts(64)
     assert c0 == c1 and len(c0) == 64 and min(c0) >= 1 and max(c0) <= 10   # identical multiset on every rank
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+@pytest.mark.parametrize("kind,tile", [("fwd", 256), ("fwd", 128), ("bwd", 128)])
+def test_attn_schedule_is_a_permutation_and_balanced(seed, kind, tile):
+    """The LPT schedule the persistent attention kernels walk (CTA c takes slots c, c + G, ...): every work item of the
+    plain list appears exactly once, padding slots are empty (seq_end <= seq_start), and the most loaded CTA carries at most
+    4/3 of the mean load + one item (Graham's bound for LPT) — pure host arithmetic, random ragged batches."""
+    from chadavit_b200.ops import PackedLayout
+    rs = np.random.RandomState(seed)
+    counts = rs.randint(1, 11, size=int(rs.randint(3, 70))).tolist()
+    npatch = int(rs.choice([36, 196]))
+    lay = PackedLayout(counts, npatch, "cpu")
+    heads = int(rs.choice([2, 12]))
+    for G in (8, 148):
+        work = lay.attn_work(heads, tile).numpy()
+        sched = lay.attn_schedule(heads, tile, kind, n_ctas=G).numpy()
+        real = sched[sched[:, 2] > sched[:, 1]]
+        assert sorted(map(tuple, real)) == sorted(map(tuple, work))
+        assert (sched[sched[:, 2] <= sched[:, 1]] == 0).all()
+        if len(work) <= G:
+            continue
+        assert len(sched) % G == 0
+        seq = (real[:, 2] - real[:, 1]).astype(np.int64)
+        if kind == "fwd":
+            cost = ((seq + 63) // 64) * np.minimum((real[:, 2] - real[:, 0] + 127) // 128, tile // 128) + 3
+        else:
+            cost = (seq + 127) // 128 + 1
+        loads = np.zeros(G, dtype=np.int64)
+        slot_cta = np.nonzero(sched[:, 2] > sched[:, 1])[0] % G
+        np.add.at(loads, slot_cta, cost)
+        assert loads.max() <= 4 / 3 * loads.mean() + cost.max()
