@@ -203,3 +203,29 @@ def test_non_square_images_oracle_and_position_grid():
         assert M.shape == (hp * wp, 196)
         ref = O.interp_pos_embed(P["pos_embed"], hp * wp, H, W, 16)[0, 0]
         assert (M @ P["pos_embed"][0, 0, 1:] - ref).abs().max().item() < 1e-6
+
+
+def test_warmup_cosine_lr_matches_reference_scheduler():
+    """Closed-form schedule for the engine step == the reference's LinearWarmupCosineAnnealingLR stepped once per update
+    (src/utils/lr_scheduler.py:14-150; skipped on machines without the reference tree: the formula is also checked at its
+    fixed points)."""
+    import importlib.util
+    from chadavit_b200.utils.lr_schedule import warmup_cosine_lr
+    from oracle import ref_loader
+    kw = dict(base_lr=0.3, warmup_steps=10, max_steps=60, warmup_start_lr=3e-5, eta_min=1e-4)
+    assert warmup_cosine_lr(0, **kw) == 3e-5 and abs(warmup_cosine_lr(9, **kw) - 0.3) < 1e-12
+    assert abs(warmup_cosine_lr(10, **kw) - 0.3) < 1e-12 and abs(warmup_cosine_lr(60, **kw) - 1e-4) < 1e-12
+    assert abs(warmup_cosine_lr(35, **kw) - (1e-4 + 0.5 * (0.3 - 1e-4))) < 1e-12          # half way down the cosine
+    if not ref_loader.available():
+        pytest.skip("reference tree not present")
+    spec = importlib.util.spec_from_file_location("_ref_lr_sched", os.path.join(ref_loader.REF_ROOT, "src/utils/lr_scheduler.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    p = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.SGD([p], lr=kw["base_lr"])
+    sched = mod.LinearWarmupCosineAnnealingLR(opt, warmup_epochs=kw["warmup_steps"], max_epochs=kw["max_steps"],
+                                              warmup_start_lr=kw["warmup_start_lr"], eta_min=kw["eta_min"])
+    for step in range(60):
+        assert abs(opt.param_groups[0]["lr"] - warmup_cosine_lr(step, **kw)) < 1e-9, step
+        opt.step()
+        sched.step()
