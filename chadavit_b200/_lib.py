@@ -19,6 +19,7 @@ SIGNATURES = {
     "cb_version": [],
     "cb_num_sms": [],
     "cb_sync_check": [_vp],
+    "cb_attn_schedule": [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp],
     "cb_gemm_bf16": [_vp, _i, _i, _vp, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _f, _i, _vp, _vp],
     "cb_ffn_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "cb_im2col_bf16": [_vp, _vp, _i, _i, _i, _i, _vp],
@@ -43,7 +44,7 @@ SIGNATURES = {
     "cb_colsum_f32": [_vp, _vp, _i, _i, _vp],
     "cb_dino_center_ema": [_vp, _vp, _f, _f, _i, _vp],
     "cb_ema_update": [_vp, _vp, _vp, _f, _l, _vp],
-    "cb_adamw_step": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _l, _f, _f, _f, _f, _f, _i, _f, _f, _vp, _vp],
+    "cb_adamw_step": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _l, _f, _f, _f, _f, _f, _i, _i, _f, _f, _vp, _vp],
     "cb_attn_probs": [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp],
     "cb_split_bf16x3": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "cb_inv_euclid": [_vp, _vp, _vp, _i, _i, _i, _f, _vp],

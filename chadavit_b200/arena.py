@@ -44,6 +44,7 @@ class ParamArena:
                 off, n, shape = self.offsets[name]
                 flat[off:off + n].copy_(p.detach().reshape(-1).to(torch.float32))
                 p.data = flat[off:off + n].view(shape)
+                p._cb_arena = (self, name)        # lets an optimizer handed bare parameters find their arena (utils/lars.py)
         self.fp32 = flat
         self.bf16 = torch.empty(self.numel, device=dev, dtype=torch.bfloat16) if dev.type == "cuda" else None
         self.grad = None
@@ -97,3 +98,13 @@ class ParamArena:
         if self.grad is None or self.grad.device != self.fp32.device:
             self.grad = torch.zeros_like(self.fp32)
         return self.grad
+
+
+def arena_of_param(p: torch.Tensor):
+    """(arena, parameter name) of a parameter owned by a chadavit_b200 module; raises for foreign parameters (no fallback)."""
+    ref = getattr(p, "_cb_arena", None)
+    if ref is None:
+        raise RuntimeError("parameter does not belong to a chadavit_b200 module (ChAdaViT / DINOHead): the fused optimizers work on "
+                           "the modules' flat parameter arenas and have no per-tensor fallback")
+    ref[0].ensure()
+    return ref

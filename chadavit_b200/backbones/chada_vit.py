@@ -132,7 +132,6 @@ class ChAdaViT(nn.Module):
         trunc_normal_(self.channel_token, std=.02)
         self.apply(self._init_weights)          # chada_vit.py:171-183 (Conv2d / in_proj keep torch defaults)
         self._arena: Optional[ParamArena] = None
-        self._layouts: Dict[tuple, ops.PackedLayout] = {}
         self._interp: Dict[tuple, torch.Tensor] = {}
 
     @staticmethod
@@ -161,13 +160,7 @@ class ChAdaViT(nn.Module):
         return a
 
     def _layout(self, counts: Sequence[int], npatch: int, device) -> ops.PackedLayout:
-        key = (tuple(counts), npatch, str(device))
-        lay = self._layouts.get(key)
-        if lay is None:
-            if len(self._layouts) > 64:
-                self._layouts.clear()
-            lay = self._layouts[key] = ops.PackedLayout(counts, npatch, device, PAD_CHANNELS)
-        return lay
+        return ops.get_layout(counts, npatch, device, PAD_CHANNELS)     # process-wide LRU shared by student and teacher
 
     def _interp_matrix(self, hp: int, wp: int, H: int, W: int, device) -> torch.Tensor:
         """(hp*wp, N0) fp32 map equal to the reference's bicubic resize of the patch position grid
@@ -293,8 +286,10 @@ class ChAdaViT(nn.Module):
         return out, (x, u, m1a, r1a, qkv, att, lse, z1, m1b, r1b, y, hid, z2, m2, r2, bits), nxt
 
     # ------------------------------------------------------------------ backward on the packed layout
-    def _backward_impl(self, s: _Saved, dout: torch.Tensor, gflat: torch.Tensor) -> None:
-        """Accumulates parameter gradients of one backbone call into the fp32 arena-shaped buffer ``gflat``."""
+    def _backward_impl(self, s: _Saved, dout: torch.Tensor, gflat: torch.Tensor, block_done=None) -> None:
+        """Accumulates parameter gradients of one backbone call into the fp32 arena-shaped buffer ``gflat``.
+        ``block_done(i)`` (optional) is called when every gradient of block i (and of everything behind it) has been queued;
+        ``block_done(-1)`` after the tokenizer — the training engine hangs its bucketed gradient all-reduce on it."""
         a = self.arena
         g = lambda n: a.g32(n, gflat)  # noqa: E731
         D, P = self.embed_dim, self.token_learner.patch_size
@@ -306,6 +301,8 @@ class ChAdaViT(nn.Module):
         for i in reversed(range(self.depth)):
             dx, dx16 = self._block_bwd(i, s.blocks[i], dx, lay, gflat, last=(i == 0))
             s.blocks[i] = None
+            if block_done is not None:
+                block_done(i)
         N0 = self.pos_embed.shape[2] - 1
         dpos = g("pos_embed").view(N0 + 1, D)
         dpos_patch = dpos[1:] if s.interp is None else torch.zeros(lay.npatch, D, device=dx16.device, dtype=torch.float32)
@@ -314,6 +311,8 @@ class ChAdaViT(nn.Module):
                          dpos_patch=dpos_patch, dpos0=dpos[0], dcls_tok=g("cls_token").view(D), dchan_tok=dchan)
         if s.interp is not None:  # pos_embed receives gradient through the bicubic resize (SURVEY.md §8c probe)
             ops.small_matmul_f32(s.interp, dpos_patch, trans_a=True, out=dpos[1:], accumulate=True)
+        if block_done is not None:
+            block_done(-1)
 
     def _block_bwd(self, i: int, sv, dxo: torch.Tensor, lay: ops.PackedLayout, gflat: torch.Tensor, last: bool):
         """dxo fp32 [T,D] -> (dx fp32, dx bf16 if last).  Gradient residual stream fp32; bf16 only for MMA operands."""

@@ -191,16 +191,19 @@ __global__ void ema_kernel(float* __restrict__ mom, const float* __restrict__ on
 }
 
 struct AdamArgs {
-  float lr, beta1, beta2, eps, wd, bc1, bc2_sqrt, grad_scale, tau;
+  float lr, beta1, beta2, eps, wd, bc1, bc2_sqrt, grad_scale, tau, bc1_late, bc2_sqrt_late;
 };
-// flags[i]: bit0 = apply weight decay, bit1 = frozen (no update).  Optional fused teacher EMA and bf16 shadows.
+// flags[i]: bit0 = apply weight decay, bit1 = frozen (no update), bit4 = the parameter started receiving gradients late (its
+// own step count, torch.optim.AdamW's per-parameter state['step']: second bias-correction pair).  Optional fused teacher EMA
+// and bf16 shadows.
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                              const uint8_t* __restrict__ flags, __nv_bfloat16* __restrict__ p16, float* __restrict__ teacher,
                              __nv_bfloat16* __restrict__ teacher16, AdamArgs a, const float* __restrict__ dev_hyper, long n) {
   const long i0 = (blockIdx.x * (long)blockDim.x + threadIdx.x) * 4;
   if (i0 >= n) return;
-  if (dev_hyper) {   // CUDA-graph replay: per-step scalars live in device memory {lr, 1-beta1^t, sqrt(1-beta2^t), tau}
+  if (dev_hyper) {   // CUDA-graph replay: per-step scalars live in device memory {lr, 1-beta1^t, sqrt(1-beta2^t), tau, late pair}
     a.lr = __ldg(dev_hyper); a.bc1 = __ldg(dev_hyper + 1); a.bc2_sqrt = __ldg(dev_hyper + 2); a.tau = __ldg(dev_hyper + 3);
+    a.bc1_late = __ldg(dev_hyper + 4); a.bc2_sqrt_late = __ldg(dev_hyper + 5);
   }
   float4 P = *reinterpret_cast<float4*>(p + i0);
   const float4 G = *reinterpret_cast<const float4*>(g + i0);
@@ -216,7 +219,8 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
     if (f & 1) x -= a.lr * a.wd * x;
     mm[j] = a.beta1 * mm[j] + (1.f - a.beta1) * gr;
     vv[j] = a.beta2 * vv[j] + (1.f - a.beta2) * gr * gr;
-    x -= (a.lr / a.bc1) * mm[j] / (sqrtf(vv[j]) / a.bc2_sqrt + a.eps);
+    const float bc1 = (f & 16) ? a.bc1_late : a.bc1, bc2s = (f & 16) ? a.bc2_sqrt_late : a.bc2_sqrt;
+    x -= (a.lr / bc1) * mm[j] / (sqrtf(vv[j]) / bc2s + a.eps);
     pp[j] = x;
   }
   *reinterpret_cast<float4*>(p + i0) = P;
@@ -306,12 +310,15 @@ extern "C" int cb_ema_update(float* momentum, const float* online, void* momentu
 }
 extern "C" int cb_adamw_step(float* p, const float* g, float* m, float* v, const unsigned char* flags, void* p_bf16, float* teacher,
                              void* teacher_bf16, long n, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
-                             float grad_scale, float tau, const float* dev_hyper, void* stream) {
+                             int step_late, float grad_scale, float tau, const float* dev_hyper, void* stream) {
   CB_CHECK(n > 0 && n % 4 == 0 && step >= 1, "adamw_step: n=%ld step=%d", n, step);
+  if (step_late < 1) step_late = 1;
   AdamArgs a;
   a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.wd = weight_decay; a.grad_scale = grad_scale; a.tau = tau;
   a.bc1 = 1.f - powf(beta1, (float)step);
   a.bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
+  a.bc1_late = 1.f - powf(beta1, (float)step_late);
+  a.bc2_sqrt_late = sqrtf(1.f - powf(beta2, (float)step_late));
   adamw_kernel<<<blocks4(n), 256, 0, STREAM>>>(p, g, m, v, flags, BFM(p_bf16), teacher, BFM(teacher_bf16), a, dev_hyper, n);
   CB_CUDA(cudaGetLastError());
   return 0;

@@ -49,12 +49,23 @@ class DINOLoss(nn.Module):
         return loss
 
     @torch.no_grad()
-    def update_center(self, teacher_output: torch.Tensor):
-        """sum -> all_reduce(SUM) -> / world / rows -> EMA (src/losses/dino.py:111-118); the EMA is done in place."""
+    def update_center(self, teacher_output: torch.Tensor, run_collective=None):
+        """sum -> all_reduce(SUM) -> / world / rows -> EMA (src/losses/dino.py:111-118); the EMA is done in place.
+        ``run_collective(fn)`` (optional) runs the all-reduce + EMA tail, e.g. on a side stream that the caller joins before the
+        centre is read again (the training engine overlaps it with the backward pass)."""
         t = teacher_output.detach().contiguous().float()
-        batch_sum = ops.colsum_f32(t)
-        world = 1
-        if dist.is_available() and dist.is_initialized():
-            dist.all_reduce(batch_sum)
-            world = dist.get_world_size()
-        ops.center_ema(self.center.view(-1), batch_sum, 1.0 / (world * t.shape[0]), self.center_momentum)
+        ws = getattr(self, "_sum_ws", None)      # persistent workspace: it may be read on a side stream after this call returns
+        if ws is None or ws.device != t.device or ws.numel() != t.shape[1]:
+            ws = self._sum_ws = torch.empty(t.shape[1], device=t.device, dtype=torch.float32)
+        batch_sum = ops.colsum_f32(t, out=ws)
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        world = dist.get_world_size() if multi else 1
+
+        def tail():
+            if multi:
+                dist.all_reduce(batch_sum)
+            ops.center_ema(self.center.view(-1), batch_sum, 1.0 / (world * t.shape[0]), self.center_momentum)
+        if run_collective is not None and multi:
+            run_collective(tail)
+        else:
+            tail()

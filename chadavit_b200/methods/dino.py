@@ -12,6 +12,8 @@ loops of src/methods/base.py:668-733,1186-1276).
 """
 from __future__ import annotations
 
+import collections
+import math
 from typing import Any, Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -243,8 +245,15 @@ class DINO(nn.Module):
         self.list_num_channels: List[List[int]] = []
         self._opt: Dict[str, Dict[str, torch.Tensor]] = {}
         self.use_cuda_graph = bool(_cfg(cfg, "engine.cuda_graph", False))
-        self._graphs: Dict[tuple, dict] = {}
+        self.max_graphs = int(_cfg(cfg, "engine.max_graphs", 2))      # each graph owns its activation pool (~14 GB at 64 images)
+        # gradient all-reduce buckets of `grad_bucket_blocks` encoder blocks, launched on a side stream as the backward retires them
+        self.grad_bucket_blocks = int(_cfg(cfg, "engine.grad_bucket_blocks", 3))
+        self.overlap_comm = bool(_cfg(cfg, "engine.overlap_comm", True))
+        self._graphs: "collections.OrderedDict[tuple, dict]" = collections.OrderedDict()
         self._staging: Optional[dict] = None
+        self._comm: Optional[torch.cuda.Stream] = None
+        self._replicas_synced = False
+        self.last_layer_steps = 0          # optimizer steps head.last_layer has taken (torch AdamW counts steps per parameter)
 
     # ------------------------------------------------------------------ reference-shaped pieces
     @property
@@ -318,11 +327,26 @@ class DINO(nn.Module):
         self.momentum_updater.update_tau(cur_step=self.global_step, max_steps=self.max_steps)
 
     def configure_optimizers(self):
-        """A stock torch optimizer for the autograd drop-in path (AdamW only; LARS lives in the fused engine step)."""
-        if self.optimizer != "adamw":
-            raise NotImplementedError("configure_optimizers: only AdamW has a stock torch counterpart; use fused_train_step for LARS")
-        params = [{"params": list(self.backbone.parameters())}, {"params": list(self.head.parameters())}]
-        return torch.optim.AdamW(params, lr=self.lr, weight_decay=self.weight_decay, betas=self.betas, eps=self.adam_eps)
+        """Optimizer for the autograd drop-in path (base.py:416-440): stock ``torch.optim.AdamW``, or the reference's LARS
+        interface (utils/lars.py) running on the flat-arena kernels.  Parameter groups as in ``learnable_params`` with the
+        ``exclude_bias_n_norm_wd`` split of base.py:426-427."""
+        groups = []
+        for net in (self.backbone, self.head):
+            ps = [p for p in net.parameters() if p.requires_grad]
+            if self.exclude_bias_n_norm_wd:
+                names = {id(p): n for n, p in net.named_parameters()}
+                nd = [p for p in ps if p.dim() <= 1 or "norm" in names[id(p)]]
+                groups += [{"params": [p for p in ps if not (p.dim() <= 1 or "norm" in names[id(p)])]}, {"params": nd, "weight_decay": 0.0}]
+            else:
+                groups.append({"params": ps})
+        for m in (self.backbone, self.head):
+            m.arena                                    # parameters become arena views before the optimizer takes references
+        if self.optimizer == "lars":
+            from ..utils.lars import LARS
+            o = self.lars
+            return LARS(groups, lr=self.lr, weight_decay=self.weight_decay, momentum=o["momentum"], dampening=o["dampening"],
+                        nesterov=o["nesterov"], eta=o["eta"], eps=o["eps"], clip_lr=o["clip_lr"], exclude_bias_n_norm=o["exclude_bias_n_norm"])
+        return torch.optim.AdamW(groups, lr=self.lr, weight_decay=self.weight_decay, betas=self.betas, eps=self.adam_eps)
 
     # ------------------------------------------------------------------ engine path
     def _opt_state(self, name: str, arena: ParamArena) -> Dict[str, torch.Tensor]:
@@ -355,7 +379,9 @@ class DINO(nn.Module):
                     if n.startswith("last_layer."):
                         off, cnt, _ = arena.offsets[n]
                         fl[off:off + cnt] = 2
+                        flags[off:off + cnt] |= 16        # AdamW: this parameter's own step count (self.last_layer_steps)
                 st["flags_frozen_last"] = fl.to(dev)
+                st["flags"] = flags.to(dev)
             self._opt[name] = st
         return st
 
@@ -380,8 +406,42 @@ class DINO(nn.Module):
             st["variants"][key] = fl
         return st["variants"][key]
 
+    def _comm_stream(self, dev) -> torch.cuda.Stream:
+        if self._comm is None or self._comm.device != dev:
+            self._comm = torch.cuda.Stream(device=dev)
+        return self._comm
+
+    def _grad_buckets(self) -> List[Tuple[int, int, int]]:
+        """Backbone gradient-arena buckets as (element start, element end, block whose backward completes the bucket; -1 = the
+        tokenizer).  Parameters are registered cls/channel/pos/token_learner, blocks.0 .. blocks.L-1, norm (contiguous per
+        block), and the backward walks norm -> blocks.L-1 -> .. -> blocks.0 -> tokenizer, so a bucket of `grad_bucket_blocks`
+        consecutive blocks is complete — and can go on the wire — as soon as its lowest block has been differentiated."""
+        a, L, nb = self.backbone.arena, self.backbone.depth, max(1, self.grad_bucket_blocks)
+        start = lambda i: a.offsets[f"blocks.{i}.self_attn.in_proj_weight"][0]  # noqa: E731
+        out, hi, i = [], a.numel, L
+        while i > 0:
+            lo = max(0, i - nb)
+            if lo == 0:
+                break
+            out.append((start(lo), hi, lo))
+            hi, i = start(lo), lo
+        out.append((0, hi, -1))
+        return out
+
     @torch.no_grad()
-    def _step_device_work(self, X, list_num_channels, *, lr: float, tau: float, step: int, world: int, dev_hyper=None) -> torch.Tensor:
+    def _sync_replicas(self) -> None:
+        """Data-parallel start-up: every rank adopts rank 0's parameters, teacher and centre (what Lightning's DDP wrapper does
+        at construction, main_pretrain.py:301), so replicas that were seeded or loaded differently cannot diverge silently."""
+        for m in (self.backbone, self.momentum_backbone, self.head, self.momentum_head):
+            dist.broadcast(m.arena.fp32, 0)
+            m.arena.mark_dirty()
+            m.arena.refresh_bf16(force=True)
+        dist.broadcast(self.dino_loss_func.center, 0)
+        self._replicas_synced = True
+
+    @torch.no_grad()
+    def _step_device_work(self, X, list_num_channels, *, lr: float, tau: float, step: int, world: int, dev_hyper=None,
+                          step_late: Optional[int] = None) -> torch.Tensor:
         """All device work of one step (zero grads .. fused AdamW+EMA); no host-side state is touched, so the sequence can be
         captured once into a CUDA graph and replayed (per-step scalars then come from ``dev_hyper``)."""
         nl = self.num_large_crops
@@ -415,17 +475,37 @@ class DINO(nn.Module):
         L = self.dino_loss_func
         temp = float(L.teacher_temp_schedule[L.epoch])
         loss, _, d16 = ops.dino_loss_fwd_bwd(logits, tlogits, L.center.view(-1), L.num_large_crops, L.student_temp, temp)
-        L.update_center(tlogits)
+        # Collectives (C1 gradient mean, C2 centre) run on a side stream under the backward kernels: the centre sum right away,
+        # the head arena once the head is differentiated, the backbone arena in buckets as the blocks retire.  The compute
+        # stream joins the side stream once, in front of the optimizer.
+        cur = torch.cuda.current_stream()
+        comm = self._comm_stream(gb.device) if (world > 1 and self.overlap_comm) else None
+
+        def on_comm(fn):
+            if comm is None:
+                return fn()
+            comm.wait_stream(cur)
+            with torch.cuda.stream(comm):
+                return fn()
+        L.update_center(tlogits, run_collective=on_comm)
         # backward: head, then each saved backbone call
         dfe = hd._backward_impl(hs, d16, gh)
-        o = 0
-        for s, r in zip(saved, rows):
-            bb._backward_impl(s, dfe[o:o + r].contiguous(), gb)
-            o += r
-        # data-parallel replicas: average gradients (C1) — flat arenas, one NCCL all-reduce each
         if world > 1:
-            dist.all_reduce(gb)
-            dist.all_reduce(gh)
+            on_comm(lambda: dist.all_reduce(gh))
+        buckets = self._grad_buckets() if world > 1 else []
+        o = 0
+        for k, (s, r) in enumerate(zip(saved, rows)):
+            last_call = k == len(saved) - 1
+
+            def block_done(i, _last=last_call):
+                if _last:
+                    for lo, hi, at in buckets:
+                        if at == i:
+                            on_comm(lambda: dist.all_reduce(gb[lo:hi]))
+            bb._backward_impl(s, dfe[o:o + r].contiguous(), gb, block_done=block_done if world > 1 else None)
+            o += r
+        if comm is not None:
+            cur.wait_stream(comm)
         # AdamW + teacher EMA + bf16 refresh of student and teacher, one launch per network
         for name, on, mo, g in (("backbone", bb, tb, gb), ("head", hd, th, gh)):
             st = self._opt_state(name, on.arena)
@@ -445,7 +525,7 @@ class DINO(nn.Module):
             if clip:
                 ops.scale_grads(g, seg_of, st["norms"])
             ops.adamw_step(on.arena.fp32, g, st["m"], st["v"], lr=lr, beta1=self.betas[0], beta2=self.betas[1], eps=self.adam_eps,
-                           weight_decay=self.weight_decay, step=step, flags=flags, p_bf16=on.arena.bf16,
+                           weight_decay=self.weight_decay, step=step, step_late=step_late, flags=flags, p_bf16=on.arena.bf16,
                            teacher=mo.arena.fp32, teacher_bf16=mo.arena.bf16, grad_scale=1.0 / world, tau=tau, dev_hyper=dev_hyper)
         return loss
 
@@ -505,17 +585,21 @@ class DINO(nn.Module):
         if staged is not None:
             torch.cuda.current_stream().wait_event(staged["ready"])
         world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        if world > 1 and not self._replicas_synced:
+            self._sync_replicas()
         self.global_step += 1
+        if self.current_epoch >= self.freeze_last_layer:
+            self.last_layer_steps += 1
         lr = self.lr if lr is None else lr
         tau = self.momentum_updater.cur_tau
-        step = self.global_step
+        step, step_late = self.global_step, max(1, self.last_layer_steps)
         loss = None
         if self.use_cuda_graph:
-            loss = self._graph_step(X, list_num_channels, lr, tau, step, world)
+            loss = self._graph_step(X, list_num_channels, lr, tau, step, step_late, world)
         if loss is None:
             dev = bb.arena.fp32.device
             X = [x if x.is_cuda else x.to(dev, non_blocking=True) for x in X]    # host (pinned) crops are accepted
-            loss = self._step_device_work(X, list_num_channels, lr=lr, tau=tau, step=step, world=world)
+            loss = self._step_device_work(X, list_num_channels, lr=lr, tau=tau, step=step, step_late=step_late, world=world)
         if staged is not None:
             staged["consumed"] = torch.cuda.Event()
             staged["consumed"].record()
@@ -525,30 +609,37 @@ class DINO(nn.Module):
         self.momentum_updater.update_tau(cur_step=self.global_step, max_steps=self.max_steps)
         return loss[0]
 
-    def _graph_step(self, X, list_num_channels, lr, tau, step, world):
+    def _graph_step(self, X, list_num_channels, lr, tau, step, step_late, world):
         L = self.dino_loss_func
         key = (tuple(tuple(int(c) for c in l) for l in list_num_channels[:len(X)]), tuple(tuple(x.shape) for x in X),
                self.current_epoch < self.freeze_last_layer, float(L.teacher_temp_schedule[L.epoch]), world)
         ent = self._graphs.get(key)
         if ent is None:                      # first sighting: run eagerly (also warms up caches / kernel attributes)
-            if len(self._graphs) >= 2:
-                self._graphs.clear()
+            while len(self._graphs) >= max(1, self.max_graphs):
+                self._graphs.popitem(last=False)          # least recently used graph (and its private activation pool)
             self._graphs[key] = {"seen": 1}
             return None
-        import math
-        hyper = [lr, 1.0 - self.betas[0] ** step, math.sqrt(1.0 - self.betas[1] ** step), tau]
+        self._graphs.move_to_end(key)
+        b1, b2 = self.betas
+        hyper = [lr, 1.0 - b1 ** step, math.sqrt(1.0 - b2 ** step), tau, 1.0 - b1 ** step_late, math.sqrt(1.0 - b2 ** step_late)]
         if "graph" not in ent:
             try:
                 dev = self.backbone.arena.fp32.device
                 ent["x"] = [torch.empty(x.shape, device=dev, dtype=torch.float32) for x in X]
-                ent["hyper"] = torch.zeros(4, dtype=torch.float32, device=dev)
+                ent["hyper"] = torch.zeros(8, dtype=torch.float32, device=dev)
                 for d, x in zip(ent["x"], X):
                     d.copy_(x, non_blocking=True)
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    ent["loss"] = self._step_device_work(ent["x"], list_num_channels, lr=lr, tau=tau, step=step, world=world,
-                                                         dev_hyper=ent["hyper"])
+                # the capture bakes in the device pointers of everything the kernels read: the packed layouts (cu_seqlens, channel
+                # maps, attention schedules) are kept alive by the entry itself, whatever the process-wide layout cache evicts
+                ops.KEEPALIVE = ent["keep"] = []
+                try:
+                    with torch.cuda.graph(g):
+                        ent["loss"] = self._step_device_work(ent["x"], list_num_channels, lr=lr, tau=tau, step=step, step_late=step_late,
+                                                             world=world, dev_hyper=ent["hyper"])
+                finally:
+                    ops.KEEPALIVE = None
                 ent["graph"] = g
             except Exception as e:            # capture unsupported in this configuration: stay eager, loudly
                 import warnings
@@ -560,8 +651,39 @@ class DINO(nn.Module):
             for d, x in zip(ent["x"], X):          # H2D (pinned host crops) or D2D into the graph's static input buffers
                 if d.data_ptr() != x.data_ptr():
                     d.copy_(x, non_blocking=True)
-        # 16 bytes from PAGEABLE memory: the driver copies them into the command stream at call time, so the host may queue many
+        # 24 bytes from PAGEABLE memory: the driver copies them into the command stream at call time, so the host may queue many
         # steps ahead without a later step's scalars overwriting an earlier step's (a reused pinned buffer would race)
-        ent["hyper"].copy_(torch.tensor(hyper, dtype=torch.float32), non_blocking=True)
+        ent["hyper"][:6].copy_(torch.tensor(hyper, dtype=torch.float32), non_blocking=True)
         ent["graph"].replay()
-        return ent["loss"]
+        return ent["loss"].clone()             # the graph's loss buffer is overwritten by the next replay
+
+    # ------------------------------------------------------------------ engine checkpoint (resume)
+    def engine_state_dict(self) -> Dict[str, Any]:
+        """Everything the fused engine keeps OUTSIDE ``state_dict()``: optimizer moments (flat arenas), LARS first-update set,
+        step counters, current tau and epoch.  Together with ``state_dict()`` (parameters, teacher, centre) this resumes a run
+        exactly; the reference gets the same from Lightning's optimizer/scheduler checkpoint state (src/utils/checkpointer.py)."""
+        opt = {}
+        for name, st in self._opt.items():
+            opt[name] = {k: (v.detach().clone() if isinstance(v, torch.Tensor) else sorted(v)) for k, v in st.items()
+                         if k in ("m", "v", "stepped")}
+        return {"optimizer": self.optimizer, "opt": opt, "global_step": self.global_step, "last_layer_steps": self.last_layer_steps,
+                "current_epoch": self.current_epoch, "cur_tau": self.momentum_updater.cur_tau}
+
+    def load_engine_state_dict(self, sd: Dict[str, Any]) -> None:
+        if sd["optimizer"] != self.optimizer:
+            raise ValueError(f"engine state was saved with optimizer '{sd['optimizer']}', this engine runs '{self.optimizer}'")
+        for name, on in (("backbone", self.backbone), ("head", self.head)):
+            if name not in sd["opt"]:
+                continue
+            on._ready()
+            st = self._opt_state(name, on.arena)
+            for k, v in sd["opt"][name].items():
+                if k == "stepped":
+                    st["stepped"] = set(v)
+                else:
+                    st[k].copy_(v)
+        self.global_step, self.last_layer_steps = int(sd["global_step"]), int(sd["last_layer_steps"])
+        self.current_epoch = int(sd["current_epoch"])
+        self.dino_loss_func.epoch = self.current_epoch
+        self.momentum_updater.cur_tau = float(sd["cur_tau"])
+        self._graphs.clear()

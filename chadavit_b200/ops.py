@@ -7,6 +7,7 @@ from __future__ import annotations
 
 from typing import List, Optional, Sequence, Tuple
 
+import collections
 import math
 
 import numpy as np
@@ -195,54 +196,41 @@ class PackedLayout:
         self.chan_img = torch.from_numpy(chan_img).to(device, non_blocking=True)
         self.chan_idx = torch.from_numpy(chan_idx).to(device, non_blocking=True)
         self._work = {}
+        self._work_host = {}
 
     def attn_work(self, nheads: int, tile: int = 128) -> torch.Tensor:
         """(n_work, 4) int32 {q_row0, seq_start, seq_end, head}, longest sequences first (LPT order)."""
-        if (nheads, tile) not in self._work:
-            items = []
-            order = np.argsort(-(self.cu_host[1:] - self.cu_host[:-1]), kind="stable")
-            for b in order:
-                s, e = int(self.cu_host[b]), int(self.cu_host[b + 1])
-                for h in range(nheads):
-                    for q0 in range(s, e, tile):
-                        items.append((q0, s, e, h))
-            w = torch.tensor(items, dtype=torch.int32).reshape(-1, 4)
-            self._work[(nheads, tile)] = w.to(self.device, non_blocking=True)
-        return self._work[(nheads, tile)]
+        return self._schedule(nheads, tile, "list", 0)
 
     def attn_schedule(self, nheads: int, tile: int, kind: str, n_ctas: Optional[int] = None) -> torch.Tensor:
         """Work list of `attn_work` re-ordered for the persistent kernels, which give CTA c the slots c, c + G, c + 2G, ...:
         items are assigned longest-processing-time-first to the least loaded of the G CTAs and written back round-major,
-        padded with empty slots (seq_end <= seq_start, skipped by the kernels).  Pure host arithmetic on Python ints.
+        padded with empty slots (seq_end <= seq_start, skipped by the kernels).  Pure host arithmetic on the Python ints of
+        list_num_channels (cb_attn_schedule, csrc/host.cu): no device synchronisation, ~50 us per schedule.
         kind = "fwd" (cost ~ kv sub-tiles x query tiles of the item) or "bwd" (cost ~ query tiles per kv tile)."""
-        import heapq
-        G = n_ctas or _lib.load().cb_num_sms()
+        return self._schedule(nheads, tile, kind, n_ctas or _lib.load().cb_num_sms())
+
+    def _schedule(self, nheads: int, tile: int, kind: str, G: int) -> torch.Tensor:
         key = (nheads, tile, kind, G)
-        if key not in self._work:
-            w = self.attn_work(nheads, tile).cpu().numpy()
-            if len(w) <= G:
-                self._work[key] = self.attn_work(nheads, tile)
-                return self._work[key]
-            seq = (w[:, 2] - w[:, 1]).astype(np.int64)
-            if kind == "fwd":
-                ntile = np.minimum((w[:, 2] - w[:, 0] + 127) // 128, tile // 128)
-                cost = ((seq + 63) // 64) * ntile + 3
-            else:
-                cost = (seq + 127) // 128 + 1
-            order = np.argsort(-cost, kind="stable")
-            heap = [(0, c) for c in range(G)]
-            lists = [[] for _ in range(G)]
-            for i in order:
-                load, c = heapq.heappop(heap)
-                lists[c].append(i)
-                heapq.heappush(heap, (load + int(cost[i]), c))
-            rounds = max(len(l) for l in lists)
-            out = np.zeros((rounds * G, 4), dtype=np.int32)
-            for c, l in enumerate(lists):
-                for r, i in enumerate(l):
-                    out[r * G + c] = w[i]
-            self._work[key] = torch.from_numpy(out).to(self.device, non_blocking=True)
-        return self._work[key]
+        w = self._work.get(key)
+        if w is None:
+            import ctypes as C
+            lib = _lib.load()
+            n_items = int(nheads * ((self.cu_host[1:] - self.cu_host[:-1] + tile - 1) // tile).sum())
+            cap = n_items if kind == "list" else (n_items // max(G, 1) + 8) * max(G, 1) + n_items // 4
+            n_out = C.c_int(0)
+            while True:
+                host = np.zeros((cap, 4), dtype=np.int32)
+                rc = lib.cb_attn_schedule(self.cu_host.ctypes.data, self.B, nheads, tile, {"list": 0, "fwd": 1, "bwd": 2}[kind], G,
+                                          host.ctypes.data, cap, C.byref(n_out))
+                if rc == 0:
+                    break
+                if n_out.value <= cap:
+                    _lib.check(rc, "cb_attn_schedule")
+                cap = n_out.value
+            self._work_host[key] = host[:n_out.value]
+            w = self._work[key] = torch.from_numpy(self._work_host[key]).to(self.device, non_blocking=True)
+        return w
 
     def non_cls_rows(self) -> torch.Tensor:
         """Packed rows of all patch tokens in (b, c, p) order (return_all_tokens=True output order, chada_vit.py:283-287)."""
@@ -250,6 +238,28 @@ class PackedLayout:
             rows = np.concatenate([np.arange(self.cu_host[b] + 1, self.cu_host[b + 1], dtype=np.int32) for b in range(self.B)])
             self._noncls = torch.from_numpy(rows).to(self.device, non_blocking=True)
         return self._noncls
+
+
+# One layout cache for the whole process (student and teacher see the same batches): LRU, strong references.  A CUDA graph
+# that baked a layout's device pointers keeps the layout alive itself (KEEPALIVE), so eviction here can never free memory a
+# captured graph still reads.
+_LAYOUTS: "collections.OrderedDict[tuple, PackedLayout]" = collections.OrderedDict()
+LAYOUT_CACHE_SIZE = 32
+KEEPALIVE: Optional[list] = None      # set to a list while a CUDA graph is being captured: every layout handed out is appended
+
+
+def get_layout(counts: Sequence[int], npatch: int, device, max_channels: int = 10) -> PackedLayout:
+    key = (tuple(counts), npatch, str(device), max_channels)
+    lay = _LAYOUTS.get(key)
+    if lay is None:
+        lay = _LAYOUTS[key] = PackedLayout(counts, npatch, device, max_channels)
+        while len(_LAYOUTS) > LAYOUT_CACHE_SIZE:
+            _LAYOUTS.popitem(last=False)
+    else:
+        _LAYOUTS.move_to_end(key)
+    if KEEPALIVE is not None:
+        KEEPALIVE.append(lay)
+    return lay
 
 
 # ------------------------------------------------------------------------------------------------ tokenizer / attention
@@ -377,8 +387,9 @@ def dino_loss_fwd_bwd(student: torch.Tensor, teacher: torch.Tensor, center: torc
     return loss, d32, d16
 
 
-def colsum_f32(x: torch.Tensor) -> torch.Tensor:
-    out = torch.empty(x.shape[1], device=x.device, dtype=torch.float32)
+def colsum_f32(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    if out is None:
+        out = torch.empty(x.shape[1], device=x.device, dtype=torch.float32)
     _call("cb_colsum_f32", _p(x), _p(out), x.shape[0], x.shape[1], _stream())
     return out
 
@@ -392,11 +403,14 @@ def ema_update(momentum_flat: torch.Tensor, online_flat: torch.Tensor, tau: floa
     _call("cb_ema_update", _p(momentum_flat), _p(online_flat), _p(momentum_bf16), float(tau), momentum_flat.numel(), _stream())
 
 
-def adamw_step(p, g, m, v, *, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, step=1, flags=None, p_bf16=None, teacher=None,
-               teacher_bf16=None, grad_scale=1.0, tau=1.0, dev_hyper=None) -> None:
-    """dev_hyper: optional device fp32[4] {lr, 1-beta1^step, sqrt(1-beta2^step), tau} read by the kernel (CUDA-graph replay)."""
+def adamw_step(p, g, m, v, *, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, step=1, step_late=None, flags=None, p_bf16=None,
+               teacher=None, teacher_bf16=None, grad_scale=1.0, tau=1.0, dev_hyper=None) -> None:
+    """step_late: step count of the elements flagged bit4 (parameters that started receiving gradients late; default = step).
+    dev_hyper: optional device fp32[6] {lr, 1-beta1^step, sqrt(1-beta2^step), tau, 1-beta1^step_late, sqrt(1-beta2^step_late)}
+    read by the kernel (CUDA-graph replay)."""
     _call("cb_adamw_step", _p(p), _p(g), _p(m), _p(v), _p(flags), _p(p_bf16), _p(teacher), _p(teacher_bf16), p.numel(), float(lr),
-          float(beta1), float(beta2), float(eps), float(weight_decay), int(step), float(grad_scale), float(tau), _p(dev_hyper), _stream())
+          float(beta1), float(beta2), float(eps), float(weight_decay), int(step), int(step if step_late is None else step_late),
+          float(grad_scale), float(tau), _p(dev_hyper), _stream())
 
 
 def param_norms(p, g, seg_start_block, seg_clip, partial, norms, *, grad_scale=1.0, clip=0.0) -> None:

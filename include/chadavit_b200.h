@@ -44,6 +44,16 @@ int cb_version(void);
 int cb_num_sms(void);
 /* synchronise `stream` and report any asynchronous kernel failure */
 int cb_sync_check(void* stream);
+/*
+ * HOST-side helper (no device work): the work list of cb_attn_varlen_fwd / _bwd for one ragged batch, derived from the host
+ * copy of cu_seqlens (B+1 ints, i.e. from list_num_channels, src/data/channels_strategies.py:31-85 — no device sync).
+ * Items are int32 quadruples {first row of the tile, seq_start, seq_end, head}, `tile` rows per item, longest sequences
+ * first.  mode 0: the plain list.  mode 1 (forward cost model) / 2 (backward cost model): the list assigned
+ * longest-processing-time-first to n_ctas persistent CTAs, written round-major (CTA c walks slots c, c + n_ctas, ...) and
+ * padded with all-zero slots.  out: host int32 [cap, 4]; *n_out = slots written (or needed, when the call fails with cap
+ * too small).
+ */
+int cb_attn_schedule(const int* cu_host, int B, int nheads, int tile, int mode, int n_ctas, int* out, int cap, int* n_out);
 
 /*
  * C[M,N] (+)= alpha * op(A)[M,K] · op(B)[N,K]^T (+ bias[N]) with the epilogue in `flags`; bf16 operands, fp32
@@ -172,11 +182,14 @@ int cb_dino_center_ema(float* center, const float* batch_sum, float scale, float
 int cb_ema_update(float* momentum, const float* online, void* momentum_bf16, float tau, long n, void* stream);
 /* torch.optim.AdamW step over a flat arena, optionally fused with the teacher EMA and the bf16 shadow
  * refresh of both networks.  flags[i]: bit0 = weight decay applies, bit1 = frozen (e.g. head.last_layer while
- * current_epoch < freeze_last_layer, dino.py:374-376); NULL = decay everything.  dev_hyper (optional, device fp32[4] =
- * {lr, 1-beta1^step, sqrt(1-beta2^step), tau}) overrides the per-step scalars so a captured CUDA graph can be replayed. */
+ * current_epoch < freeze_last_layer, dino.py:374-376), bit4 = the element belongs to a parameter whose own step count is
+ * step_late (torch.optim.AdamW counts steps per parameter and skips parameters without a gradient, so head.last_layer starts
+ * at 1 when it is unfrozen); NULL = decay everything.  dev_hyper (optional, device fp32[6] = {lr, 1-beta1^step,
+ * sqrt(1-beta2^step), tau, 1-beta1^step_late, sqrt(1-beta2^step_late)}) overrides the per-step scalars so a captured CUDA
+ * graph can be replayed. */
 int cb_adamw_step(float* p, const float* g, float* m, float* v, const unsigned char* flags, void* p_bf16, float* teacher,
                   void* teacher_bf16, long n, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
-                  float grad_scale, float tau, const float* dev_hyper, void* stream);
+                  int step_late, float grad_scale, float tau, const float* dev_hyper, void* stream);
 
 /* Attention probabilities of one block for ChAdaViT.get_last_selfattention (src/backbones/vit/chada_vit.py:313-320, read by
  * main_attn.py:200-207): out[b, h, i, j] = softmax_j(q_i . k_j * scale) over the tokens of packed sequence b; qkv is the
@@ -207,7 +220,7 @@ int cb_scale_grads(float* g, const int* seg_of_block, const float* norms, long n
 /* LARS.step over a flat arena (src/utils/lars.py:113-167), fused with the teacher EMA and the bf16 shadow refresh like
  * cb_adamw_step.  flags[i]: bit0 = the group's weight decay applies (0 otherwise: base.py:426-427), bit1 = frozen / no
  * gradient, bit2 = layer-wise adaptation applies (p.ndim != 1 or not exclude_bias_n_norm), bit3 = first update of this
- * parameter (momentum buffer := d_p).  The gradient used is g * grad_scale * coef_s.  dev_hyper (optional, device fp32[4];
+ * parameter (momentum buffer := d_p).  The gradient used is g * grad_scale * coef_s.  dev_hyper (optional, device fp32[>=4];
  * slots 0 = lr and 3 = tau are read) serves CUDA-graph replay. */
 int cb_lars_step(float* p, const float* g, float* buf, const unsigned char* flags, const int* seg_of_block, const float* norms,
                  void* p_bf16, float* teacher, void* teacher_bf16, long n, float lr, float momentum, float dampening,

@@ -70,7 +70,7 @@ def main():
         yo = O.backbone_forward(x, 0, [c["counts"]], P, nhead=nhead, final_eps=eps,
                                 return_all_tokens=c["all_tokens"], max_channels_model=c["max_ch"])
         print(f"{name}: ref vs oracle max|d| = {(y - yo).abs().max().item():.3e}  shape {tuple(y.shape)}")
-        if name in ("tiny_224_cls", "tiny_96_cls"):
+        if name in ("tiny_224_cls", "tiny_96_cls", "moyen_224_cls"):
             wgt = torch.from_numpy(det.det_uniform(tuple(y.shape), 99, 1.0))
             (y * wgt).sum().backward()
             for k, p in m.named_parameters():

@@ -170,6 +170,8 @@ def test_engine_optimizer_flags_host_logic():
             off, cnt, _ = ar.offsets[n]
             used[off:off + cnt] = True
             want = (0 if p.dim() <= 1 else 1) | (0 if p.requires_grad else 2) | (4 if p.dim() != 1 else 0)
+            if name == "head" and n.startswith("last_layer."):
+                want |= 16                                                                   # AdamW: the parameter's own step count
             assert (fl[off:off + cnt] == want).all(), (n, want, fl[off].item())
         assert (fl[~used] == 2).all()                                                        # padding never moves
         start, seg_of = ar.segment_maps()
@@ -181,8 +183,15 @@ def test_engine_optimizer_flags_host_logic():
     assert m.head.last_layer.weight_g.requires_grad is False
     with pytest.raises(NotImplementedError):
         DINO({**cfg, "optimizer": {"name": "sgd"}})
-    with pytest.raises(NotImplementedError):
-        m.configure_optimizers()                                                             # stock torch counterpart exists for AdamW only
+    from chadavit_b200.utils.lars import LARS
+    opt = m.configure_optimizers()                                                           # the reference's LARS interface (lars.py:21-111)
+    assert isinstance(opt, LARS) and isinstance(opt, torch.optim.Optimizer) and len(opt.param_groups) == 4
+    assert [g["weight_decay"] for g in opt.param_groups] == [1e-6, 0.0, 1e-6, 0.0] and opt.param_groups[0]["eta"] == 0.02
+    assert all(p.requires_grad for g in opt.param_groups for p in g["params"])
+    foreign = torch.nn.Parameter(torch.zeros(3))
+    foreign.grad = torch.ones(3)
+    with pytest.raises(RuntimeError):
+        LARS([foreign], lr=0.1).step()                                                       # bare tensors: no per-tensor fallback
 
 
 def test_non_square_images_oracle_and_position_grid():
