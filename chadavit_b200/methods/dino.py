@@ -551,15 +551,18 @@ class DINO(nn.Module):
             st = self._staging = {"device": dev, "stream": torch.cuda.Stream(device=dev), "sets": [{}, {}], "next": 0}
         s = st["sets"][st["next"]]
         st["next"] ^= 1
-        shapes = tuple(tuple(x.shape) for x in X)
         cs: torch.cuda.Stream = st["stream"]
-        if s.get("shapes") != shapes:
-            s["shapes"] = shapes
-            s["x"] = [torch.empty(sh, device=dev, dtype=torch.float32) for sh in shapes]
+        # Device buffers are kept at the largest size seen per crop and handed out as views: ragged batches change sum(C_b)
+        # every step, and a fresh allocation would force the copy stream to wait for all queued compute.
+        need = [x.numel() for x in X]
+        if len(s.get("buf", ())) != len(X) or any(b.numel() < n for b, n in zip(s["buf"], need)):
+            s["buf"] = [torch.empty(max(n, s["buf"][i].numel() if i < len(s.get("buf", ())) else 0), device=dev, dtype=torch.float32)
+                        for i, n in enumerate(need)]
             s["consumed"] = None
             cs.wait_stream(torch.cuda.current_stream(dev))     # fresh blocks may still be in use by queued work of this stream
         elif s["consumed"] is not None:
             cs.wait_event(s["consumed"])                       # the step that read this set two batches ago has finished with it
+        s["x"] = [b[:n].view(x.shape) for b, n, x in zip(s["buf"], need, X)]
         with torch.cuda.stream(cs):
             for d, x in zip(s["x"], X):
                 d.copy_(x, non_blocking=True)

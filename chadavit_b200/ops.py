@@ -120,7 +120,8 @@ def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps:
     y32 = torch.empty(rows, D, device=x.device, dtype=torch.float32) if out_f32 else None
     mean = torch.empty(rows, device=x.device, dtype=torch.float32) if save_stats else None
     rstd = torch.empty(rows, device=x.device, dtype=torch.float32) if save_stats else None
-    _call("cb_layernorm_fwd", _p(x), _p(in_idx), _p(gamma), _p(beta), _p(y), _p(y32), _p(mean), _p(rstd), rows, D, float(eps), _stream())
+    _call("cb_layernorm_fwd", _p(x), _p(in_idx), _p(gamma), _p(beta), _p(y), _p(y32), _p(mean), _p(rstd), rows, D, float(eps), _stream(),
+          nbytes=float(rows) * D * (4 + (2 if out_bf16 else 0) + (4 if out_f32 else 0)))
     return y, y32, mean, rstd
 
 
@@ -132,7 +133,7 @@ def layernorm2_fwd(x: torch.Tensor, gamma_a, beta_a, eps_a: float, gamma_b, beta
     y2 = torch.empty(rows, D, device=x.device, dtype=bf16)
     st = [torch.empty(rows, device=x.device, dtype=torch.float32) if save_stats else None for _ in range(4)]
     _call("cb_layernorm2_fwd", _p(x), _p(gamma_a), _p(beta_a), float(eps_a), _p(gamma_b), _p(beta_b), float(eps_b), _p(y1), _p(y2),
-          _p(st[0]), _p(st[1]), _p(st[2]), _p(st[3]), rows, D, _stream())
+          _p(st[0]), _p(st[1]), _p(st[2]), _p(st[3]), rows, D, _stream(), nbytes=float(rows) * D * 10)
     return (y1, y2, *st)
 
 
@@ -148,7 +149,8 @@ def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, mean: 
     dx32 = mk(x.shape, device=x.device, dtype=torch.float32) if want_f32 else None
     dx16 = mk(x.shape, device=x.device, dtype=bf16) if want_bf16 else None
     _call("cb_layernorm_bwd", _p(dy), _p(x), _p(idx), _p(gamma), _p(mean), _p(rstd), _p(dres), _p(dx32), _p(dx16), _p(dgamma),
-          _p(dbeta), _p(dcolsum), rows, D, _stream())
+          _p(dbeta), _p(dcolsum), rows, D, _stream(),
+          nbytes=float(rows) * D * (8 + (4 if dres is not None else 0) + (4 if want_f32 else 0) + (2 if want_bf16 else 0)))
     return dx32, dx16
 
 

@@ -145,10 +145,79 @@ def test_two_rank_reductions_equal_single_process_on_concatenated_batch(tmp_path
 
 
 def test_bench_sharding_is_token_balanced():
+    """bench.py deals every step's GLOBAL batch (same draw on every rank) to the ranks with data/balance.py: the shards are a
+    partition of the global batch with equal cardinality, and the most loaded rank carries < 1 % more estimated work than the
+    mean (contiguous DistributedSampler-like slices: several %)."""
     sys.path.insert(0, ROOT)
     import bench
+    from chadavit_b200.data.balance import image_cost, token_balanced_shards
     c0, c1 = bench.channel_counts(64), bench.channel_counts(64)
-    assert c0 == c1 and len(c0) == 64 and min(c0) >= 1 and max(c0) <= 10   # identical multiset on every rank
+    assert c0 == c1 and len(c0) == 64 and min(c0) >= 1 and max(c0) <= 10
+    for world in (2, 4, 8):
+        worst_bal, worst_raw = 0.0, 0.0
+        for step in range(6):
+            glob = bench.channel_counts(64 * world, seed=1234 + 7919 * step)
+            shards = token_balanced_shards(glob, world)
+            assert sorted(i for s in shards for i in s) == list(range(64 * world)) and all(len(s) == 64 for s in shards)
+            per_rank = [bench.step_counts(step, r, world) for r in range(world)]
+            assert sorted(c for cs in per_rank for c in cs) == sorted(glob)
+            load = np.array([sum(image_cost(c) for c in cs) for cs in per_rank])
+            raw = np.array([sum(image_cost(c) for c in bench.step_counts(step, r, world, balanced=False)) for r in range(world)])
+            worst_bal, worst_raw = max(worst_bal, load.max() / load.mean()), max(worst_raw, raw.max() / raw.mean())
+        assert worst_bal < 1.01 < worst_raw, (world, worst_bal, worst_raw)
+    with pytest.raises(ValueError):
+        token_balanced_shards([1, 2, 3], 2)
+
+
+def _bucket_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from chadavit_b200.methods import DINO
+    m = DINO({"backbone": {"kwargs": {"embed_dim": 32}}, "method_kwargs": {"num_prototypes": 64}, "engine": {"grad_bucket_blocks": 5}})
+    a = m.backbone.arena
+    g = torch.arange(a.numel, dtype=torch.float32) * (rank + 1)
+    flat = g.clone()
+    dist.all_reduce(flat)
+    fired = []
+    for i in list(range(m.backbone.depth - 1, -1, -1)) + [-1]:        # the order _backward_impl calls block_done in
+        for lo, hi, at in m._grad_buckets():
+            if at == i:
+                dist.all_reduce(g[lo:hi])
+                fired.append((lo, hi, at))
+    if rank == 0:
+        torch.save({"equal": torch.equal(g, flat), "fired": fired, "numel": a.numel}, out)
+    dist.destroy_process_group()
+
+
+def test_bucketed_gradient_allreduce_plan_two_ranks(tmp_path):
+    """The engine's gradient buckets (DINO._grad_buckets: contiguous arena slices of `grad_bucket_blocks` encoder blocks, fired
+    as the backward retires them) partition the arena, fire in descending address order, contain every parameter of the blocks
+    differentiated so far, and all-reducing them one by one (gloo, world_size 2) equals ONE flat all-reduce."""
+    from chadavit_b200.methods import DINO
+    world = 2
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    out = str(tmp_path / "b.pt")
+    mp.spawn(_bucket_worker, args=(world, port, out), nprocs=world, join=True)
+    got = torch.load(out)
+    assert got["equal"]
+    fired = got["fired"]
+    assert fired[0][1] == got["numel"] and fired[-1][0] == 0 and fired[-1][2] == -1
+    assert all(fired[k][0] == fired[k + 1][1] for k in range(len(fired) - 1))            # contiguous, descending, no gaps
+    for nb in (1, 3, 12, 40):
+        m = DINO({"backbone": {"kwargs": {"embed_dim": 32}}, "method_kwargs": {"num_prototypes": 64}, "engine": {"grad_bucket_blocks": nb}})
+        a = m.backbone.arena
+        bk = m._grad_buckets()
+        assert sum(hi - lo for lo, hi, _ in bk) == a.numel and 1 <= len(bk) <= 13
+        for lo, hi, at in bk:
+            for n in a.names:
+                off, cnt, _ = a.offsets[n]
+                if lo <= off < hi:                                   # a parameter inside a bucket is complete when the bucket fires
+                    blk = int(n.split(".")[1]) if n.startswith("blocks.") else (99 if n.startswith("norm.") else -1)
+                    assert blk >= at, (n, at)
+                    assert off + cnt <= hi
 
 
 @pytest.mark.parametrize("seed", [0, 1, 2])
