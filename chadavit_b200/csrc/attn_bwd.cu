@@ -9,9 +9,12 @@
 //     dQ_i = dS K             (SS MMA: the SAME dS^T smem tile read MN-major, K MN-major) -> TMEM -> fp32 atomics
 //   dK/dV stay in TMEM for the whole work item and are written once as bf16 into dqkv[:, D:3D].
 // delta = rowsum(dO o O) and the fp32->bf16 conversion of the dQ accumulator are small row-wise kernels below.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "chadavit_b200.h"
 #include "internal.h"
+#include "attn_bwd.cuh"
 
 namespace cb {
 
@@ -20,46 +23,13 @@ static __device__ unsigned long long g_cb_timeline[CB_TL_ROLES][CB_TL_LEN];
 #endif
 
 template <int HD>
-struct BwdCfg {
-  static constexpr int CHUNK = (HD % 64 == 0) ? 64 : (HD % 32 == 0 ? 32 : 16);
-  static constexpr int NCH = HD / CHUNK;
-  static constexpr int SWZ = CHUNK == 64 ? 3 : (CHUNK == 32 ? 2 : 1);
-  static constexpr int CHUNK_BYTES = 128 * CHUNK * 2;
-  static constexpr int TILE_BYTES = NCH * CHUNK_BYTES;
-  static constexpr int SBO = 8 * CHUNK * 2;
-  static constexpr int QDO_STAGES = HD <= 96 ? 2 : 1;
-  static constexpr int DS_BYTES = 128 * 128 * 2;  // two [128 x 64] 128B-swizzled sub-tiles
-  static constexpr int DQ_SLABS = (HD + 31) / 32;       // 16-column dQ chunks handled by one epilogue warp
-  static constexpr int DQ_STAGE_BYTES = 8 * DQ_SLABS * 2048;   // dQ drain: per warp DQ_SLABS x (32 rows x 64 B) slabs for TMA reduce-add
-  static constexpr int SMEM_BYTES = TILE_BYTES * (2 + 2 * QDO_STAGES) + DS_BYTES + DQ_STAGE_BYTES + 1024 /*lse,delta*/ + 1024 + 256;
-  static constexpr int COL_S = 0, COL_DP = 128, COL_DK = 256, COL_DV = 384;
-};
-
-__device__ __forceinline__ float fast_exp2_b(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-struct AttnBwdArgs {
-  const int4* work;  // {kv_row0 (global row), seq_start, seq_end, head}
-  int n_work;
-  const float* lse;    // [H, T]
-  const float* delta;  // [H, T]
-  float* dq_acc;       // [T, D] fp32, zero-initialised
-  __nv_bfloat16* dqkv; // [T, 3D]: dK -> cols [D,2D), dV -> cols [2D,3D)
-  int T, D;
-  float scale, scale_log2;
-};
-
-template <int HD>
 __global__ void __launch_bounds__(352, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                 const __grid_constant__ CUtensorMap tmDQ, const AttnBwdArgs a) {
   using Cfg = BwdCfg<HD>;
   constexpr int NS = Cfg::QDO_STAGES;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
   uint8_t* sK = smem;
   uint8_t* sV = sK + Cfg::TILE_BYTES;
   uint8_t* sQ = sV + Cfg::TILE_BYTES;                  // [NS]
@@ -275,15 +245,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       // LSE (threads 0-127) / delta (threads 128-255) of a q tile: loaded into a register one iteration ahead (the global
       // latency hides under the wait for the dV/dK/dQ MMAs), published to smem at the start of the iteration.
       const float* stage_src = (tid256 < 128 ? a.lse : a.delta) + (long)head * a.T;
-      auto stage_load = [&](int i_) -> float {           // LSE in the exp2 domain / delta pre-multiplied by the softmax scale
+      // the RAW value stays in the register and is scaled when it is published: arithmetic on it here would stall the warp for the
+      // whole global-memory latency
+      const float stage_mul = tid256 < 128 ? LOG2E : a.scale;   // LSE in the exp2 domain / delta pre-multiplied by the softmax scale
+      const float stage_oob = tid256 < 128 ? INFINITY : 0.f;    // +inf -> p = 0 for q rows past the sequence
+      auto stage_load = [&](int i_) -> float {
         const int t = wk.y + i_ * 128 + (tid256 & 127);
-        if (t < wk.z) return tid256 < 128 ? __ldg(stage_src + t) * LOG2E : __ldg(stage_src + t) * a.scale;
-        return tid256 < 128 ? INFINITY : 0.f;            // +inf -> p = 0 for q rows past the sequence
+        return ldg_f32_pinned(stage_src + (t < wk.z ? t : wk.y));
       };
+      auto stage_fix = [&](float v, int i_) -> float { return (wk.y + i_ * 128 + (tid256 & 127) < wk.z) ? v * stage_mul : stage_oob; };
       float stage_val = stage_load(0);
       for (int i = 0; i < nq; ++i, ++it) {
         const int q0 = wk.y + i * 128;
-        if (tid256 < 128) sLSE[tid256] = stage_val; else sDelta[tid256 - 128] = stage_val;
+        if (tid256 < 128) sLSE[tid256] = stage_fix(stage_val, i); else sDelta[tid256 - 128] = stage_fix(stage_val, i);
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (tl_on) CB_TL(tl_role, tl, 1);
         mbar_wait(s_full, it & 1);
@@ -493,14 +467,22 @@ extern "C" int cb_attn_varlen_bwd(const void* dout, const void* qkv, const void*
   AttnBwdArgs a{};
   a.work = reinterpret_cast<const int4*>(work); a.n_work = n_work; a.lse = lse; a.delta = delta_ws; a.dq_acc = dq_acc_ws;
   a.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv); a.T = T; a.D = D; a.scale = softmax_scale; a.scale_log2 = softmax_scale * 1.4426950408889634f;
+  // generation 2 (attn_bwd2.cu: E / D phases overlapped with the tensor pipe) needs 64 free TMEM columns: head_dim <= 96.
+  // CB_ATTN_BWD_V=1 (read once) forces generation 1 everywhere — A/B measurements only.
+  static const bool force_v1 = [] { const char* e = getenv("CB_ATTN_BWD_V"); return e && e[0] == '1'; }();
   int rc;
-  switch (D / H) {
-    case 16: rc = launch_bwd<16>(qkv, dout, a, s); break;
-    case 32: rc = launch_bwd<32>(qkv, dout, a, s); break;
-    case 64: rc = launch_bwd<64>(qkv, dout, a, s); break;
-    case 96: rc = launch_bwd<96>(qkv, dout, a, s); break;
-    case 128: rc = launch_bwd<128>(qkv, dout, a, s); break;
-    default: set_error("attn_bwd: unsupported head_dim %d (supported: 16, 32, 64, 96, 128)", D / H); return 1;
+  const int hd = D / H;
+  if (!force_v1 && (hd == 32 || hd == 64 || hd == 96)) {   // (head_dim 16: generation 1 measures 5 % faster)
+    rc = attn_bwd2_launch(hd, qkv, dout, a, s);
+  } else {
+    switch (hd) {
+      case 16: rc = launch_bwd<16>(qkv, dout, a, s); break;
+      case 32: rc = launch_bwd<32>(qkv, dout, a, s); break;
+      case 64: rc = launch_bwd<64>(qkv, dout, a, s); break;
+      case 96: rc = launch_bwd<96>(qkv, dout, a, s); break;
+      case 128: rc = launch_bwd<128>(qkv, dout, a, s); break;
+      default: set_error("attn_bwd: unsupported head_dim %d (supported: 16, 32, 64, 96, 128)", hd); return 1;
+    }
   }
   if (rc) return rc;
   const long n8 = ((long)T * D + 7) / 8;

@@ -51,7 +51,7 @@ template <int HD>
 __global__ void __launch_bounds__(192, 1) attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdArgs a) {
   using Cfg = AttCfg<HD>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + Cfg::TILE_BYTES;
   uint8_t* sV = sK + ATT_KV_STAGES * Cfg::TILE_BYTES;

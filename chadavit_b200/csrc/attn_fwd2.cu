@@ -139,7 +139,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   using Cfg = Att2Cfg<HD>;
   constexpr int NS = Cfg::KV_STAGES, KVT = Cfg::KVT;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
   uint8_t* sQ = smem;                                   // [2] query tiles
   uint8_t* sK = sQ + 2 * Cfg::Q_TILE_BYTES;             // [NS] KVT-row sub-tiles
   uint8_t* sV = sK + NS * Cfg::KV_TILE_BYTES;           // [NS]

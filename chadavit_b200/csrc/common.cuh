@@ -69,6 +69,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Non-blocking probe (mbarrier.test_wait): try_wait may suspend the thread for an implementation-defined time when the phase
+// is not complete, which is what a waiter wants but would serialise a loop that polls SEVERAL barriers.
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a protocol bug must not hang the GPU (a hung box is a lost box).  ~2^28 polls ≈ seconds.
 __device__ __forceinline__ uint64_t global_ns() {
   uint64_t t;
@@ -280,6 +291,14 @@ __device__ __forceinline__ void ldg256(const void* p, uint32_t (&r)[8]) {
 }
 __device__ __forceinline__ void stg256(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f, uint32_t g, uint32_t h) {
   asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e), "r"(f), "r"(g), "r"(h) : "memory");
+}
+
+// Global load that STAYS where it is written: a plain __ldg may be sunk by the compiler to its first use, which turns a
+// prefetch-into-register (issue now, consume one tile later) into a fully exposed memory latency.
+__device__ __forceinline__ float ldg_f32_pinned(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
 }
 
 // bf16 helpers

@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(320, 1)
 ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
                const FfnArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
   uint8_t* sY = smem;                                   // [2] row tiles
   uint8_t* sW1 = sY + 2 * FF_Y_BYTES;                   // [S1] W1 chunks
   uint8_t* sW2 = sW1 + FF_S1 * FF_W1_BYTES;             // [S2] W2 chunks

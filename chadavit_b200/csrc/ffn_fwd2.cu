@@ -48,7 +48,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
 ffn_fwd2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2, const Ffn2Args a) {
   using namespace f2;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
   uint8_t* sW1 = smem;
   uint8_t* sW2 = sW1 + S1 * W1_BYTES;
   float* sB1 = reinterpret_cast<float*>(sW2 + S2 * W2_BYTES);

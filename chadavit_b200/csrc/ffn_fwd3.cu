@@ -49,7 +49,7 @@ ffn_fwd3_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
                 const Ffn3Args a) {
   using namespace f3;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
   uint8_t* sY = smem;
   uint8_t* sW1 = sY + Y_BYTES;
   uint8_t* sW2 = sW1 + S1 * W1_BYTES;

@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
   const int kb_total = (g.K + BK - 1) / BK;
   // staged: [STAGES x A k-block][STAGES x B k-block][epilogue slabs]; WRES: [kb_total x B k-block][2 x kb_total x A k-block][slabs]
   uint8_t* sB = WRES ? smem : smem + Cfg::STAGES * Cfg::A_BYTES;

@@ -88,9 +88,65 @@ def test_backward_matches_oracle_and_golden(name):
         if eg is not None:
             worst_g = max(worst_g, eg)
             print(f"  grad {k}: rel err vs bf16-operand oracle {eo:.3e} | vs fp32 reference {eg:.3e}")
-        assert eo < 0.12, (k, eo)
+        assert eo < GRAD_TOL[name], (k, eo)
     print(f"{name}: worst grad rel err vs bf16-operand oracle {worst_o:.3e}, vs fp32 reference {worst_g:.3e}")
     assert worst_g < 0.3
+
+
+# End-to-end gradients of the 12-block post-norm net are ill-conditioned under bf16 operand rounding: on CPU the ORACLE with
+# bf16 operands sits 14.3 % (cls_token), 9.7 % (pos_embed), 7-9 % (block weights) from its own fp32 evaluation for
+# moyen_224_cls (measured).  Two bf16 evaluations that round at different points (kernels vs oracle)
+# differ by about as much, so the end-to-end bound cannot be tight; what pins the kernels is the PER-BLOCK test below, where
+# nothing is amplified through the depth.
+GRAD_TOL = {"tiny_224_cls": 0.12, "tiny_96_cls": 0.12, "moyen_224_cls": 0.16}
+
+
+@pytest.mark.parametrize("name,blocks", [("moyen_224_cls", [0, 5, 11]), ("moyen_h12_cls", [3]), ("tiny_224_cls", [7])])
+def test_block_backward_matches_oracle_per_block(name, blocks):
+    """Backward of ONE encoder block at a time, at the headline width (D = 192: fused FFN forward with the hidden store and the
+    1-bit ReLU mask, d(hidden) with CB_EPI_MASK_BITS, layernorm2, attention backward generation 2): the block's own saved input
+    x_i and a fixed upstream gradient go through ChAdaViT._block_bwd and through the oracle's encoder_layer (bf16 operand
+    rounding, every sequence on its own = the packed semantics).  No depth amplification: d(input) and every parameter
+    gradient of the block agree to a few 1e-3 .. 1e-2 (chada_vit.py:75-116)."""
+    c = CASES[name]
+    P, x, nhead, eps = backbone_case(c)
+    m = _build(c)
+    m.load_state_dict(P)
+    m = m.cuda().train()
+    m._ready()
+    with torch.no_grad():
+        _, saved = m._forward_impl(x.cuda(), c["counts"], save=True)
+        lay = saved.lay
+        cu = lay.cu_host.tolist()
+        for i in blocks:
+            sv = saved.blocks[i]
+            xi = sv[0].float().cpu()
+            dxo = torch.from_numpy(det.det_uniform(tuple(xi.shape), 300 + i, 1.0))
+            gflat = torch.zeros_like(m.arena.fp32)
+            dx, _ = m._block_bwd(i, sv, dxo.cuda(), lay, gflat, last=False)
+            torch.cuda.synchronize()
+            pre = f"blocks.{i}."
+            Pb = {k: v.clone().requires_grad_() for k, v in P.items() if k.startswith(pre)}
+            xo = xi.clone().requires_grad_()
+            with torch.enable_grad(), O.operand_rounding(torch.bfloat16):
+                tot = 0.0
+                for b in range(len(cu) - 1):
+                    seq = xo[cu[b]:cu[b + 1]][None]
+                    out = O.encoder_layer(seq, torch.zeros(1, seq.shape[1], dtype=torch.bool), Pb, pre, nhead)
+                    tot = tot + (out[0] * dxo[cu[b]:cu[b + 1]]).sum()
+                tot.backward()
+            e_dx = rel_err(dx.cpu(), xo.grad)
+            worst, wk = e_dx, "dx"
+            for k, v in Pb.items():
+                e = rel_err(m.arena.g32(k, gflat).cpu(), v.grad)
+                if e > worst:
+                    worst, wk = e, k
+                assert e < BLOCK_TOL, (name, i, k, e)
+            print(f"{name} block {i}: d(input) rel err {e_dx:.3e}, worst parameter gradient {wk} {worst:.3e}")
+            assert e_dx < BLOCK_TOL, (name, i, e_dx)
+
+
+BLOCK_TOL = 4e-2
 
 
 def test_error_conventions():

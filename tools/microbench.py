@@ -79,6 +79,20 @@ def dh_section(dev, T):
                2.0 * TT * D * F, TT * (D * 2 + F * 2 + F / 8))
 
 
+def attn_section(dev):
+    """Attention forward / backward alone: the bench's ragged global-crop batch, 32 uniform 1961-token sequences, and the
+    base/16 stress shape (D = 768, 12 heads of 64)."""
+    r = lambda *s: (torch.randn(*s, device=dev) * 0.5).to(bf16)  # noqa: E731
+    for tag, counts, D, H in (("ragged 64 (bench)", np.random.RandomState(1234).randint(1, 11, size=64).tolist(), 192, 2),
+                              ("ragged 128 (2 crops)", np.random.RandomState(1234).randint(1, 11, size=64).tolist() * 2, 192, 2),
+                              ("32 x 1961", [10] * 32, 192, 2), ("base/16 64 x 1961", [10] * 64, 768, 12), ("moyen h12 64 ragged", np.random.RandomState(1234).randint(1, 11, size=64).tolist(), 192, 12)):
+        lay = ops.PackedLayout(counts, 196, dev)
+        qkv, do = r(lay.T, 3 * D), r(lay.T, D)
+        out, lse = ops.attn_fwd(qkv, lay, H)
+        report(f"attn fwd {tag} T={lay.T} H={H} d={D // H}", timeit(lambda: ops.attn_fwd(qkv, lay, H)), 4.0 * D * lay.sum_sq, lay.T * 4 * D * 2)
+        report(f"attn bwd {tag} T={lay.T} H={H} d={D // H}", timeit(lambda: ops.attn_bwd(do, qkv, out, lse, lay, H)), 10.0 * D * lay.sum_sq, lay.T * 9 * D * 2)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--tokens", type=int, default=68664)
@@ -90,6 +104,8 @@ def main():
         return ffn_section("cuda", a.tokens)
     if a.only == "dh":
         return dh_section("cuda", a.tokens)
+    if a.only == "attn":
+        return attn_section("cuda")
     T, D, F = a.tokens, 192, 2048
     dev = "cuda"
     r = lambda *s: (torch.randn(*s, device=dev) * 0.5).to(bf16)  # noqa: E731

@@ -39,7 +39,7 @@ w2f, b2f, x32f = r(D, F), torch.randn(D, device=dev), torch.randn(T, D, device=d
 def run():
     if which == "fwd":
         ops.attn_fwd(qkv, lay, 2)
-    elif which == "bwd":
+    elif which in ("bwd", "bwd2"):
         ops.attn_bwd(do, qkv, out, lse, lay, 2)
     elif which in ("ffn", "ffn2", "ffn3"):
         ops.ffn_fwd(x16, w1, b1, w2f, b2f, x32f, save_hidden=False)
