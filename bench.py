@@ -480,7 +480,7 @@ def main():
         cfg["engine"]["overlap_comm"] = False
     model = DINO(cfg).to(dev)
     pools = make_pools(1234 + rank, dev)
-    n_total = args.warmup + 3 * args.steps + 8
+    n_total = args.warmup + 3 * args.steps + 16
     all_counts = [step_counts(t, rank, world, balanced=not args.unbalanced) for t in range(n_total)]
 
     def batch_of(t, src=pools):
@@ -496,7 +496,12 @@ def main():
         tcur[0] += 1
         return batch_of(tcur[0], src)
     model.use_cuda_graph = bool(args.fixed_batch)
-    for _ in range(args.warmup):
+    # Untimed allocator settle, then the W warm-up steps: every ragged batch has its own tensor sizes, and until torch's caching
+    # allocator has grown blocks for the largest of them a step can hit cudaMalloc (milliseconds, synchronising).  The worst
+    # case (all images 10 channels) first, then a few ordinary batches.
+    if not args.fixed_batch:
+        model.fused_train_step(([p for p in pools], None, [[10] * BATCH] * (N_GLOBAL + N_LOCAL)))
+    for _ in range(6 + args.warmup):
         loss = model.fused_train_step(next_batch())
     sync()
     # ---- timed region 1: inputs resident in HBM, a new ragged batch every step

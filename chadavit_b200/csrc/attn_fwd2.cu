@@ -1,21 +1,19 @@
-// Varlen attention forward, production kernel (attn_fwd.cu keeps the simpler 1-tile kernel as a cross-check).
+// Varlen multi-head self-attention forward (the SDPA inside nn.MultiheadAttention, chada_vit.py:105-111) for sm_100a.
 //
 // A work item is (sequence, head, PAIR of 128-query tiles A, B): every K/V tile fetched from L2 serves 256 query rows.
 // Roles: warps 0-3 softmax of tile A, warps 4-7 softmax of tile B (1 thread = 1 query row, no cross-thread reductions),
 // warps 8 / 9 MMA issuers of tile A / B (whole warp convergent, one elected lane issues: back-to-back UTCHMMA), warp 10 TMA.
 //
-// The KV dimension advances in 48-row SUB-TILES, every query tile owns TWO score buffers, and Q lives in TENSOR MEMORY:
-//     TMEM columns (d = 96):  S_A0 48 | S_A1 48 | S_B0 48 | S_B1 48 | O_A 96 | O_B 96 | Q_A 48 | Q_B 48   = 480 of 512
+// The KV dimension advances in 64-row SUB-TILES and every query tile owns TWO score buffers; Q and K/V come through TMA:
+//     TMEM columns:  S_A0 64 | S_A1 64 | S_B0 64 | S_B1 64 | O_A 128 | O_B 128   = 512
+//     shared memory: Q_A, Q_B (one [128 x d] tile each) + a K/V ring of [64 x d] sub-tiles (up to 8 stages)
 //   * two score buffers: the MMA stream  S_A(0) S_B(0) S_A(1) S_B(1) | PV_A(0) S_A(2) | PV_B(0) S_B(2) | PV_A(1) S_A(3) ...  has
 //     the next score tile of a warpgroup finished before that warpgroup is done with the current one.  The in-kernel timeline
 //     (tools/timeline.py) of the earlier design (one 128-wide score buffer per query tile) showed each warpgroup idle for a
 //     tensor-pipe round trip (PV + next QK) after every tile, and the two warpgroups then colliding on the MUFU unit
-//     (4 ex2/clk/SMSP: 2048 clk per 128x256 score block against 1536 clk of MMA — the binding resource at d = 96);
-//   * Q in TMEM: S = Q·K^T is a TS MMA (A from tensor memory), so only K comes out of shared memory.  With Q in shared memory
-//     the operand fetch of every QK MMA (Q 4 KB + K) ran into the ~100 B/clk the tensor pipe gets from smem (measured: 81 clk
-//     per 128x128x16 MMA instead of 64, 73 clk per 128x64x16 instead of 32).  Each softmax thread loads its own query row
-//     from global memory (192 contiguous bytes) and stores it with tcgen05.st — no TMA, no smem for Q;
-//   * 48 = the widest sub-tile for which all of the above fits 512 columns at d = 96 (32 at d = 128).
+//     (4 ex2/clk/SMSP: 2048 clk per 128x256 score block against 1536 clk of MMA — the binding resource at d = 96).
+//   * Measured and not kept: 48-row sub-tiles with Q in tensor memory (630 TFLOP/s against 704), 8 softmax
+//     warps row-split on one tile, software prefetch of the next S.
 //
 // Softmax details: bf16 P overwrites the first half of its own S buffer and feeds O += P·V as a TS MMA (V read MN-major from
 // its TMA tile).  S is read once per sub-tile: probabilities are computed speculatively against the running reference
@@ -406,8 +404,8 @@ static int launch_fwd2(const void* qkv, const Attn2Args& a, cudaStream_t stream)
   return 0;
 }
 
-int attn_fwd2_run(const void* qkv, const int* work, int n_work, void* out, float* lse, int T, int D, int H, float softmax_scale,
-                  cudaStream_t s) {
+static int attn_fwd2_run(const void* qkv, const int* work, int n_work, void* out, float* lse, int T, int D, int H, float softmax_scale,
+                         cudaStream_t s) {
   Attn2Args a{};
   a.work = reinterpret_cast<const int4*>(work); a.n_work = n_work; a.out = reinterpret_cast<__nv_bfloat16*>(out); a.lse = lse;
   a.T = T; a.D = D; a.scale_log2 = softmax_scale * 1.4426950408889634f;
@@ -422,6 +420,15 @@ int attn_fwd2_run(const void* qkv, const int* work, int n_work, void* out, float
 }
 
 }  // namespace cb
+
+extern "C" int cb_attn_varlen_fwd(const void* qkv, const int* work, int n_work, int q_tile, void* out, float* lse, int T, int D, int H,
+                                  float softmax_scale, void* stream) {
+  using namespace cb;
+  CB_CHECK(T > 0 && H > 0 && D % H == 0 && n_work > 0, "attn_fwd: bad shape T=%d D=%d H=%d n_work=%d", T, D, H, n_work);
+  CB_CHECK((3 * D) % 8 == 0, "attn_fwd: 3*D must be a multiple of 8");
+  CB_CHECK(q_tile == 256, "attn_fwd: q_tile must be 256 (work items are pairs of 128-row query tiles)");
+  return attn_fwd2_run(qkv, work, n_work, out, lse, T, D, H, softmax_scale, reinterpret_cast<cudaStream_t>(stream));
+}
 
 #ifdef CB_TIMELINE
 extern "C" int cb_debug_timeline_fwd(void* dst) {   // host buffer of CB_TL_ROLES * CB_TL_LEN u64; clears the device copy

@@ -289,24 +289,22 @@ extern "C" int cb_debug_timeline_ffn(void* dst) {
 #endif
 
 extern "C" int cb_ffn_fwd(const void* y, const void* w1, const float* b1, const void* w2, const float* b2, const float* resid, float* z2,
-                          void* hid, unsigned int* mask_bits, int ld_bits, int T, int D, int F, void* stream) {
+                          void* hid, unsigned int* mask_bits, int ld_bits, int T, int D, int F, int kernel, void* stream) {
   using namespace cb;
   CB_CHECK(T > 0 && D == FF_D && F % FF_C == 0 && F >= FF_C && F <= FF_MAX_F, "ffn_fwd: T=%d D=%d F=%d (this kernel handles D = %d, F a multiple of %d up to %d)", T, D, F, FF_D, FF_C, FF_MAX_F);
   CB_CHECK(!mask_bits || (ld_bits >= T && ld_bits % 32 == 0 && (reinterpret_cast<uintptr_t>(mask_bits) & 127) == 0),
            "ffn_fwd: mask_bits needs ld_bits >= T (a multiple of 32) and a 128-byte aligned buffer");
   CB_CHECK(((reinterpret_cast<uintptr_t>(resid) | reinterpret_cast<uintptr_t>(z2) | reinterpret_cast<uintptr_t>(hid) | reinterpret_cast<uintptr_t>(b1) |
              reinterpret_cast<uintptr_t>(b2)) & 31) == 0, "ffn_fwd: resid / z2 / hid / biases must be 32-byte aligned");
-  // Kernel generations (measured at T = 68664 / 137328, F = 2048: profiles/r01_microbench_kernels.txt):
-  //   3  ffn_fwd3.cu  cluster of two, 128-unit chunks          122 / 230 us without the hidden store, 165 / 319 us with it
-  //   2  ffn_fwd2.cu  cluster of two, y in tensor memory       133 / 252 us                            155 / 300 us
-  //   1  this file    pair of tiles per CTA                    142 / 275 us                            155 / 299 us
+  // Two kernels (measured at T = 68664 / 137328, F = 2048: profiles/r01_microbench_kernels.txt):
+  //   ffn_fwd3.cu  cluster of two, 128-unit chunks          122 / 230 us without the hidden store, 165 / 319 us with it
+  //   this file    pair of tiles per CTA                    142 / 275 us                            155 / 299 us
   // The per-thread 32-byte stores of the hidden activations go through the same L1/shared-memory pipe as the SS operand
-  // reads that bound generation 3, so the student pass (hidden stored) stays on generation 1; CB_FFN_V forces one for tests.
-  const char* env = getenv("CB_FFN_V");
-  const int ver = (env && env[0] >= '1' && env[0] <= '3') ? env[0] - '0' : 0;
-  const int use = ver ? ver : (hid == nullptr ? 3 : 1);
+  // reads that bound the cluster kernel, so the student pass (hidden stored) stays on this one.  `kernel` = 1 | 3 forces one of
+  // them (A/B measurements, tests); 0 = this choice.
+  CB_CHECK(kernel == 0 || kernel == 1 || kernel == 3, "ffn_fwd: kernel must be 0 (auto), 1 or 3");
+  const int use = kernel ? kernel : (hid == nullptr ? 3 : 1);
   if (use == 3 && F % 128 == 0) return ffn_fwd3_run(y, w1, b1, w2, b2, resid, z2, hid, mask_bits, ld_bits, T, F, reinterpret_cast<cudaStream_t>(stream));
-  if (use == 2 || (use == 3 && ver)) return ffn_fwd2_run(y, w1, b1, w2, b2, resid, z2, hid, mask_bits, ld_bits, T, F, reinterpret_cast<cudaStream_t>(stream));
   static bool attr_set = false;
   if (!attr_set) {
     CB_CUDA(cudaFuncSetAttribute(ffn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM_BYTES));

@@ -1,6 +1,6 @@
 // Fused feed-forward block, third generation (same contract as ffn_fwd.cu: z2 = resid + relu(y W1^T + b1) W2^T + b2, D = 192).
 //
-// ffn_fwd2.cu (cluster of two CTAs, one row tile per CTA, multicast weight halves) showed that a tcgen05.mma with N = 64 costs
+// An earlier cluster kernel (two CTAs, one row tile per CTA, multicast weight halves, 64-unit chunks; removed) showed that a tcgen05.mma with N = 64 costs
 // ~53 clocks whatever its operands (gpurun_out/tl_ffn5.txt: 12 H MMAs = 640 clk, while the 4 Z MMAs with N = 192 take their
 // nominal 4 x 96) — the H products were paying a per-instruction floor.  Here the hidden dimension is walked in chunks of 128:
 //     H(c)  = y_t · W1[c]^T        12 SS MMAs, M = 128, N = 128, K = 16 (nominal 64 clk each)       -> TMEM (128 fp32 columns)
@@ -8,7 +8,7 @@
 //     Z    += P(c) · W2[:, c]^T     8 TS MMAs, N = 192
 // TMEM: H0 128 | H1 128 | Z 192 = 448 columns (y cannot also live in tensor memory: 96 more), so y_t comes from shared memory
 // (one TMA tile per item) and the two hidden buffers alternate: the tensor pipe runs Z(c), H(c+2) while the epilogue warps turn
-// H(c+1) into P(c+1).  A cluster of two CTAs shares every weight chunk exactly as in ffn_fwd2.cu (either CTA fetches half of
+// H(c+1) into P(c+1).  A cluster of two CTAs shares every weight chunk (either CTA fetches half of
 // W1[c] / W2[:, c] and multicasts it), so the L2 -> SM weight stream is one fetch per 256 rows.
 // Shared memory: y 48 KB | W1 ring 2 x 48 KB | W2 ring 3 x 24 KB (64-unit k-blocks) | b1 8 KB.
 #include "common.cuh"

@@ -31,11 +31,8 @@ struct GemmArgs {
 // C = op(A) op(B)^T with the epilogue in g.flags; see gemm.cu
 int gemm_run(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, GemmArgs g, cudaStream_t stream);
 
-// fused feed-forward, cluster-of-two kernel (ffn_fwd2.cu); same contract as cb_ffn_fwd with D = 192
-int ffn_fwd2_run(const void* y, const void* w1, const float* b1, const void* w2, const float* b2, const float* resid, float* z2, void* hid,
-                 unsigned int* mask_bits, int ld_bits, int T, int F, cudaStream_t stream);
-
-// third generation (ffn_fwd3.cu): 128-unit hidden chunks, y tile in shared memory; needs F % 128 == 0
+// fused feed-forward, cluster-of-two kernel (ffn_fwd3.cu): 128-unit hidden chunks, y tile in shared memory; same contract as
+// cb_ffn_fwd with D = 192; needs F % 128 == 0
 int ffn_fwd3_run(const void* y, const void* w1, const float* b1, const void* w2, const float* b2, const float* resid, float* z2, void* hid,
                  unsigned int* mask_bits, int ld_bits, int T, int F, cudaStream_t stream);
 

@@ -86,10 +86,10 @@ def ffn_fused_ok(D: int, F: int) -> bool:
 
 
 def ffn_fwd(y: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor, resid: torch.Tensor, *,
-            save_hidden: bool, save_mask_bits: Optional[bool] = None):
+            save_hidden: bool, save_mask_bits: Optional[bool] = None, kernel: int = 0):
     """z2 = resid + relu(y W1^T + b1) W2^T + b2 in one kernel (D = 192).  Returns (z2 fp32, hidden bf16 | None), or — when the
     ``save_mask_bits`` keyword is given at all — (z2, hidden | None, bits | None): the ReLU mask as bits, uint32 [F/32, ld]
-    (for gemm(..., flags=EPI_RELU_MASK | EPI_MASK_BITS))."""
+    (for gemm(..., flags=EPI_RELU_MASK | EPI_MASK_BITS)).  ``kernel``: 0 = the library's choice, 1 / 3 force one (tests, A/B)."""
     T, D = y.shape
     F = w1.shape[0]
     assert y.dtype == bf16 and w1.dtype == bf16 and w2.dtype == bf16 and resid.dtype == torch.float32
@@ -98,7 +98,7 @@ def ffn_fwd(y: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tenso
     hid = torch.empty(T, F, device=y.device, dtype=bf16) if save_hidden else None
     bits = torch.empty(F // 32, (T + 31) // 32 * 32, device=y.device, dtype=torch.int32) if save_mask_bits else None
     _call("cb_ffn_fwd", _p(y), _p(w1), _p(b1), _p(w2), _p(b2), _p(resid), _p(z2), _p(hid), _p(bits), bits.shape[1] if bits is not None else 0,
-          T, D, F, _stream(), work=4.0 * T * D * F, pkey="cb_ffn_fwd" if save_hidden else "cb_ffn_fwd:nostore",
+          T, D, F, int(kernel), _stream(), work=4.0 * T * D * F, pkey="cb_ffn_fwd" if save_hidden else "cb_ffn_fwd:nostore",
           nbytes=float(T) * (D * 2 + D * 8 + (F * 2 if save_hidden else 0) + (F / 8 if save_mask_bits else 0)) + 4.0 * D * F)
     return (z2, hid) if save_mask_bits is None else (z2, hid, bits)
 
@@ -294,11 +294,12 @@ def tokenize_bwd(dtokens: torch.Tensor, patches: torch.Tensor, lay: PackedLayout
           T, D, _p(dw_pe), _p(db_pe), _p(dpos_patch), _p(dpos0), _p(dcls_tok), _p(dchan_tok), ks, _stream())
 
 
-def attn_fwd(qkv: torch.Tensor, lay: PackedLayout, nheads: int, *, need_lse: bool = True, q_tile: int = 256) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+def attn_fwd(qkv: torch.Tensor, lay: PackedLayout, nheads: int, *, need_lse: bool = True) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     T, D3 = qkv.shape
     D = D3 // 3
     d = D // nheads
-    work = lay.attn_schedule(nheads, q_tile, "fwd") if q_tile == 256 else lay.attn_work(nheads, q_tile)
+    q_tile = 256                                             # work item = a pair of 128-row query tiles
+    work = lay.attn_schedule(nheads, q_tile, "fwd")
     out = torch.empty(T, D, device=qkv.device, dtype=bf16)
     lse = torch.empty(nheads, T, device=qkv.device, dtype=torch.float32) if need_lse else None
     _call("cb_attn_varlen_fwd", _p(qkv), _p(work), work.shape[0], q_tile, _p(out), _p(lse), T, D, nheads, float(d) ** -0.5, _stream(),

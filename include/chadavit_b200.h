@@ -123,9 +123,9 @@ int cb_small_matmul_f32(const float* A, const float* B, float* C, int M, int N, 
  * Packed varlen multi-head self-attention forward (nn.MultiheadAttention inside _sa_block, chada_vit.py:105-111).
  *   qkv bf16 [T, 3D] (= in_proj output: q | k | v, head h in columns h*d..(h+1)*d of each third)
  *   work int32 [n_work, 4] = {first query row (global), seq_start, seq_end, head}: one entry per q_tile query rows
- *        (q_tile = 256: two 128-row tiles per item, two softmax warpgroups, the production kernel; 128: one tile),
+ *        (q_tile must be 256: two 128-row tiles per item, one softmax warpgroup each),
  *        built on the host from list_num_channels (no device sync).  The persistent kernels give CTA c the entries c, c + G,
- *        c + 2G, ... (G = min(n_work, SM count)); the q_tile = 256 kernel and the backward skip EMPTY entries (seq_end <=
+ *        c + 2G, ... (G = min(n_work, SM count)); both kernels skip EMPTY entries (seq_end <=
  *        seq_start), so the host may pad the list to balance the CTAs (PackedLayout.attn_schedule: LPT assignment)
  *   out bf16 [T, D];  lse fp32 [H, T] (log-sum-exp of the scaled scores, natural log) or NULL
  */
@@ -148,9 +148,11 @@ int cb_attn_varlen_bwd(const void* dout, const void* qkv, const void* out, const
  * [F/32, ld_bits] (ld_bits >= T, a multiple of 32): bit j of mask_bits[w][t] <=> hid[t, 32 w + j] > 0 — what the backward
  * product d(hidden) = (dz2 W2) o (hidden > 0) reads through CB_EPI_MASK_BITS instead of the 16x larger hid.
  * D must be 192 (tensor-memory budget), F a multiple of 64; other shapes use two cb_gemm_bf16 calls.
+ * kernel: 0 = the library's choice (cluster-of-two kernel without the hidden store, pair-of-tiles kernel with it); 1 / 3 force
+ * the pair-of-tiles / the cluster kernel (A/B measurements and tests; 3 needs F % 128 == 0).
  */
 int cb_ffn_fwd(const void* y, const void* w1, const float* b1, const void* w2, const float* b2, const float* resid, float* z2,
-               void* hid, unsigned int* mask_bits, int ld_bits, int T, int D, int F, void* stream);
+               void* hid, unsigned int* mask_bits, int ld_bits, int T, int D, int F, int kernel, void* stream);
 
 /* ---------------- DINOHead pieces (src/methods/dino.py:61-111); the Linear layers themselves are cb_gemm_bf16 ---------------- */
 /* nn.GELU (exact erf): out bf16 = gelu(pre fp32);  backward: dpre bf16 = dact fp32 * gelu'(pre) */

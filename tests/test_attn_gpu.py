@@ -24,15 +24,14 @@ def _ref_attn(qkv, cu, H):
     return out, lse
 
 
-@pytest.mark.parametrize("q_tile", [256, 128])
 @pytest.mark.parametrize("D,H", [(192, 2), (32, 2), (192, 12), (768, 12), (64, 2), (256, 2)])
 @pytest.mark.parametrize("counts,npatch", [([1, 3, 10, 5], 196), ([2, 10, 1], 36), ([1], 4), ([7, 2, 2, 9, 1, 4], 196)])
-def test_attn_fwd(D, H, counts, npatch, q_tile):
+def test_attn_fwd(D, H, counts, npatch):
     from chadavit_b200 import ops
     lay = ops.PackedLayout(counts, npatch, "cuda")
     g = torch.Generator(device="cpu").manual_seed(D + H + npatch)
     qkv = (torch.randn(lay.T, 3 * D, generator=g) * 1.5).to(torch.bfloat16).cuda()
-    out, lse = ops.attn_fwd(qkv, lay, H, q_tile=q_tile)
+    out, lse = ops.attn_fwd(qkv, lay, H)
     ops.sync_check()
     ref, ref_lse = _ref_attn(qkv, lay.cu_host.tolist(), H)
     err = (out.float() - ref).abs().max().item()
