@@ -36,6 +36,8 @@ SIGNATURES = {
     "cb_attn_varlen_bwd": [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _f, _vp],
     "cb_gelu_fwd": [_vp, _vp, _l, _vp],
     "cb_gelu_bwd": [_vp, _vp, _vp, _l, _vp],
+    "cb_bn_gelu_fwd": [_vp, _vp, _vp, _vp, _vp, _f, _f, _i, _vp, _vp, _vp, _vp, _i, _i, _vp],
+    "cb_bn_gelu_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _vp],
     "cb_l2norm_fwd": [_vp, _vp, _vp, _i, _i, _f, _vp],
     "cb_l2norm_bwd": [_vp, _vp, _vp, _vp, _i, _i, _vp],
     "cb_weightnorm_fwd": [_vp, _vp, _vp, _vp, _i, _i, _vp],

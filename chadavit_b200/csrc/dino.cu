@@ -33,6 +33,82 @@ __global__ void gelu_bwd_kernel(const float* __restrict__ dact, const float* __r
                                                     pack_bf16(d.z * gelu_grad_f(v.z), d.w * gelu_grad_f(v.w)));
 }
 
+// nn.BatchNorm1d + nn.GELU of the projector (DINOHead(use_bn=True), src/methods/dino.py:66-73).  Block = 32 columns x 8 row
+// groups; R (= views x batch rows) is a few hundred, so two passes over the L2-resident column strip are cheaper than anything
+// clever.  Training mode: batch statistics (biased variance for the normalisation, unbiased for running_var, momentum as
+// torch: running = (1 - m) running + m batch); eval mode: running statistics.
+__device__ __forceinline__ float bn_block_sum(float v, float (*sh)[33]) {   // sum over the 8 row groups, result in every thread
+  sh[threadIdx.y][threadIdx.x] = v;
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s += sh[k][threadIdx.x];
+  __syncthreads();
+  return s;
+}
+__global__ void __launch_bounds__(256) bn_gelu_fwd_kernel(const float* __restrict__ pre, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          float* __restrict__ running_mean, float* __restrict__ running_var, float momentum,
+                                                          float eps, int training, float* __restrict__ bn_out, __nv_bfloat16* __restrict__ act,
+                                                          float* __restrict__ save_mean, float* __restrict__ save_invstd, int R, int C) {
+  __shared__ float sh[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const bool ok = c < C;
+  float mean, invstd;
+  if (training) {
+    float s = 0.f;
+    if (ok) for (int r = threadIdx.y; r < R; r += 8) s += pre[(long)r * C + c];
+    mean = bn_block_sum(s, sh) / R;
+    float q = 0.f;
+    if (ok) for (int r = threadIdx.y; r < R; r += 8) { const float d = pre[(long)r * C + c] - mean; q += d * d; }
+    const float var = bn_block_sum(q, sh) / R;
+    invstd = rsqrtf(var + eps);
+    if (ok && threadIdx.y == 0) {
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * var * (R > 1 ? (float)R / (R - 1) : 1.f);
+    }
+  } else {
+    mean = ok ? running_mean[c] : 0.f;
+    invstd = ok ? rsqrtf(running_var[c] + eps) : 0.f;
+  }
+  if (!ok) return;
+  if (threadIdx.y == 0 && save_mean) { save_mean[c] = mean; save_invstd[c] = invstd; }
+  const float g = gamma[c], b = beta[c];
+  for (int r = threadIdx.y; r < R; r += 8) {
+    const float y = (pre[(long)r * C + c] - mean) * invstd * g + b;
+    if (bn_out) bn_out[(long)r * C + c] = y;
+    act[(long)r * C + c] = __float2bfloat16(gelu_f(y));
+  }
+}
+// dpre (bf16) from dact = d loss / d gelu output; dgamma / dbeta accumulate (+=)
+__global__ void __launch_bounds__(256) bn_gelu_bwd_kernel(const float* __restrict__ dact, const float* __restrict__ bn_out, const float* __restrict__ pre,
+                                                          const float* __restrict__ gamma, const float* __restrict__ save_mean,
+                                                          const float* __restrict__ save_invstd, int training, __nv_bfloat16* __restrict__ dpre,
+                                                          float* __restrict__ dgamma, float* __restrict__ dbeta, int R, int C) {
+  __shared__ float sh[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const bool ok = c < C;
+  const float mean = ok ? save_mean[c] : 0.f, invstd = ok ? save_invstd[c] : 0.f, g = ok ? gamma[c] : 0.f;
+  float s1 = 0.f, s2 = 0.f;
+  if (ok)
+    for (int r = threadIdx.y; r < R; r += 8) {
+      const long i = (long)r * C + c;
+      const float d = dact[i] * gelu_grad_f(bn_out[i]);
+      s1 += d;
+      s2 += d * (pre[i] - mean) * invstd;
+    }
+  s1 = bn_block_sum(s1, sh);
+  s2 = bn_block_sum(s2, sh);
+  if (!ok) return;
+  if (threadIdx.y == 0) { dbeta[c] += s1; dgamma[c] += s2; }
+  const float m1 = training ? s1 / R : 0.f, m2 = training ? s2 / R : 0.f;
+  for (int r = threadIdx.y; r < R; r += 8) {
+    const long i = (long)r * C + c;
+    const float d = dact[i] * gelu_grad_f(bn_out[i]);
+    const float xh = (pre[i] - mean) * invstd;
+    dpre[i] = __float2bfloat16(g * invstd * (d - m1 - xh * m2));
+  }
+}
+
 // One warp per row.  fwd: out = x / max(||x||, eps) (bf16), inv[r] = 1/max(||x||, eps).
 __global__ void l2norm_fwd_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, float* __restrict__ inv, int rows, int C, float eps) {
   const int lane = threadIdx.x & 31, r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -252,6 +328,24 @@ extern "C" int cb_gelu_fwd(const float* pre, void* out, long n, void* stream) {
 extern "C" int cb_gelu_bwd(const float* dact, const float* pre, void* dpre, long n, void* stream) {
   CB_CHECK(n > 0 && n % 4 == 0, "gelu_bwd: n=%ld must be a positive multiple of 4", n);
   gelu_bwd_kernel<<<blocks4(n), 256, 0, STREAM>>>(dact, pre, BFM(dpre), n);
+  CB_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int cb_bn_gelu_fwd(const float* pre, const float* gamma, const float* beta, float* running_mean, float* running_var, float momentum,
+                              float eps, int training, float* bn_out, void* act, float* save_mean, float* save_invstd, int R, int C,
+                              void* stream) {
+  CB_CHECK(R > 0 && C > 0 && pre && gamma && beta && running_mean && running_var && act, "bn_gelu_fwd: R=%d C=%d or a NULL pointer", R, C);
+  bn_gelu_fwd_kernel<<<(C + 31) / 32, dim3(32, 8), 0, STREAM>>>(pre, gamma, beta, running_mean, running_var, momentum, eps, training, bn_out,
+                                                                 BFM(act), save_mean, save_invstd, R, C);
+  CB_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int cb_bn_gelu_bwd(const float* dact, const float* bn_out, const float* pre, const float* gamma, const float* save_mean,
+                              const float* save_invstd, int training, void* dpre, float* dgamma, float* dbeta, int R, int C, void* stream) {
+  CB_CHECK(R > 0 && C > 0 && dact && bn_out && pre && gamma && save_mean && save_invstd && dpre && dgamma && dbeta,
+           "bn_gelu_bwd: R=%d C=%d or a NULL pointer", R, C);
+  bn_gelu_bwd_kernel<<<(C + 31) / 32, dim3(32, 8), 0, STREAM>>>(dact, bn_out, pre, gamma, save_mean, save_invstd, training, BFM(dpre), dgamma,
+                                                                 dbeta, R, C);
   CB_CUDA(cudaGetLastError());
   return 0;
 }

@@ -28,7 +28,7 @@ from ..utils.momentum import MomentumUpdater, initialize_momentum_params
 
 
 class _HeadSaved:
-    __slots__ = ("ins", "pres", "z", "inv", "zn16", "wn16", "winv")
+    __slots__ = ("ins", "pres", "z", "inv", "zn16", "wn16", "winv", "bn")
 
 
 class _HeadFn(torch.autograd.Function):
@@ -56,18 +56,22 @@ class DINOHead(nn.Module):
     def __init__(self, in_dim: int, num_prototypes: int, use_bn: bool = True, norm_last_layer: bool = True, num_layers: int = 3,
                  hidden_dim: int = 2048, bottleneck_dim: int = 256):
         super().__init__()
-        if use_bn:
-            raise NotImplementedError("chadavit_b200.DINOHead: use_bn=True (BatchNorm1d in the projector) is not supported; the "
-                                      "reference's DINO config default is use_bn_in_head=False (src/methods/dino.py:207-209)")
         num_layers = max(num_layers, 1)
         if num_layers == 1:
             self.mlp = nn.Linear(in_dim, bottleneck_dim)
         else:
-            layers: List[Any] = [nn.Linear(in_dim, hidden_dim), nn.GELU()]
+            layers: List[Any] = [nn.Linear(in_dim, hidden_dim)]
+            if use_bn:
+                layers.append(nn.BatchNorm1d(hidden_dim))          # parameter / running-statistics container (dino.py:66-67)
+            layers.append(nn.GELU())
             for _ in range(num_layers - 2):
-                layers += [nn.Linear(hidden_dim, hidden_dim), nn.GELU()]
+                layers.append(nn.Linear(hidden_dim, hidden_dim))
+                if use_bn:
+                    layers.append(nn.BatchNorm1d(hidden_dim))
+                layers.append(nn.GELU())
             layers.append(nn.Linear(hidden_dim, bottleneck_dim))
             self.mlp = nn.Sequential(*layers)
+        self.use_bn = bool(use_bn) and num_layers > 1
         self.apply(self._init_weights)
         import warnings
         with warnings.catch_warnings():
@@ -97,6 +101,11 @@ class DINOHead(nn.Module):
             return ["mlp"]
         return [f"mlp.{i}" for i, l in enumerate(self.mlp) if isinstance(l, nn.Linear)]
 
+    def _bn_after(self, linear_name: str):
+        """The BatchNorm1d that follows a projector Linear (use_bn=True), with its arena parameter names."""
+        i = int(linear_name.split(".")[1]) + 1
+        return self.mlp[i], f"mlp.{i}.weight", f"mlp.{i}.bias"
+
     def _ready(self) -> ParamArena:
         a = self.arena
         a.ensure()
@@ -118,21 +127,29 @@ class DINOHead(nn.Module):
         a = self.arena
         names = self._linear_names()
         h16 = ops.cast_bf16(x.detach().contiguous().float())
-        ins, pres = [], []
+        ins, pres, bns = [], [], []
         pre = None
         for li, n in enumerate(names):
             pre = ops.gemm(h16, a.v16(n + ".weight"), bias=a.v32(n + ".bias"), flags=ops.EPI_OUT_F32)
             ins.append(h16)
             if li < len(names) - 1:
                 pres.append(pre)
-                h16 = ops.gelu_fwd(pre)
+                if self.use_bn:          # Linear -> BatchNorm1d -> GELU (dino.py:65-73); per-process batch statistics
+                    bn, wn, bname = self._bn_after(n)
+                    h16, bn_out, mean, invstd = ops.bn_gelu_fwd(pre, a.v32(wn), a.v32(bname), bn.running_mean, bn.running_var,
+                                                                bn.momentum, bn.eps, self.training, save)
+                    if self.training:
+                        bn.num_batches_tracked += 1
+                    bns.append((bn_out, mean, invstd, self.training))
+                else:
+                    h16 = ops.gelu_fwd(pre)
         zn16, inv = ops.l2norm_fwd(pre, 1e-12)
         wn16, winv = ops.weightnorm_fwd(a.v32("last_layer.weight_v"), a.v32("last_layer.weight_g").view(-1))
         logits = ops.gemm(zn16, wn16, flags=ops.EPI_OUT_F32)
         if not save:
             return logits, None
         s = _HeadSaved()
-        s.ins, s.pres, s.z, s.inv, s.zn16, s.wn16, s.winv = ins, pres, pre, inv, zn16, wn16, winv
+        s.ins, s.pres, s.z, s.inv, s.zn16, s.wn16, s.winv, s.bn = ins, pres, pre, inv, zn16, wn16, winv, bns
         return logits, s
 
     def _backward_impl(self, s: _HeadSaved, dlogits: torch.Tensor, gflat: torch.Tensor) -> torch.Tensor:
@@ -153,7 +170,11 @@ class DINOHead(nn.Module):
             ops.gemm(dcur, s.ins[li], a_mn=True, b_mn=True, flags=ops.EPI_ATOMIC, out=g(n + ".weight"))
             ops.colsum(dcur, g(n + ".bias"))
             dact = ops.gemm(dcur, a.v16(n + ".weight"), b_mn=True, flags=ops.EPI_OUT_F32)
-            if li > 0:
+            if li > 0 and self.use_bn:
+                _, wn, bname = self._bn_after(names[li - 1])
+                bn_out, mean, invstd, was_training = s.bn[li - 1]
+                dcur = ops.bn_gelu_bwd(dact, bn_out, s.pres[li - 1], a.v32(wn), mean, invstd, was_training, g(wn), g(bname))
+            elif li > 0:
                 dcur = ops.gelu_bwd(dact, s.pres[li - 1])
             else:
                 dx = dact

@@ -346,6 +346,26 @@ def gelu_bwd(dact: torch.Tensor, pre: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def bn_gelu_fwd(pre: torch.Tensor, gamma, beta, running_mean, running_var, momentum: float, eps: float, training: bool, save: bool):
+    """BatchNorm1d + GELU (DINOHead(use_bn=True)): returns (act bf16, bn_out fp32 | None, save_mean | None, save_invstd | None)."""
+    R, C = pre.shape
+    act = torch.empty(R, C, device=pre.device, dtype=bf16)
+    bn_out = torch.empty_like(pre) if save else None
+    mean = torch.empty(C, device=pre.device, dtype=torch.float32) if save else None
+    invstd = torch.empty(C, device=pre.device, dtype=torch.float32) if save else None
+    _call("cb_bn_gelu_fwd", _p(pre), _p(gamma), _p(beta), _p(running_mean), _p(running_var), float(momentum), float(eps), int(bool(training)),
+          _p(bn_out), _p(act), _p(mean), _p(invstd), R, C, _stream())
+    return act, bn_out, mean, invstd
+
+
+def bn_gelu_bwd(dact: torch.Tensor, bn_out, pre, gamma, mean, invstd, training: bool, dgamma, dbeta) -> torch.Tensor:
+    R, C = pre.shape
+    dpre = torch.empty(R, C, device=pre.device, dtype=bf16)
+    _call("cb_bn_gelu_bwd", _p(dact), _p(bn_out), _p(pre), _p(gamma), _p(mean), _p(invstd), int(bool(training)), _p(dpre), _p(dgamma), _p(dbeta),
+          R, C, _stream())
+    return dpre
+
+
 def l2norm_fwd(x: torch.Tensor, eps: float = 1e-12):
     rows, C = x.shape
     out = torch.empty(rows, C, device=x.device, dtype=bf16)

@@ -158,6 +158,15 @@ int cb_ffn_fwd(const void* y, const void* w1, const float* b1, const void* w2, c
 /* nn.GELU (exact erf): out bf16 = gelu(pre fp32);  backward: dpre bf16 = dact fp32 * gelu'(pre) */
 int cb_gelu_fwd(const float* pre, void* out, long n, void* stream);
 int cb_gelu_bwd(const float* dact, const float* pre, void* dpre, long n, void* stream);
+/* nn.BatchNorm1d + nn.GELU of the projector when the head is built with use_bn=True (the class default, src/methods/dino.py:40,
+ * 66-73): pre fp32 [R,C] (Linear output) -> bn_out fp32 [R,C] (normalised + affine, saved for the backward; may be NULL) and
+ * act bf16 [R,C] = gelu(bn_out).  training != 0: batch statistics, running_mean / running_var updated in place with `momentum`
+ * (unbiased variance, as torch), save_mean / save_invstd [C] written; training == 0: running statistics.  Backward: dpre bf16
+ * from dact fp32 = d loss / d act; dgamma / dbeta accumulate (+=).  Per-process statistics (no SyncBatchNorm). */
+int cb_bn_gelu_fwd(const float* pre, const float* gamma, const float* beta, float* running_mean, float* running_var, float momentum,
+                   float eps, int training, float* bn_out, void* act, float* save_mean, float* save_invstd, int R, int C, void* stream);
+int cb_bn_gelu_bwd(const float* dact, const float* bn_out, const float* pre, const float* gamma, const float* save_mean,
+                   const float* save_invstd, int training, void* dpre, float* dgamma, float* dbeta, int R, int C, void* stream);
 /* F.normalize(x, dim=-1, eps): out bf16 [rows,C], inv fp32 [rows] = 1/max(||x||,eps);  backward -> dx bf16 */
 int cb_l2norm_fwd(const float* x, void* out, float* inv, int rows, int C, float eps, void* stream);
 int cb_l2norm_bwd(const float* dy, const float* x, const float* inv, void* dx, int rows, int C, void* stream);

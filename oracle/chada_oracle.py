@@ -166,11 +166,31 @@ def backbone_forward(x: Tensor, index: int, list_num_channels: List[List[int]], 
 
 
 # --------------------------------------------------------------------------- DINO head / loss / EMA
-def dino_head(f: Tensor, P: Dict[str, Tensor]) -> Tensor:
-    """DINOHead.forward with use_bn=False, num_layers=3 (src/methods/dino.py:61-111)."""
-    h = F.gelu(f @ P["mlp.0.weight"].t() + P["mlp.0.bias"])
-    h = F.gelu(h @ P["mlp.2.weight"].t() + P["mlp.2.bias"])
-    h = h @ P["mlp.4.weight"].t() + P["mlp.4.bias"]
+def dino_head(f: Tensor, P: Dict[str, Tensor], bn_training: bool = True) -> Tensor:
+    """DINOHead.forward, num_layers=3 (src/methods/dino.py:61-111).  use_bn=False: mlp.{0,2,4} Linear; use_bn=True (detected
+    from the keys): mlp.{0,3,6} Linear with BatchNorm1d mlp.{1,4} between Linear and GELU — batch statistics when
+    ``bn_training`` (running statistics are updated in place in ``P`` as torch does), running statistics otherwise."""
+    use_bn = "mlp.6.weight" in P
+    lin = ("mlp.0", "mlp.3", "mlp.6") if use_bn else ("mlp.0", "mlp.2", "mlp.4")
+
+    def bn(h, pre):
+        if not use_bn:
+            return h
+        rm, rv = P[pre + ".running_mean"], P[pre + ".running_var"]
+        if bn_training:
+            mean, var = h.mean(0), h.var(0, unbiased=False)
+            with torch.no_grad():
+                n = h.shape[0]
+                rm.mul_(0.9).add_(0.1 * mean.detach())
+                rv.mul_(0.9).add_(0.1 * var.detach() * n / max(n - 1, 1))
+                if pre + ".num_batches_tracked" in P:
+                    P[pre + ".num_batches_tracked"] += 1
+        else:
+            mean, var = rm, rv
+        return (h - mean) / torch.sqrt(var + 1e-5) * P[pre + ".weight"] + P[pre + ".bias"]
+    h = F.gelu(bn(f @ P[lin[0] + ".weight"].t() + P[lin[0] + ".bias"], "mlp.1"))
+    h = F.gelu(bn(h @ P[lin[1] + ".weight"].t() + P[lin[1] + ".bias"], "mlp.4"))
+    h = h @ P[lin[2] + ".weight"].t() + P[lin[2] + ".bias"]
     h = h / h.norm(dim=-1, keepdim=True).clamp_min(1e-12)                                # F.normalize
     v, g = P["last_layer.weight_v"], P["last_layer.weight_g"]
     w = v * (g / v.norm(dim=1, keepdim=True))                                            # weight_norm, dim=0
@@ -268,13 +288,20 @@ def backbone_shapes(D: int, depth: int = 12, patch: int = 16, npatch: int = 196,
     return s
 
 
-def head_shapes(in_dim: int, K: int, hidden: int = 2048, bottleneck: int = 256) -> Dict[str, tuple]:
-    return {
-        "mlp.0.weight": (hidden, in_dim), "mlp.0.bias": (hidden,),
-        "mlp.2.weight": (hidden, hidden), "mlp.2.bias": (hidden,),
-        "mlp.4.weight": (bottleneck, hidden), "mlp.4.bias": (bottleneck,),
-        "last_layer.weight_g": (K, 1), "last_layer.weight_v": (K, bottleneck),
-    }
+def head_shapes(in_dim: int, K: int, hidden: int = 2048, bottleneck: int = 256, use_bn: bool = False) -> Dict[str, tuple]:
+    """state_dict shapes of DINOHead(in_dim, K, use_bn=use_bn) in registration order (buffers of BatchNorm1d included)."""
+    if not use_bn:
+        return {"mlp.0.weight": (hidden, in_dim), "mlp.0.bias": (hidden,), "mlp.2.weight": (hidden, hidden), "mlp.2.bias": (hidden,),
+                "mlp.4.weight": (bottleneck, hidden), "mlp.4.bias": (bottleneck,),
+                "last_layer.weight_g": (K, 1), "last_layer.weight_v": (K, bottleneck)}
+    d: Dict[str, tuple] = {}
+    for lin, bn, (o, i) in (("mlp.0", "mlp.1", (hidden, in_dim)), ("mlp.3", "mlp.4", (hidden, hidden))):
+        d[lin + ".weight"], d[lin + ".bias"] = (o, i), (o,)
+        d[bn + ".weight"], d[bn + ".bias"], d[bn + ".running_mean"], d[bn + ".running_var"] = (o,), (o,), (o,), (o,)
+        d[bn + ".num_batches_tracked"] = ()
+    d["mlp.6.weight"], d["mlp.6.bias"] = (bottleneck, hidden), (bottleneck,)
+    d["last_layer.weight_g"], d["last_layer.weight_v"] = (K, 1), (K, bottleneck)
+    return d
 
 
 def packed_index(counts: Sequence[int], npatch: int) -> Tuple[List[int], List[int]]:

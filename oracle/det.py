@@ -53,6 +53,14 @@ def param_scale(name: str, shape=()) -> tuple[float, float]:
         return 0.25, 1.0
     if "norm" in name and name.endswith("bias"):
         return 0.10, 0.0
+    if name.endswith("running_var"):
+        return 0.20, 1.0
+    if name.endswith("running_mean"):
+        return 0.10, 0.0
+    if name.endswith("num_batches_tracked"):
+        return 0.0, 0.0
+    if len(shape) == 1 and name.endswith("weight"):   # BatchNorm1d of DINOHead(use_bn=True)
+        return 0.25, 1.0
     if name.endswith("bias"):
         return 0.05, 0.0
     if name in ("cls_token", "channel_token", "pos_embed"):

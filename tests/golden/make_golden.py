@@ -108,6 +108,27 @@ def main():
                     out[f"head.{tag}.grad.{k}.abs"] = np.float64(p.grad.double().abs().sum().item())
                     out[f"head.{tag}.grad.{k}.sub"] = p.grad.reshape(-1)[::997].numpy().copy()
 
+        # the class default: use_bn=True (BatchNorm1d after the first two Linear layers), train mode, then one eval-mode forward
+        head = R.DINOHead(in_dim=32, num_prototypes=256)
+        head.train()
+        Ph = load_det(head, 12)
+        f = torch.from_numpy(det.det_uniform((12, 32), 22, 1.5)).requires_grad_()
+        z = head(f)
+        zo = O.dino_head(f.detach(), Ph, bn_training=True)
+        print(f"head bn: ref vs oracle {(z - zo).abs().max().item():.3e}")
+        out["head.bn.out"] = z.detach().numpy().copy()
+        wgt = torch.from_numpy(det.det_uniform(tuple(z.shape), 97, 1.0))
+        (z * wgt).sum().backward()
+        out["head.bn.grad_in"] = f.grad.numpy().copy()
+        for k, p in head.named_parameters():
+            if p.grad is not None:
+                out[f"head.bn.grad.{k}"] = p.grad.numpy().copy() if p.grad.numel() <= 4096 else p.grad.reshape(-1)[::97].numpy().copy()
+        for k, b in head.named_buffers():
+            out[f"head.bn.buf.{k}"] = b.detach().numpy().copy()
+        head.eval()
+        with torch.no_grad():
+            out["head.bn.out_eval"] = head(f.detach()).numpy().copy()
+
     # ---------------- DINO loss (+ center, + grad wrt student), V = 2 and V = 8, two consecutive calls
     for V in (2, 8):
         B, K = 5, 4096

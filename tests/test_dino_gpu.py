@@ -180,3 +180,37 @@ def test_multicrop_loss_variant_runs():
     l2 = model.fused_train_step((crops, None, [counts] * 4))
     torch.cuda.synchronize()
     assert torch.isfinite(l1) and torch.isfinite(l2) and l1.item() > 0
+
+
+def test_head_with_batchnorm_vs_reference():
+    """DINOHead() with the class default use_bn=True (src/methods/dino.py:36-84): BatchNorm1d + GELU kernel, train-mode forward /
+    backward, running statistics and the eval-mode forward against the reference module's golden outputs."""
+    from chadavit_b200.methods import DINOHead
+    head = DINOHead(32, 256)                       # the bare default constructor path
+    assert head.use_bn and [type(m).__name__ for m in head.mlp] == ["Linear", "BatchNorm1d", "GELU", "Linear", "BatchNorm1d", "GELU", "Linear"]
+    P = det_params(O.head_shapes(32, 256, use_bn=True), 12)
+    assert list(head.state_dict().keys()) == list(P.keys())
+    head.load_state_dict({k: (v.to(torch.int64) if k.endswith("num_batches_tracked") else v) for k, v in P.items()})
+    head = head.cuda().train()
+    f = torch.from_numpy(det.det_uniform((12, 32), 22, 1.5)).cuda().requires_grad_()
+    z = head(f)
+    ref = torch.from_numpy(G["head.bn.out"])
+    assert (z.detach().cpu() - ref).abs().max().item() < 2e-2 * ref.abs().max().item()
+    (z * torch.from_numpy(det.det_uniform(tuple(z.shape), 97, 1.0)).cuda()).sum().backward()
+    torch.cuda.synchronize()
+    assert rel_err(f.grad.cpu(), torch.from_numpy(G["head.bn.grad_in"])) < 5e-2
+    for k, p in head.named_parameters():
+        key = f"head.bn.grad.{k}"
+        if key not in G.files or p.grad is None:
+            continue
+        ref = torch.from_numpy(G[key])
+        got = p.grad.cpu() if p.grad.numel() <= 4096 else p.grad.cpu().reshape(-1)[::97]
+        assert rel_err(got.reshape(-1), ref.reshape(-1)) < 5e-2, (k, rel_err(got.reshape(-1), ref.reshape(-1)))
+    for k, b in head.named_buffers():
+        ref = torch.from_numpy(G[f"head.bn.buf.{k}"])
+        assert (b.detach().cpu().float() - ref.float()).abs().max().item() < 2e-3 * max(1.0, ref.float().abs().max().item()), k
+    head.eval()
+    with torch.no_grad():
+        ze = head(f.detach())
+    ref = torch.from_numpy(G["head.bn.out_eval"])
+    assert (ze.cpu() - ref).abs().max().item() < 2e-2 * ref.abs().max().item()

@@ -91,3 +91,28 @@ def test_dino_step_matches_reference():
             if key in G.files and v.grad is not None:
                 ref = float(G[key])
                 assert abs(v.grad.double().abs().sum().item() - ref) <= 2e-3 * max(ref, 1e-3), k
+
+
+def test_head_with_batchnorm_matches_reference():
+    """DINOHead(use_bn=True) — the class default (src/methods/dino.py:40,66-73): train-mode forward, input / parameter gradients,
+    running statistics after the call, then an eval-mode forward, all against the reference module's golden outputs."""
+    P = det_params(O.head_shapes(32, 256, use_bn=True), 12)
+    for k in P:
+        if k.endswith("num_batches_tracked"):
+            P[k] = P[k].to(torch.int64)
+        elif not ("running" in k or k.endswith("weight_g")):
+            P[k].requires_grad_()
+    f = torch.from_numpy(det.det_uniform((12, 32), 22, 1.5)).requires_grad_()
+    z = O.dino_head(f, P, bn_training=True)
+    assert (z.detach() - torch.from_numpy(G["head.bn.out"])).abs().max().item() < 1e-5
+    (z * torch.from_numpy(det.det_uniform(tuple(z.shape), 97, 1.0))).sum().backward()
+    assert (f.grad - torch.from_numpy(G["head.bn.grad_in"])).abs().max().item() < 1e-5
+    for k in ("mlp.1.weight", "mlp.1.bias", "mlp.4.weight", "mlp.6.bias"):
+        ref = torch.from_numpy(G[f"head.bn.grad.{k}"])
+        assert (P[k].grad - ref).abs().max().item() < 1e-4 * max(1.0, ref.abs().max().item()), k
+    for k in ("mlp.1.running_mean", "mlp.1.running_var", "mlp.4.running_var"):
+        assert (P[k] - torch.from_numpy(G[f"head.bn.buf.{k}"])).abs().max().item() < 1e-6, k
+    assert int(P["mlp.1.num_batches_tracked"]) == int(G["head.bn.buf.mlp.1.num_batches_tracked"]) == 1
+    with torch.no_grad():
+        ze = O.dino_head(f.detach(), P, bn_training=False)
+    assert (ze - torch.from_numpy(G["head.bn.out_eval"])).abs().max().item() < 1e-5
