@@ -44,16 +44,19 @@ def channel_counts(batch: int, seed: int = 1234):
     return np.random.RandomState(seed).randint(1, 11, size=batch).tolist()
 
 
+SHARD_WORLD = 8     # the job the per-rank work is taken from: 8 GPUs x 64 images, whatever N this run uses
+
+
 def step_counts(step: int, rank: int, world: int, balanced: bool = True):
-    """Channel counts of this rank's 64 images at `step`: the GLOBAL batch (64 x world images, same draw on every rank) is
-    dealt to the ranks token-balanced (default) or in contiguous slices (DistributedSampler-like)."""
+    """Channel counts of this rank's 64 images at `step`.  Weak scaling with IDENTICAL per-rank work at every N: each step
+    draws the global batch of the 8-GPU job (512 images, same draw on every rank), deals it to 8 shards — token-balanced
+    (chadavit_b200/data/balance.py, default) or contiguous (DistributedSampler-like) — and rank r runs shard r; a run on
+    N < 8 GPUs runs the first N shards of that job."""
     from chadavit_b200.data.balance import token_balanced_shards
-    glob = channel_counts(BATCH * world, seed=1234 + 7919 * step)
-    if world == 1:
-        return glob
+    glob = channel_counts(BATCH * SHARD_WORLD, seed=1234 + 7919 * step)
     if not balanced:
         return glob[rank * BATCH:(rank + 1) * BATCH]
-    return [glob[i] for i in token_balanced_shards(glob, world)[rank]]
+    return [glob[i] for i in token_balanced_shards(glob, SHARD_WORLD)[rank % SHARD_WORLD]]
 
 
 def make_pools(seed, device, pin=False):
@@ -721,7 +724,8 @@ def main():
                    "global_batch": imgs, "per_gpu_batch": BATCH,
                    "sum_channels_per_gpu_mean": float(np.mean([sum(c) for c in timed_counts])),
                    "tokens_per_gpu_global_crop_mean": float(np.mean(tok_g)), "tokens_per_gpu_global_crop_min_max": [int(min(tok_g)), int(max(tok_g))],
-                   "parallelism": f"dp{world}", "sharding": "contiguous" if args.unbalanced else "token-balanced (data/balance.py)",
+                   "parallelism": f"dp{world}", "sharding": ("contiguous" if args.unbalanced else "token-balanced (data/balance.py)") +
+                   f": rank r runs shard r of the {SHARD_WORLD}-GPU job's global batch at every N",
                    "rank_work_spread": spread, "cuda_graph": bool(args.fixed_batch),
                    "grad_allreduce": ("flat, after the backward" if args.no_overlap else
                                       f"bucketed ({model.grad_bucket_blocks} blocks per bucket) on a side stream under the backward") if world > 1 else None,

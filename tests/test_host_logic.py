@@ -154,17 +154,20 @@ def test_bench_sharding_is_token_balanced():
     c0, c1 = bench.channel_counts(64), bench.channel_counts(64)
     assert c0 == c1 and len(c0) == 64 and min(c0) >= 1 and max(c0) <= 10
     for world in (2, 4, 8):
-        worst_bal, worst_raw = 0.0, 0.0
-        for step in range(6):
+        for step in range(3):
             glob = bench.channel_counts(64 * world, seed=1234 + 7919 * step)
             shards = token_balanced_shards(glob, world)
             assert sorted(i for s in shards for i in s) == list(range(64 * world)) and all(len(s) == 64 for s in shards)
-            per_rank = [bench.step_counts(step, r, world) for r in range(world)]
-            assert sorted(c for cs in per_rank for c in cs) == sorted(glob)
-            load = np.array([sum(image_cost(c) for c in cs) for cs in per_rank])
-            raw = np.array([sum(image_cost(c) for c in bench.step_counts(step, r, world, balanced=False)) for r in range(world)])
-            worst_bal, worst_raw = max(worst_bal, load.max() / load.mean()), max(worst_raw, raw.max() / raw.mean())
-        assert worst_bal < 1.01 < worst_raw, (world, worst_bal, worst_raw)
+    worst_bal, worst_raw = 0.0, 0.0
+    for step in range(6):                       # bench.py: rank r runs shard r of the 8-GPU job's global batch, at every N
+        glob = bench.channel_counts(64 * bench.SHARD_WORLD, seed=1234 + 7919 * step)
+        per_rank = [bench.step_counts(step, r, 8) for r in range(8)]
+        assert sorted(c for cs in per_rank for c in cs) == sorted(glob)
+        assert bench.step_counts(step, 1, 2) == per_rank[1] and bench.step_counts(step, 0, 1) == per_rank[0]
+        load = np.array([sum(image_cost(c) for c in cs) for cs in per_rank])
+        raw = np.array([sum(image_cost(c) for c in bench.step_counts(step, r, 8, balanced=False)) for r in range(8)])
+        worst_bal, worst_raw = max(worst_bal, load.max() / load.mean()), max(worst_raw, raw.max() / raw.mean())
+    assert worst_bal < 1.01 < worst_raw, (worst_bal, worst_raw)
     with pytest.raises(ValueError):
         token_balanced_shards([1, 2, 3], 2)
 
