@@ -443,6 +443,7 @@ def main():
     ap.add_argument("--fixed-batch", action="store_true", help="headline = one batch replayed from a CUDA graph (round-1 behaviour)")
     ap.add_argument("--unbalanced", action="store_true", help="N > 1: contiguous shards instead of token-balanced ones")
     ap.add_argument("--no-overlap", action="store_true", help="N > 1: flat all-reduces after the backward instead of bucketed overlap")
+    ap.add_argument("--serial-forward", action="store_true", help="teacher / local-crop forwards on the compute stream instead of side streams")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -481,6 +482,8 @@ def main():
     cfg = dino_cfg(False, graph=False)
     if args.no_overlap:
         cfg["engine"]["overlap_comm"] = False
+    if args.serial_forward:
+        cfg["engine"]["overlap_forward"] = False
     model = DINO(cfg).to(dev)
     pools = make_pools(1234 + rank, dev)
     n_total = args.warmup + 3 * args.steps + 16

@@ -270,6 +270,10 @@ class DINO(nn.Module):
         # gradient all-reduce buckets of `grad_bucket_blocks` encoder blocks, launched on a side stream as the backward retires them
         self.grad_bucket_blocks = int(_cfg(cfg, "engine.grad_bucket_blocks", 3))
         self.overlap_comm = bool(_cfg(cfg, "engine.overlap_comm", True))
+        # teacher forward and the (discarded) student local-crop forward on side streams: independent kernel chains fill each
+        # other's launch gaps and tails (every kernel is one persistent wave)
+        self.overlap_forward = bool(_cfg(cfg, "engine.overlap_forward", True))
+        self._side: Optional[List[torch.cuda.Stream]] = None
         self._graphs: "collections.OrderedDict[tuple, dict]" = collections.OrderedDict()
         self._staging: Optional[dict] = None
         self._comm: Optional[torch.cuda.Stream] = None
@@ -477,21 +481,54 @@ class DINO(nn.Module):
             if len(crops) > 1 and all(c.shape[1:] == crops[0].shape[1:] for c in crops):
                 return [net._forward_impl(torch.cat(crops), [n for cs in counts for n in cs], save=save)]
             return [net._forward_impl(x, cs, save=save) for x, cs in zip(crops, counts)]
-        # student: large crops (saved for backward), small crops (reference: forward only, output discarded)
+        # Three independent kernel chains: student large crops (saved for backward), teacher large crops, student small crops
+        # (reference wiring: forward only, output discarded — base.py:701-707).  The last two run on side streams; the packed
+        # layouts and attention schedules they share are created (H2D copies) on the compute stream BEFORE the fork.
+        cur = torch.cuda.current_stream()
+        dev = gb.device
+        side = None
+        if self.overlap_forward:
+            if self._side is None or self._side[0].device != dev:
+                self._side = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+            side = self._side
+            for crops, counts in ((X[:nl], list_num_channels[:nl]), (X[nl:], list_num_channels[:len(X) - nl])):
+                if len(crops) == 0:
+                    continue
+                P = bb.token_learner.patch_size
+                same = len(crops) > 1 and all(c.shape[1:] == crops[0].shape[1:] for c in crops)
+                groups = [[n for cs in counts for n in cs]] if same else [list(cs) for cs in counts]
+                for x, cts in zip(crops if not same else crops[:1], groups):
+                    lay = ops.get_layout(cts, (x.shape[2] // P) * (x.shape[3] // P), dev)
+                    lay.attn_schedule(bb.num_heads, 256, "fwd")
+                    lay.attn_schedule(bb.num_heads, 128, "bwd")
+            for st in side:
+                st.wait_stream(cur)
+
+        def on_side(k, fn):
+            if side is None:
+                return fn()
+            with torch.cuda.stream(side[k]):
+                return fn()
+        # teacher: large crops only
+        def teacher():
+            tf = [f for f, _ in batched(tb, X[:nl], list_num_channels[:nl], False)]
+            return th._forward_impl(torch.cat(tf) if len(tf) > 1 else tf[0], save=False)[0]
+        tlogits = on_side(0, teacher)
         saved, feats = [], []
-        for f, s in batched(bb, X[:nl], list_num_channels[:nl], True):
-            saved.append(s)
+        local_on_side = len(X) > nl and not self.multicrop_loss
+        if local_on_side:                                 # base.py:701-707: the small crops index list_num_channels from 0 (Q12)
+            on_side(1, lambda: batched(bb, X[nl:], list_num_channels[:len(X) - nl], False))
+        for f, s_ in batched(bb, X[:nl], list_num_channels[:nl], True):
+            saved.append(s_)
             feats.append(f)
-        if len(X) > nl:                                   # base.py:701-707: the small crops index list_num_channels from 0 (Q12)
-            for f, s in batched(bb, X[nl:], list_num_channels[:len(X) - nl], self.multicrop_loss):
-                if self.multicrop_loss:
-                    saved.append(s)
-                    feats.append(f)
+        if len(X) > nl and self.multicrop_loss:
+            for f, s_ in batched(bb, X[nl:], list_num_channels[:len(X) - nl], True):
+                saved.append(s_)
+                feats.append(f)
         rows = [f.shape[0] for f in feats]
         logits, hs = hd._forward_impl(torch.cat(feats) if len(feats) > 1 else feats[0], save=True)
-        # teacher: large crops only
-        tfeats = [f for f, _ in batched(tb, X[:nl], list_num_channels[:nl], False)]
-        tlogits, _ = th._forward_impl(torch.cat(tfeats) if len(tfeats) > 1 else tfeats[0], save=False)
+        if side is not None:
+            cur.wait_stream(side[0])
         # loss + d(loss)/d(student logits) in one pass, then the centre update (old centre used by the loss, Q13)
         L = self.dino_loss_func
         temp = float(L.teacher_temp_schedule[L.epoch])
@@ -499,7 +536,6 @@ class DINO(nn.Module):
         # Collectives (C1 gradient mean, C2 centre) run on a side stream under the backward kernels: the centre sum right away,
         # the head arena once the head is differentiated, the backbone arena in buckets as the blocks retire.  The compute
         # stream joins the side stream once, in front of the optimizer.
-        cur = torch.cuda.current_stream()
         comm = self._comm_stream(gb.device) if (world > 1 and self.overlap_comm) else None
 
         def on_comm(fn):
@@ -527,6 +563,8 @@ class DINO(nn.Module):
             o += r
         if comm is not None:
             cur.wait_stream(comm)
+        if side is not None:
+            cur.wait_stream(side[1])        # the local-crop forward reads the student's bf16 weights the optimizer is about to rewrite
         # AdamW + teacher EMA + bf16 refresh of student and teacher, one launch per network
         for name, on, mo, g in (("backbone", bb, tb, gb), ("head", hd, th, gh)):
             st = self._opt_state(name, on.arena)

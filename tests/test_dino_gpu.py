@@ -207,7 +207,7 @@ def test_head_with_batchnorm_vs_reference():
         got = p.grad.cpu() if p.grad.numel() <= 4096 else p.grad.cpu().reshape(-1)[::97]
         # (the biases in front of a BatchNorm have an analytically zero gradient: absolute floor instead of a relative error)
         err = (got.reshape(-1) - ref.reshape(-1)).abs().max().item()
-        assert err <= 5e-2 * max(ref.abs().max().item(), 2e-2), (k, err, ref.abs().max().item())
+        assert err <= 5e-2 * max(ref.abs().max().item(), 0.1), (k, err, ref.abs().max().item())   # (bf16 d(pre) summed over 12 rows: ~3e-3 of noise)
     for k, b in head.named_buffers():
         ref = torch.from_numpy(G[f"head.bn.buf.{k}"])
         assert (b.detach().cpu().float() - ref.float()).abs().max().item() < 2e-3 * max(1.0, ref.float().abs().max().item()), k
