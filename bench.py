@@ -533,7 +533,11 @@ def main():
         model.use_cuda_graph = True
         sync()
     # ---- instrumented eager pass over the same kind of steps: CUDA-event duration of every launch of the big kernel classes
+    # The instrumented pass runs the step on ONE stream (teacher / local-crop forwards not on side streams): every kernel of
+    # this library is a persistent launch over all 148 SMs, so an event pair around a launch that shares the device with a
+    # side-stream kernel times the contention, not the kernel (class totals then add up to more than the step).
     keep_graph, model.use_cuda_graph = model.use_cuda_graph, False
+    keep_ovl, model.overlap_forward = model.overlap_forward, False
     classes = ["cb_attn_varlen_fwd", "cb_attn_varlen_bwd", "cb_gemm_bf16", "cb_ffn_fwd", "cb_ffn_fwd:nostore", "cb_ffn_bwd", "cb_layernorm_fwd",
                "cb_layernorm2_fwd", "cb_layernorm_bwd"]
     ops.PROFILE = {k: [0, 0.0, [], 0.0] for k in classes}
@@ -545,6 +549,7 @@ def main():
     sync()
     ms_eager = ev0.elapsed_time(ev1)
     model.use_cuda_graph = keep_graph
+    model.overlap_forward = keep_ovl
     prof = {}
     for name, (n, work, evs, nbytes) in ops.PROFILE.items():
         t = sum(a.elapsed_time(b) for a, b in evs)
@@ -701,7 +706,8 @@ def main():
                 "avg_launch_ms": tp["ms_total"] / max(1, tp["launches"]), "share_of_step": roof[top]["share_of_step"], "all": roof,
                 "hbm_note": "a one-directional HBM stream tops out near 3.9 TB/s (write) / 4.3 TB/s (read) on this part; only mixed "
                             "traffic reaches the 6.55 TB/s copy figure (tools/membw.py, profiles/r01_hw_probes.txt)",
-                "timing": "CUDA events around every launch of the class in an instrumented eager pass over the same kind of steps "
+                "timing": "CUDA events around every launch of the class in an instrumented eager pass over the same kind of steps, all "
+                          "launches on one stream (the timed steps run the teacher / local-crop forwards on side streams) "
                           f"({ms_eager / args.steps:.1f} ms/step instrumented vs {ms / args.steps:.1f} ms/step timed)"}
 
     cpu = None
