@@ -15,7 +15,8 @@ struct GemmArgs {
   int flags;
   float alpha;
   int direct;             // set by gemm_run: C / aux are 32-byte aligned with 32-byte row pitches -> row-direct epilogue allowed
-  float* colsum;          // optional fp32 [N]: += column sums of the stored C (EM_BF16_MASK only: bias gradient of linear1)
+  float* colsum;          // optional fp32, accumulated.  EM_BF16_MASK: [N] column sums of the stored C (bias gradient of linear1);
+                          // EM_ATOMIC (dW = dY^T X): [M] sums of op(A) over K, formed on the tensor pipe (bias gradient next to dW)
   // tokenizer epilogue (CB_EPI_TOKENIZE): A rows are already in packed token order (CLS rows hold zeros);
   // row t of sequence b (cu[b] <= t < cu[b+1]): off = t - cu[b]; off == 0 -> CLS row = cls_row, else
   // c = (off-1)/npatch, p = (off-1)%npatch: acc + bias + pos[p] + chan_tok[c]        (chada_vit.py:245-265)

@@ -9,6 +9,7 @@ from typing import List, Optional, Sequence, Tuple
 
 import collections
 import math
+import os
 
 import numpy as np
 import torch
@@ -79,6 +80,15 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
           nbytes=2.0 * (M * K + N * K) + float(M) * N * out.element_size() +
           (0.0 if aux is None else float(M) * N / 8 if flags & EPI_MASK_BITS else float(M) * N * aux.element_size()))
     return out
+
+
+_GEMM_ROWSUM = os.environ.get("CB_NO_GEMM_ROWSUM", "") != "1"   # A/B switch (read once): bias gradients on the tensor pipe of the dW products
+
+
+def gemm_rowsum_ok(N: int) -> bool:
+    """True when a weight-gradient product gemm(dY, X, a_mn=True, b_mn=True, flags=EPI_ATOMIC) with X of width N can also
+    deliver the bias gradient dY.sum(0) through ``colsum`` (the 192-wide column tile has the spare accumulator columns)."""
+    return _GEMM_ROWSUM and N % 192 == 0 and N % 256 != 0
 
 
 def ffn_fused_ok(D: int, F: int) -> bool:

@@ -61,8 +61,11 @@ int cb_attn_schedule(const int* cu_host, int B, int nheads, int tile, int mode, 
  * row-major (lda).  Same for B / b_mn with [N,K] vs [K,N].  Replaces every nn.Linear / F.linear on the path
  * (MHA in/out projection chada_vit.py:106, linear1/linear2 :115, DINOHead.mlp / last_layer dino.py:65-81) and
  * their autograd backward products.  N, lda, ldb multiples of 8; MN-major dims multiples of 32.
- * colsum (optional, only with CB_EPI_RELU_MASK): fp32 [N] += column sums of the stored C, i.e. the bias gradient of
- * linear1 fused into the product that makes d(hidden).
+ * colsum (optional, accumulated): with CB_EPI_RELU_MASK fp32 [N] += column sums of the stored C; with CB_EPI_ATOMIC (the
+ * weight-gradient product dW = dY^T X: a_mn = b_mn = 1, N a multiple of 192 but not of 256, M and N multiples of 64)
+ * fp32 [M] += sum over K of op(A)[m,k], i.e. the bias gradient that belongs to dW (torch.autograd of F.linear:
+ * grad_bias = grad_output.sum(0)), formed by the same tensor-core instructions as the tile (one extra block of ones behind
+ * the B operand).
  */
 int cb_gemm_bf16(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* C, int ldc, int M, int N,
                  int K, const float* bias, const void* aux, int ld_aux, int flags, float alpha, int k_splits,

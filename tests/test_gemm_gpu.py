@@ -92,6 +92,27 @@ def test_gemm_weight_grad_splitk():
     assert err <= 2e-3 * ref.abs().max().item()
 
 
+@pytest.mark.parametrize("T,out_f,splits", [(5000, 2048, 0), (4999, 576, 0), (68664, 2048, 0), (300, 576, 1), (130, 64, 3)])
+def test_gemm_weight_grad_with_bias_grad(T, out_f, splits):
+    """The weight-gradient product also delivers the bias gradient dY.sum(0) (F.linear's autograd: grad_bias = grad_output.sum(0))
+    through `colsum`: sums of the A operand over K, formed on the tensor pipe next to the tile.  Both outputs accumulate."""
+    from chadavit_b200 import ops
+    in_f = 192
+    assert ops.gemm_rowsum_ok(in_f)
+    dY, X = _rand((T, out_f), 18, 0.1), _rand((T, in_f), 19)
+    dW = torch.full((out_f, in_f), 0.5, device="cuda")
+    db = torch.full((out_f,), -2.0, device="cuda")
+    ops.gemm(dY, X, a_mn=True, b_mn=True, flags=ops.EPI_ATOMIC, out=dW, k_splits=splits or ops.splitk_for(T, (out_f + 127) // 128 * 2), colsum=db)
+    ops.sync_check()
+    ref_w = dY.float().t() @ X.float()
+    ref_b = dY.double().sum(0)
+    err_w = (dW - 0.5 - ref_w).abs().max().item()
+    err_b = (db.double() + 2.0 - ref_b).abs().max().item()
+    print(f"dW + db T={T} out={out_f}: dW err {err_w:.3e} (max {ref_w.abs().max().item():.2f}), db err {err_b:.3e} (max {ref_b.abs().max().item():.2f})")
+    assert err_w <= 2e-3 * max(1.0, ref_w.abs().max().item())
+    assert err_b <= 1e-3 * max(1.0, ref_b.abs().max().item())   # fp32 sums of bf16 values: only the summation order differs
+
+
 @pytest.mark.parametrize("T,F", [(1000, 2048), (128, 64), (129, 128), (257, 2048), (40000, 2048), (128 * 148 * 2 + 5, 512)])
 @pytest.mark.parametrize("save_hidden", [True, False])
 @pytest.mark.parametrize("gen", [0, 1, 3])

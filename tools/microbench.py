@@ -79,6 +79,28 @@ def dh_section(dev, T):
                2.0 * TT * D * F, TT * (D * 2 + F * 2 + F / 8))
 
 
+def dw_section(dev, T):
+    """Bias gradients next to the weight gradients: d(hidden) with / without the column sums in its epilogue, the dW1 / dWin
+    split-K products with / without the tensor-pipe sums of their A operand, and the separate column-sum pass they replace."""
+    D, F = 192, 2048
+    r = lambda *s: (torch.randn(*s, device=dev) * 0.5).to(bf16)  # noqa: E731
+    for TT in (T, 2 * T):
+        dz, w2, y, dh, dqkv = r(TT, D), r(D, F), r(TT, D), r(TT, F), r(TT, 3 * D)
+        bits = torch.randint(-2 ** 31, 2 ** 31 - 1, (F // 32, (TT + 31) // 32 * 32), device=dev, dtype=torch.int32)
+        o, cs = torch.empty(TT, F, device=dev, dtype=bf16), torch.zeros(F, device=dev)
+        M = ops.EPI_RELU_MASK | ops.EPI_MASK_BITS
+        report(f"dh T={TT} bits, colsum in the epilogue", timeit(lambda: ops.gemm(dz, w2, b_mn=True, aux=bits, flags=M, out=o, colsum=cs)), 2.0 * TT * D * F, TT * (D * 2 + F * 2 + F / 8))
+        report(f"dh T={TT} bits, no colsum", timeit(lambda: ops.gemm(dz, w2, b_mn=True, aux=bits, flags=M, out=o)), 2.0 * TT * D * F, TT * (D * 2 + F * 2 + F / 8))
+        g1, gq, cq = torch.zeros(F, D, device=dev), torch.zeros(3 * D, D, device=dev), torch.zeros(3 * D, device=dev)
+        k1, kq = ops.splitk_for(TT, 16 * 2), ops.splitk_for(TT, 5 * 2)
+        A = ops.EPI_ATOMIC
+        report(f"dW1 T={TT} split-K {k1}", timeit(lambda: ops.gemm(dh, y, a_mn=True, b_mn=True, flags=A, out=g1, k_splits=k1)), 2.0 * TT * D * F, TT * (D + F) * 2)
+        report(f"dW1 T={TT} split-K {k1} + db1 (N = 208)", timeit(lambda: ops.gemm(dh, y, a_mn=True, b_mn=True, flags=A, out=g1, k_splits=k1, colsum=cs)), 2.0 * TT * D * F, TT * (D + F) * 2)
+        report(f"dWin T={TT} split-K {kq}", timeit(lambda: ops.gemm(dqkv, y, a_mn=True, b_mn=True, flags=A, out=gq, k_splits=kq)), 2.0 * TT * D * 3 * D, TT * 4 * D * 2)
+        report(f"dWin T={TT} split-K {kq} + db_in (N = 208)", timeit(lambda: ops.gemm(dqkv, y, a_mn=True, b_mn=True, flags=A, out=gq, k_splits=kq, colsum=cq)), 2.0 * TT * D * 3 * D, TT * 4 * D * 2)
+        report(f"colsum bf16 [T={TT},576] (replaced)", timeit(lambda: ops.colsum(dqkv, cq)), 0, TT * 3 * D * 2)
+
+
 def attn_section(dev):
     """Attention forward / backward alone: the bench's ragged global-crop batch, 32 uniform 1961-token sequences, and the
     base/16 stress shape (D = 768, 12 heads of 64)."""
@@ -104,6 +126,8 @@ def main():
         return ffn_section("cuda", a.tokens)
     if a.only == "dh":
         return dh_section("cuda", a.tokens)
+    if a.only == "dw":
+        return dw_section("cuda", a.tokens)
     if a.only == "attn":
         return attn_section("cuda")
     T, D, F = a.tokens, 192, 2048
