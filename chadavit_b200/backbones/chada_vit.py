@@ -331,11 +331,16 @@ class ChAdaViT(nn.Module):
         # bias gradients db = dY.sum(0) ride on the weight-gradient products dW = dY^T X where the kernel supports it
         # (ops.gemm_rowsum_ok: tensor-pipe sums of the A operand); otherwise the d(hidden) epilogue / a column-sum pass form them
         cs = ops.gemm_rowsum_ok(D)
-        dh = ops.gemm(dz2h, a.v16(pre + "linear2.weight"), b_mn=True, aux=hid if bits is None else bits,
-                      flags=ops.EPI_RELU_MASK | (0 if bits is None else ops.EPI_MASK_BITS), colsum=None if cs else g("linear1.bias"))
+        fused = bits is not None and cs and ops.ffn_bwd_fused_ok(D, FFN_DIM)
+        if fused:   # d(hidden) and dy in one kernel: d(hidden) is written once (for dW1) and not read back for dy
+            dy, dh = ops.ffn_bwd(dz2h, a.v16(pre + "linear2.weight"), a.v16(pre + "linear1.weight"), bits, dz2)
+        else:
+            dh = ops.gemm(dz2h, a.v16(pre + "linear2.weight"), b_mn=True, aux=hid if bits is None else bits,
+                          flags=ops.EPI_RELU_MASK | (0 if bits is None else ops.EPI_MASK_BITS), colsum=None if cs else g("linear1.bias"))
         ops.gemm(dh, y, a_mn=True, b_mn=True, flags=A, out=g("linear1.weight"), k_splits=sk(mt(FFN_DIM) * mt(D)),
                  colsum=g("linear1.bias") if cs else None)
-        dy = ops.gemm(dh, a.v16(pre + "linear1.weight"), b_mn=True, aux=dz2, flags=ops.EPI_RESIDUAL_F32 | ops.EPI_OUT_F32)
+        if not fused:
+            dy = ops.gemm(dh, a.v16(pre + "linear1.weight"), b_mn=True, aux=dz2, flags=ops.EPI_RESIDUAL_F32 | ops.EPI_OUT_F32)
         # y = LN1(z1), z1 = x + att Wo^T + bo      (second use of norm1: gradients accumulate)
         dz1, dz1h = ops.layernorm_bwd(dy, z1, a.v32(pre + "norm1.weight"), m1b, r1b, dgamma=g("norm1.weight"), dbeta=g("norm1.bias"),
                                       dcolsum=g("self_attn.out_proj.bias"), want_bf16=True)

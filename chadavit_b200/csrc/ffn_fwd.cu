@@ -14,6 +14,14 @@
 // SM) would exceed what L2 delivers.  Warps 0-3 / 4-7: bias + ReLU (+ hidden store) and final epilogue of tile A / B;
 // warp 8: MMA issuer (convergent warp, elected lane) serving A, B, A, B ...; warp 9: TMA.  While the epilogue warps turn
 // H_A(c) into P_A(c), the tensor pipe runs Z_B += P_B(c) W2 and H_B(c+1), and vice versa.
+//
+// BWD = true is the backward of the same block through the hidden layer (autograd of chada_vit.py:113-116), the same pipeline
+// with the roles of the weights exchanged and the ReLU replaced by its mask:
+//     DH_t(c) = dz2_t · W2[:, c]           SS MMA, B = W2 [D, F] read MN-major ([K, N] row-major), N = 64, K = D
+//     P_t(c)  = bf16(DH_t(c)) where hidden > 0   (1 bit per unit, written by the forward), stored as d(hidden) for dW1 = dh^T y
+//     DY_t   += P_t(c) · W1[c, :]          TS MMA, B = W1 [F, D] read MN-major, N = D, K = 64
+//     dy      = DY + dz2 (fp32: the residual branch of chada_vit.py:100)
+// i.e. cb_gemm_bf16(dz2, W2, relu-mask) + cb_gemm_bf16(dh, W1, +residual) without reading the [T, F] d(hidden) back.
 #include "common.cuh"
 #include "chadavit_b200.h"
 #include "internal.h"
@@ -38,19 +46,26 @@ constexpr int FF_SMEM_BYTES = 2 * FF_Y_BYTES + FF_S1 * FF_W1_BYTES + FF_S2 * FF_
 constexpr int FF_COL_Z = 128;      // H_t at 64 t, Z_t at 128 + 192 t
 
 struct FfnArgs {
-  const float* b1;     // [F]
-  const float* b2;     // [D]
-  const float* resid;  // [T, D] fp32 (norm1 output, the residual of chada_vit.py:100)
-  float* z2;           // [T, D] fp32
-  __nv_bfloat16* hid;  // [T, F] bf16 or null
-  uint32_t* mask_bits; // [F/32, ld_bits] ReLU mask as bits, or null
+  const float* b1;     // [F]                                                                 (BWD: unused)
+  const float* b2;     // [D]                                                                 (BWD: unused)
+  const float* resid;  // [T, D] fp32 (norm1 output, the residual of chada_vit.py:100)        (BWD: dz2 fp32)
+  float* z2;           // [T, D] fp32                                                         (BWD: dy)
+  __nv_bfloat16* hid;  // [T, F] bf16 or null                                                 (BWD: d(hidden), always stored)
+  uint32_t* mask_bits; // [F/32, ld_bits] ReLU mask as bits, or null                          (BWD: read)
   int ld_bits;
   int T, F;
 };
 
+__device__ __forceinline__ uint32_t ldg_u32_pinned(const uint32_t* p) {   // stays where it is written (see ldg_f32_pinned)
+  uint32_t v;
+  asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
+template <bool BWD>
 __global__ void __launch_bounds__(320, 1)
-ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
-               const FfnArgs a) {
+ffn_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
+           const FfnArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
   uint8_t* sY = smem;                                   // [2] row tiles
@@ -84,7 +99,7 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
     for (int i = 0; i < FF_S2; ++i) { mbar_init(&w2_full[i], 1); mbar_init(&w2_empty[i], 1); }
     fence_barrier_init();
   }
-  for (int i = threadIdx.x; i < a.F; i += blockDim.x) sB1[i] = __ldg(a.b1 + i);
+  if (!BWD) for (int i = threadIdx.x; i < a.F; i += blockDim.x) sB1[i] = __ldg(a.b1 + i);
   if (warp == W_MMA) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
@@ -108,11 +123,15 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
           mbar_wait(&w1_empty[s1], p1 ^ 1);
           mbar_expect_tx(&w1_full[s1], FF_W1_BYTES);
 #pragma unroll
-          for (int kb = 0; kb < FF_KB; ++kb) tma_load_2d(sW1 + s1 * FF_W1_BYTES + kb * (FF_C * 128), &tmW1, &w1_full[s1], kb * 64, c * FF_C);
+          for (int kb = 0; kb < FF_KB; ++kb) {
+            if (!BWD) tma_load_2d(sW1 + s1 * FF_W1_BYTES + kb * (FF_C * 128), &tmW1, &w1_full[s1], kb * 64, c * FF_C);
+            else tma_load_3d(sW1 + s1 * FF_W1_BYTES + kb * (FF_C * 128), &tmW1, &w1_full[s1], 0, kb * 64, c);   // W2 rows kb*64.., unit block c
+          }
           if (++s1 == FF_S1) { s1 = 0; p1 ^= 1; }
           mbar_wait(&w2_empty[s2], p2 ^ 1);
           mbar_expect_tx(&w2_full[s2], FF_W2_BYTES);
-          tma_load_2d(sW2 + s2 * FF_W2_BYTES, &tmW2, &w2_full[s2], c * FF_C, 0);
+          if (!BWD) tma_load_2d(sW2 + s2 * FF_W2_BYTES, &tmW2, &w2_full[s2], c * FF_C, 0);
+          else tma_load_3d(sW2 + s2 * FF_W2_BYTES, &tmW2, &w2_full[s2], 0, c * FF_C, 0);   // W1 rows (units) c*64.., all FF_KB column blocks
           if (++s2 == FF_S2) { s2 = 0; p2 ^= 1; }
         }
       }
@@ -122,10 +141,13 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
     // ONE issuing warp serving both tiles in strict A, B, A, B order: the groups are large here (16 MMAs = 960 clk), so the
     // ~160 clk per group on the issuing warp is amortised, and exclusive back-to-back groups keep the ping-pong tight (with
     // one issuer per tile the two streams interleaved MMA by MMA and every group took twice as long to retire).
-    constexpr uint32_t idesc_h = umma_idesc_bf16(128, FF_C, false, false);
-    constexpr uint32_t idesc_z = umma_idesc_bf16(128, FF_D, false, false);
+    constexpr uint32_t idesc_h = umma_idesc_bf16(128, FF_C, false, BWD);
+    constexpr uint32_t idesc_z = umma_idesc_bf16(128, FF_D, false, BWD);
     const uint64_t y_desc0 = umma_smem_desc(smem_u32(sY), 16, 1024, 3);
-    const uint64_t w1_desc0 = umma_smem_desc(smem_u32(sW1), 16, 1024, 3), w2_desc0 = umma_smem_desc(smem_u32(sW2), 16, 1024, 3);
+    // forward: both weight chunks K-major (rows of 64 k-elements, 32 bytes per K = 16 step).  Backward: MN-major blocks of
+    // [64 k-rows x 64 n-elements] (8 KB, LBO = distance between n-blocks), 2048 bytes per K = 16 step (gemm.cu, operand mode 1).
+    constexpr uint32_t W_LBO = BWD ? 64 * 128 : 16, W_KSTEP = BWD ? 2048 : 32;
+    const uint64_t w1_desc0 = umma_smem_desc(smem_u32(sW1), W_LBO, 1024, 3), w2_desc0 = umma_smem_desc(smem_u32(sW2), W_LBO, 1024, 3);
     int s1 = 0, s2 = 0; uint32_t p1 = 0, p2 = 0, ni = 0, nib = 0, np = 0, npb = 0;   // rings; items / p_full uses of tile A, tile B
     CB_TL_DECL(tl);
     auto mma_h = [&](int t, int slot) {                // H_t = y_t · W1[c]^T ; caller is the elected lane
@@ -134,7 +156,7 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
       for (int kb = 0; kb < FF_KB; ++kb)
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_ss(tmem_base + t * FF_C, umma_desc_add(yd, kb * (128 * 128) + k * 32), umma_desc_add(wd, kb * (FF_C * 128) + k * 32), idesc_h, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_ss(tmem_base + t * FF_C, umma_desc_add(yd, kb * (128 * 128) + k * 32), umma_desc_add(wd, kb * (FF_C * 128) + k * W_KSTEP), idesc_h, (kb > 0 || k > 0) ? 1u : 0u);
       tc_commit(&h_full[t]);
     };
     for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++ni) {
@@ -166,7 +188,7 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
             const uint64_t w2d = umma_desc_add(w2_desc0, s2 * FF_W2_BYTES);
 #pragma unroll
             for (int kk = 0; kk < FF_C / 16; ++kk)     // Z_t += P_t(c) · W2[:, c]^T
-              umma_ts(tmem_base + FF_COL_Z + t * FF_D, tmem_base + t * FF_C + kk * 8, umma_desc_add(w2d, kk * 32), idesc_z, (c > 0 || kk > 0) ? 1u : 0u);
+              umma_ts(tmem_base + FF_COL_Z + t * FF_D, tmem_base + t * FF_C + kk * 8, umma_desc_add(w2d, kk * W_KSTEP), idesc_z, (c > 0 || kk > 0) ? 1u : 0u);
             if (more) mma_h(t, s1);                    // H_t(c+1) over P_t(c): the in-order pipe has retired its reader by then
             else { tc_commit(&y_empty[t]); tc_commit(&z_full[t]); }
           }
@@ -200,6 +222,8 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
           const long row = (long)(2 * it + t) * 128 + r_in_tile;
           const uint32_t h_addr = lane_addr + t * FF_C + hf * 32;
           if (tl_on) CB_TL(1 + hf, tl, 1 + 4 * t);
+          uint32_t mw = 0u;   // BWD: ReLU mask of this thread's 32 units, requested before the accumulator wait (a warp = one 128-byte line)
+          if (BWD && row < a.T) mw = ldg_u32_pinned(a.mask_bits + (long)(2 * c + hf) * a.ld_bits + row);
           mbar_wait(&h_full[t], (t ? nh1 : nh0) & 1);
           if (t) ++nh1; else ++nh0;
           tc_fence_after();
@@ -208,12 +232,21 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
           tmem_ld32(h_addr, r0);
           tmem_ld_wait();
           uint32_t pk[16];
-          const float* bp = sB1 + c * FF_C + hf * 32;    // bias of this half chunk: broadcast 16-byte smem loads
+          if (!BWD) {
+            const float* bp = sB1 + c * FF_C + hf * 32;    // bias of this half chunk: broadcast 16-byte smem loads
 #pragma unroll
-          for (int e = 0; e < 32; e += 4) {
-            const float4 ba = *reinterpret_cast<const float4*>(bp + e);
-            pk[e >> 1] = pack_bf16(fmaxf(__uint_as_float(r0[e]) + ba.x, 0.f), fmaxf(__uint_as_float(r0[e + 1]) + ba.y, 0.f));
-            pk[(e >> 1) + 1] = pack_bf16(fmaxf(__uint_as_float(r0[e + 2]) + ba.z, 0.f), fmaxf(__uint_as_float(r0[e + 3]) + ba.w, 0.f));
+            for (int e = 0; e < 32; e += 4) {
+              const float4 ba = *reinterpret_cast<const float4*>(bp + e);
+              pk[e >> 1] = pack_bf16(fmaxf(__uint_as_float(r0[e]) + ba.x, 0.f), fmaxf(__uint_as_float(r0[e + 1]) + ba.y, 0.f));
+              pk[(e >> 1) + 1] = pack_bf16(fmaxf(__uint_as_float(r0[e + 2]) + ba.z, 0.f), fmaxf(__uint_as_float(r0[e + 3]) + ba.w, 0.f));
+            }
+          } else {   // d(hidden) = (dz2 . W2) where hidden > 0: bit 2e / 2e+1 of the mask word <=> low / high bf16 of pk[e] (relu_bits16)
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const uint32_t b2 = mw >> (2 * e);
+              const uint32_t sel = ((b2 & 1u) ? 0xffffu : 0u) | ((b2 & 2u) ? 0xffff0000u : 0u);
+              pk[e] = pack_bf16(__uint_as_float(r0[2 * e]), __uint_as_float(r0[2 * e + 1])) & sel;
+            }
           }
           // P (bf16): hidden units 32 hf .. 32 hf + 31 of the chunk -> TMEM columns 16 hf .. 16 hf + 15 of H_t.  Half 1 writes
           // columns 16..31, which belong to half 0's fp32 input range: wait until half 0 has read its columns (it arrives on
@@ -230,7 +263,7 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
             stg256(dst, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
             stg256(dst + 16, pk[8], pk[9], pk[10], pk[11], pk[12], pk[13], pk[14], pk[15]);
           }
-          if (a.mask_bits && row < a.T) a.mask_bits[(long)(2 * c + hf) * a.ld_bits + row] = relu_bits16(pk);   // a warp = 32 consecutive rows: one line
+          if (!BWD && a.mask_bits && row < a.T) a.mask_bits[(long)(2 * c + hf) * a.ld_bits + row] = relu_bits16(pk);   // a warp = 32 consecutive rows: one line
         }
       }
       // ---- final epilogue: z2 = Z + b2 + resid (fp32); this warp's half: 32-column slabs hf, hf + 2, hf + 4 (128 contiguous bytes each)
@@ -257,7 +290,8 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
             float* dst = a.z2 + row * FF_D + s * 32;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.b2 + s * 32 + 8 * k)), b1 = __ldg(reinterpret_cast<const float4*>(a.b2 + s * 32 + 8 * k + 4));
+              float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+              if (!BWD) { b0 = __ldg(reinterpret_cast<const float4*>(a.b2 + s * 32 + 8 * k)); b1 = __ldg(reinterpret_cast<const float4*>(a.b2 + s * 32 + 8 * k + 4)); }
               const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
               uint32_t o[8];
 #pragma unroll
@@ -307,7 +341,7 @@ extern "C" int cb_ffn_fwd(const void* y, const void* w1, const float* b1, const 
   if (use == 3 && F % 128 == 0) return ffn_fwd3_run(y, w1, b1, w2, b2, resid, z2, hid, mask_bits, ld_bits, T, F, reinterpret_cast<cudaStream_t>(stream));
   static bool attr_set = false;
   if (!attr_set) {
-    CB_CUDA(cudaFuncSetAttribute(ffn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM_BYTES));
+    CB_CUDA(cudaFuncSetAttribute(ffn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM_BYTES));
     attr_set = true;
   }
   CUtensorMap ty, t1, t2;
@@ -327,7 +361,43 @@ extern "C" int cb_ffn_fwd(const void* y, const void* w1, const float* b1, const 
   a.b1 = b1; a.b2 = b2; a.resid = resid; a.z2 = z2; a.hid = reinterpret_cast<__nv_bfloat16*>(hid); a.mask_bits = mask_bits; a.ld_bits = ld_bits; a.T = T; a.F = F;
   const int n_items = ((T + 127) / 128 + 1) / 2;
   const int grid = n_items < num_sms() ? n_items : num_sms();
-  ffn_fwd_kernel<<<grid, 320, FF_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(ty, t1, t2, a);
+  ffn_kernel<false><<<grid, 320, FF_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(ty, t1, t2, a);
+  CB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int cb_ffn_bwd(const void* dz2_bf16, const void* w2, const void* w1, const unsigned int* mask_bits, int ld_bits, const float* dz2,
+                          float* dy, void* dh, int T, int D, int F, void* stream) {
+  using namespace cb;
+  CB_CHECK(T > 0 && D == FF_D && F % FF_C == 0 && F >= FF_C && F <= FF_MAX_F, "ffn_bwd: T=%d D=%d F=%d (this kernel handles D = %d, F a multiple of %d up to %d)", T, D, F, FF_D, FF_C, FF_MAX_F);
+  CB_CHECK(mask_bits && dh && dz2 && dy && dz2_bf16 && w1 && w2, "ffn_bwd: null argument");
+  CB_CHECK(ld_bits >= T && (reinterpret_cast<uintptr_t>(mask_bits) & 3) == 0, "ffn_bwd: mask_bits is uint32 [F/32, ld_bits >= T]");
+  CB_CHECK(((reinterpret_cast<uintptr_t>(dz2) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dh)) & 31) == 0 &&
+           ((reinterpret_cast<uintptr_t>(dz2_bf16) | reinterpret_cast<uintptr_t>(w1) | reinterpret_cast<uintptr_t>(w2)) & 15) == 0,
+           "ffn_bwd: dz2 / dy / dh must be 32-byte, the bf16 operands 16-byte aligned");
+  static bool attr_set = false;
+  if (!attr_set) {
+    CB_CUDA(cudaFuncSetAttribute(ffn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM_BYTES));
+    attr_set = true;
+  }
+  CUtensorMap ty, t1, t2;
+  {
+    uint64_t dims[2] = {(uint64_t)D, (uint64_t)T}; uint64_t strides[1] = {(uint64_t)D * 2}; uint32_t box[2] = {64, 128};
+    if (make_tmap(&ty, dz2_bf16, 2, dims, strides, box, 3)) return 1;
+  }
+  {   // first product: B = W2 [D, F] row-major = [K, N]: (64 n, K, N / 64) boxes of one [64 k x 64 n] block
+    uint64_t dims[3] = {64, (uint64_t)D, (uint64_t)(F / 64)}; uint64_t strides[2] = {(uint64_t)F * 2, 128}; uint32_t box[3] = {64, 64, 1};
+    if (make_tmap(&t1, w2, 3, dims, strides, box, 3)) return 1;
+  }
+  {   // second product: B = W1 [F, D] row-major = [K, N]: boxes of [64 k (units) x D n] = FF_KB blocks
+    uint64_t dims[3] = {64, (uint64_t)F, (uint64_t)(D / 64)}; uint64_t strides[2] = {(uint64_t)D * 2, 128}; uint32_t box[3] = {64, (uint32_t)FF_C, (uint32_t)FF_KB};
+    if (make_tmap(&t2, w1, 3, dims, strides, box, 3)) return 1;
+  }
+  FfnArgs a{};
+  a.resid = dz2; a.z2 = dy; a.hid = reinterpret_cast<__nv_bfloat16*>(dh); a.mask_bits = const_cast<uint32_t*>(mask_bits); a.ld_bits = ld_bits; a.T = T; a.F = F;
+  const int n_items = ((T + 127) / 128 + 1) / 2;
+  const int grid = n_items < num_sms() ? n_items : num_sms();
+  ffn_kernel<true><<<grid, 320, FF_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(ty, t1, t2, a);
   CB_CUDA(cudaGetLastError());
   return 0;
 }

@@ -113,6 +113,28 @@ def ffn_fwd(y: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tenso
     return (z2, hid) if save_mask_bits is None else (z2, hid, bits)
 
 
+_FFN_BWD_FUSED = os.environ.get("CB_NO_FFN_BWD", "") != "1"   # A/B switch (read once): fused d(hidden) + dy kernel
+
+
+def ffn_bwd_fused_ok(D: int, F: int) -> bool:
+    return _FFN_BWD_FUSED and ffn_fused_ok(D, F)
+
+
+def ffn_bwd(dz2h: torch.Tensor, w2: torch.Tensor, w1: torch.Tensor, bits: torch.Tensor, dz2: torch.Tensor):
+    """dh = (dz2 W2) o (hidden > 0) (bf16 [T, F], stored for dW1) and dy = dh W1 + dz2 (fp32 [T, D]) in one kernel; ``bits`` is the
+    ReLU mask written by ffn_fwd(save_mask_bits=True).  Returns (dy, dh)."""
+    T, D = dz2h.shape
+    F = w1.shape[0]
+    assert dz2h.dtype == bf16 and w1.dtype == bf16 and w2.dtype == bf16 and dz2.dtype == torch.float32 and bits.dtype == torch.int32
+    assert dz2h.is_contiguous() and w1.is_contiguous() and w2.is_contiguous() and dz2.is_contiguous() and bits.is_contiguous()
+    assert w2.shape == (D, F) and w1.shape == (F, D) and dz2.shape == (T, D) and bits.shape[0] == F // 32 and bits.shape[1] >= T
+    dy = torch.empty(T, D, device=dz2h.device, dtype=torch.float32)
+    dh = torch.empty(T, F, device=dz2h.device, dtype=bf16)
+    _call("cb_ffn_bwd", _p(dz2h), _p(w2), _p(w1), _p(bits), bits.shape[1], _p(dz2), _p(dy), _p(dh), T, D, F, _stream(),
+          work=4.0 * T * D * F, nbytes=float(T) * (D * 2 + D * 8 + F * 2 + F / 8) + 4.0 * D * F)
+    return dy, dh
+
+
 def splitk_for(K: int, tiles: int, target_ctas: int = 148) -> int:
     """Number of K splits so that a weight-gradient GEMM with `tiles` output tiles fills the GPU."""
     kb = (K + 63) // 64

@@ -157,6 +157,20 @@ int cb_attn_varlen_bwd(const void* dout, const void* qkv, const void* out, const
 int cb_ffn_fwd(const void* y, const void* w1, const float* b1, const void* w2, const float* b2, const float* resid, float* z2,
                void* hid, unsigned int* mask_bits, int ld_bits, int T, int D, int F, int kernel, void* stream);
 
+/*
+ * Backward of the same block through the hidden layer (torch.autograd of linear2(relu(linear1(y))) + the residual branch,
+ * chada_vit.py:113-116 / :100), one kernel instead of two cb_gemm_bf16 calls:
+ *   dh = (dz2 W2) o (hidden > 0)        bf16 [T, F], stored (the weight gradient dW1 = dh^T y reads it)
+ *   dy = dh W1 + dz2                    fp32 [T, D]
+ * dz2_bf16 bf16 [T, D] and dz2 fp32 [T, D] are the two forms of d(z2) that cb_layernorm_bwd returns; w2 bf16 [D, F]
+ * (linear2.weight), w1 bf16 [F, D] (linear1.weight), both read in place (MN-major operands, no transposed copies);
+ * mask_bits uint32 [F/32, ld_bits >= T] as written by cb_ffn_fwd.  The [T, F] d(hidden) is written once and not read back by
+ * this kernel.  D must be 192, F a multiple of 64 (<= 2048); other shapes use cb_gemm_bf16 with CB_EPI_RELU_MASK and
+ * CB_EPI_RESIDUAL_F32.
+ */
+int cb_ffn_bwd(const void* dz2_bf16, const void* w2, const void* w1, const unsigned int* mask_bits, int ld_bits, const float* dz2,
+               float* dy, void* dh, int T, int D, int F, void* stream);
+
 /* ---------------- DINOHead pieces (src/methods/dino.py:61-111); the Linear layers themselves are cb_gemm_bf16 ---------------- */
 /* nn.GELU (exact erf): out bf16 = gelu(pre fp32);  backward: dpre bf16 = dact fp32 * gelu'(pre) */
 int cb_gelu_fwd(const float* pre, void* out, long n, void* stream);

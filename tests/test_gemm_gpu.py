@@ -170,3 +170,36 @@ def test_relu_mask_bits_equals_bf16_mask(T):
     assert (cs_a - cs_b).abs().max().item() <= 1e-3 * max(1.0, cs_a.abs().max().item())       # fp32 atomics: order differs
     full = (dz.float() @ w2.float()) * (hid > 0)
     assert (got.float() - full).abs().max().item() < 2e-2 * max(1.0, full.abs().max().item())
+
+
+@pytest.mark.parametrize("T,F", [(1000, 2048), (128, 64), (129, 128), (257, 2048), (40000, 2048), (128 * 148 * 2 + 5, 512)])
+def test_ffn_bwd_fused(T, F):
+    """cb_ffn_bwd == autograd of linear2(relu(linear1(y))) + residual w.r.t. the hidden layer and y (chada_vit.py:113-116):
+    dh = (dz2 W2) o (hidden > 0) rounded to bf16, dy = dh W1 + dz2 — against fp32 torch on the same bf16 operands and against
+    the two cb_gemm_bf16 calls it replaces."""
+    from chadavit_b200 import ops
+    D = 192
+    assert ops.ffn_bwd_fused_ok(D, F)
+    y, w1, w2 = _rand((T, D), 31), _rand((F, D), 32, 0.08), _rand((D, F), 33, 0.05)
+    b1, b2 = torch.randn(F, device="cuda") * 0.1, torch.randn(D, device="cuda") * 0.1
+    y32 = y.float()
+    _, hid, bits = ops.ffn_fwd(y, w1, b1, w2, b2, y32, save_hidden=True, save_mask_bits=True)
+    dz2 = torch.randn(T, D, device="cuda", generator=torch.Generator(device="cuda").manual_seed(34)) * 0.3
+    dz2h = dz2.to(torch.bfloat16)
+    dy, dh = ops.ffn_bwd(dz2h, w2, w1, bits, dz2)
+    ops.sync_check()
+    ref_dh = ((dz2h.float() @ w2.float()) * (hid.float() > 0)).to(torch.bfloat16)
+    ref_dy = ref_dh.float() @ w1.float() + dz2
+    e_dh = (dh.float() - ref_dh.float()).abs().max().item()
+    e_dy = (dy - ref_dy).abs().max().item()
+    u_dh = ops.gemm(dz2h, w2, b_mn=True, aux=bits, flags=ops.EPI_RELU_MASK | ops.EPI_MASK_BITS)
+    u_dy = ops.gemm(u_dh, w1, b_mn=True, aux=dz2, flags=ops.EPI_RESIDUAL_F32 | ops.EPI_OUT_F32)
+    ops.sync_check()
+    d_dh = (dh.float() - u_dh.float()).abs().max().item()
+    d_dy = (dy - u_dy).abs().max().item()
+    print(f"ffn bwd T={T} F={F}: dh err {e_dh:.3e} (max {ref_dh.float().abs().max().item():.2f}), dy err {e_dy:.3e} (max {ref_dy.abs().max().item():.2f}); "
+          f"vs unfused: dh {d_dh:.3e}, dy {d_dy:.3e}")
+    assert e_dh <= 1.6e-2 * max(1.0, ref_dh.float().abs().max().item())      # one bf16 ulp of the largest element
+    assert e_dy <= 3e-3 * max(1.0, ref_dy.abs().max().item())
+    assert d_dh <= 1.6e-2 * max(1.0, ref_dh.float().abs().max().item()) and d_dy <= 3e-3 * max(1.0, ref_dy.abs().max().item())
+    assert (dh.float() != 0).sum().item() == ((hid.float() > 0) & (dh.float() != 0)).sum().item()   # nothing leaks through the mask

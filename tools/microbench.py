@@ -101,6 +101,24 @@ def dw_section(dev, T):
         report(f"colsum bf16 [T={TT},576] (replaced)", timeit(lambda: ops.colsum(dqkv, cq)), 0, TT * 3 * D * 2)
 
 
+def ffnbwd_section(dev, T):
+    """Backward through the hidden layer: the fused kernel against the two products it replaces (same operands)."""
+    D, F = 192, 2048
+    r = lambda *s: (torch.randn(*s, device=dev) * 0.5).to(bf16)  # noqa: E731
+    for TT in (T, 2 * T):
+        dz, w2, w1 = r(TT, D), r(D, F), r(F, D)
+        dz32 = torch.randn(TT, D, device=dev)
+        bits = torch.randint(-2 ** 31, 2 ** 31 - 1, (F // 32, (TT + 31) // 32 * 32), device=dev, dtype=torch.int32)
+        o, dy = torch.empty(TT, F, device=dev, dtype=bf16), torch.empty(TT, D, device=dev)
+        M, R = ops.EPI_RELU_MASK | ops.EPI_MASK_BITS, ops.EPI_RESIDUAL_F32 | ops.EPI_OUT_F32
+        t1 = timeit(lambda: ops.gemm(dz, w2, b_mn=True, aux=bits, flags=M, out=o))
+        t2 = timeit(lambda: ops.gemm(o, w1, b_mn=True, aux=dz32, flags=R, out=dy))
+        report(f"dh T={TT} (bits, no colsum)", t1, 2.0 * TT * D * F, TT * (D * 2 + F * 2 + F / 8))
+        report(f"dy T={TT} [T,2048]x[2048,192] +res32", t2, 2.0 * TT * D * F, TT * (F * 2 + D * 8))
+        report(f"  sum of the two T={TT}", t1 + t2, 4.0 * TT * D * F, TT * (D * 10 + F * 4 + F / 8))
+        report(f"ffn bwd fused T={TT} (dh stored once)", timeit(lambda: ops.ffn_bwd(dz, w2, w1, bits, dz32)), 4.0 * TT * D * F, TT * (D * 10 + F * 2 + F / 8))
+
+
 def attn_section(dev):
     """Attention forward / backward alone: the bench's ragged global-crop batch, 32 uniform 1961-token sequences, and the
     base/16 stress shape (D = 768, 12 heads of 64)."""
@@ -126,6 +144,8 @@ def main():
         return ffn_section("cuda", a.tokens)
     if a.only == "dh":
         return dh_section("cuda", a.tokens)
+    if a.only == "ffnbwd":
+        return ffnbwd_section("cuda", a.tokens)
     if a.only == "dw":
         return dw_section("cuda", a.tokens)
     if a.only == "attn":
