@@ -62,7 +62,10 @@ __device__ __forceinline__ uint32_t ldg_u32_pinned(const uint32_t* p) {   // sta
   return v;
 }
 
-template <bool BWD>
+// WMN: the two weight operands are read MN-major in place (the backward reads the stored weights: no transposed copies);
+// false: K-major (forward).  Measured: the backward on pre-transposed K-major copies runs in the same time to the microsecond
+// (156.7 vs 156.5 us per 68 k tokens, profiles/r02_microbench_ffn_bwd.txt), so only the in-place form is kept.
+template <bool BWD, bool WMN = BWD>
 __global__ void __launch_bounds__(320, 1)
 ffn_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
            const FfnArgs a) {
@@ -124,13 +127,13 @@ ffn_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUte
           mbar_expect_tx(&w1_full[s1], FF_W1_BYTES);
 #pragma unroll
           for (int kb = 0; kb < FF_KB; ++kb) {
-            if (!BWD) tma_load_2d(sW1 + s1 * FF_W1_BYTES + kb * (FF_C * 128), &tmW1, &w1_full[s1], kb * 64, c * FF_C);
+            if (!WMN) tma_load_2d(sW1 + s1 * FF_W1_BYTES + kb * (FF_C * 128), &tmW1, &w1_full[s1], kb * 64, c * FF_C);
             else tma_load_3d(sW1 + s1 * FF_W1_BYTES + kb * (FF_C * 128), &tmW1, &w1_full[s1], 0, kb * 64, c);   // W2 rows kb*64.., unit block c
           }
           if (++s1 == FF_S1) { s1 = 0; p1 ^= 1; }
           mbar_wait(&w2_empty[s2], p2 ^ 1);
           mbar_expect_tx(&w2_full[s2], FF_W2_BYTES);
-          if (!BWD) tma_load_2d(sW2 + s2 * FF_W2_BYTES, &tmW2, &w2_full[s2], c * FF_C, 0);
+          if (!WMN) tma_load_2d(sW2 + s2 * FF_W2_BYTES, &tmW2, &w2_full[s2], c * FF_C, 0);
           else tma_load_3d(sW2 + s2 * FF_W2_BYTES, &tmW2, &w2_full[s2], 0, c * FF_C, 0);   // W1 rows (units) c*64.., all FF_KB column blocks
           if (++s2 == FF_S2) { s2 = 0; p2 ^= 1; }
         }
@@ -141,12 +144,12 @@ ffn_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUte
     // ONE issuing warp serving both tiles in strict A, B, A, B order: the groups are large here (16 MMAs = 960 clk), so the
     // ~160 clk per group on the issuing warp is amortised, and exclusive back-to-back groups keep the ping-pong tight (with
     // one issuer per tile the two streams interleaved MMA by MMA and every group took twice as long to retire).
-    constexpr uint32_t idesc_h = umma_idesc_bf16(128, FF_C, false, BWD);
-    constexpr uint32_t idesc_z = umma_idesc_bf16(128, FF_D, false, BWD);
+    constexpr uint32_t idesc_h = umma_idesc_bf16(128, FF_C, false, WMN);
+    constexpr uint32_t idesc_z = umma_idesc_bf16(128, FF_D, false, WMN);
     const uint64_t y_desc0 = umma_smem_desc(smem_u32(sY), 16, 1024, 3);
     // forward: both weight chunks K-major (rows of 64 k-elements, 32 bytes per K = 16 step).  Backward: MN-major blocks of
     // [64 k-rows x 64 n-elements] (8 KB, LBO = distance between n-blocks), 2048 bytes per K = 16 step (gemm.cu, operand mode 1).
-    constexpr uint32_t W_LBO = BWD ? 64 * 128 : 16, W_KSTEP = BWD ? 2048 : 32;
+    constexpr uint32_t W_LBO = WMN ? 64 * 128 : 16, W_KSTEP = WMN ? 2048 : 32;
     const uint64_t w1_desc0 = umma_smem_desc(smem_u32(sW1), W_LBO, 1024, 3), w2_desc0 = umma_smem_desc(smem_u32(sW2), W_LBO, 1024, 3);
     int s1 = 0, s2 = 0; uint32_t p1 = 0, p2 = 0, ni = 0, nib = 0, np = 0, npb = 0;   // rings; items / p_full uses of tile A, tile B
     CB_TL_DECL(tl);
@@ -214,16 +217,30 @@ ffn_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUte
     uint32_t nh0 = 0, nh1 = 0, ni0 = 0, ni1 = 0;   // h_full uses / items so far of tile A, tile B
     CB_TL_DECL(tl);
     const bool tl_on = (warp == 0 || warp == 4) && lane == 0;
+    // BWD: the ReLU mask word of this thread's 32 units of (item, chunk, tile) — a warp reads one 128-byte line.  It sits on the
+    // critical chain H(c) -> P(c) -> Z += / H(c+1), so it is requested ONE CHUNK AHEAD (for the same tile, across item
+    // boundaries too) and is in a register when the accumulator arrives; mwA / mwB hold the words of tile A / B.
+    auto load_mw = [&](int it_, int c_, int t_) -> uint32_t {
+      if (c_ == n_chunks) { c_ = 0; it_ += gridDim.x; }
+      const long row_ = (long)(2 * it_ + t_) * 128 + r_in_tile;
+      return (it_ < n_items && row_ < a.T) ? ldg_u32_pinned(a.mask_bits + (long)(2 * c_ + hf) * a.ld_bits + row_) : 0u;
+    };
+    uint32_t mwA = 0u, mwB = 0u;
+    if (BWD && (int)blockIdx.x < n_items) { mwA = load_mw(blockIdx.x, 0, 0); mwB = load_mw(blockIdx.x, 0, 1); }
     for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
       const int nt = (2 * it + 1 < n_tiles) ? 2 : 1;
       for (int c = 0; c < n_chunks; ++c) {
-#pragma unroll 1
-        for (int t = 0; t < nt; ++t) {
+        // BWD: the two-tile loop is unrolled so that mwA / mwB are statically named registers — in the rolled loop the hand-over
+        // `if (t) mwB = nx; else mwA = nx;` is a select that DEPENDS on the load just issued and blocks the warp for the whole
+        // global-load latency (in-kernel timeline: 1550 clk in front of every accumulator wait, profiles/r02_timeline_ffn_bwd.txt).
+#pragma unroll (BWD ? 2 : 1)
+        for (int t = 0; t < 2; ++t) {
+          if (t >= nt) break;
           const long row = (long)(2 * it + t) * 128 + r_in_tile;
           const uint32_t h_addr = lane_addr + t * FF_C + hf * 32;
           if (tl_on) CB_TL(1 + hf, tl, 1 + 4 * t);
-          uint32_t mw = 0u;   // BWD: ReLU mask of this thread's 32 units, requested before the accumulator wait (a warp = one 128-byte line)
-          if (BWD && row < a.T) mw = ldg_u32_pinned(a.mask_bits + (long)(2 * c + hf) * a.ld_bits + row);
+          const uint32_t mw = t ? mwB : mwA;
+          if (BWD) { const uint32_t nx = load_mw(it, c + 1, t); if (t) mwB = nx; else mwA = nx; }
           mbar_wait(&h_full[t], (t ? nh1 : nh0) & 1);
           if (t) ++nh1; else ++nh0;
           tc_fence_after();
@@ -377,7 +394,7 @@ extern "C" int cb_ffn_bwd(const void* dz2_bf16, const void* w2, const void* w1, 
            "ffn_bwd: dz2 / dy / dh must be 32-byte, the bf16 operands 16-byte aligned");
   static bool attr_set = false;
   if (!attr_set) {
-    CB_CUDA(cudaFuncSetAttribute(ffn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM_BYTES));
+    CB_CUDA(cudaFuncSetAttribute(ffn_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM_BYTES));
     attr_set = true;
   }
   CUtensorMap ty, t1, t2;
@@ -385,6 +402,10 @@ extern "C" int cb_ffn_bwd(const void* dz2_bf16, const void* w2, const void* w1, 
     uint64_t dims[2] = {(uint64_t)D, (uint64_t)T}; uint64_t strides[1] = {(uint64_t)D * 2}; uint32_t box[2] = {64, 128};
     if (make_tmap(&ty, dz2_bf16, 2, dims, strides, box, 3)) return 1;
   }
+  FfnArgs a{};
+  a.resid = dz2; a.z2 = dy; a.hid = reinterpret_cast<__nv_bfloat16*>(dh); a.mask_bits = const_cast<uint32_t*>(mask_bits); a.ld_bits = ld_bits; a.T = T; a.F = F;
+  const int n_items = ((T + 127) / 128 + 1) / 2;
+  const int grid = n_items < num_sms() ? n_items : num_sms();
   {   // first product: B = W2 [D, F] row-major = [K, N]: (64 n, K, N / 64) boxes of one [64 k x 64 n] block
     uint64_t dims[3] = {64, (uint64_t)D, (uint64_t)(F / 64)}; uint64_t strides[2] = {(uint64_t)F * 2, 128}; uint32_t box[3] = {64, 64, 1};
     if (make_tmap(&t1, w2, 3, dims, strides, box, 3)) return 1;
@@ -393,11 +414,7 @@ extern "C" int cb_ffn_bwd(const void* dz2_bf16, const void* w2, const void* w1, 
     uint64_t dims[3] = {64, (uint64_t)F, (uint64_t)(D / 64)}; uint64_t strides[2] = {(uint64_t)D * 2, 128}; uint32_t box[3] = {64, (uint32_t)FF_C, (uint32_t)FF_KB};
     if (make_tmap(&t2, w1, 3, dims, strides, box, 3)) return 1;
   }
-  FfnArgs a{};
-  a.resid = dz2; a.z2 = dy; a.hid = reinterpret_cast<__nv_bfloat16*>(dh); a.mask_bits = const_cast<uint32_t*>(mask_bits); a.ld_bits = ld_bits; a.T = T; a.F = F;
-  const int n_items = ((T + 127) / 128 + 1) / 2;
-  const int grid = n_items < num_sms() ? n_items : num_sms();
-  ffn_kernel<true><<<grid, 320, FF_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(ty, t1, t2, a);
+  ffn_kernel<true, true><<<grid, 320, FF_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(ty, t1, t2, a);
   CB_CUDA(cudaGetLastError());
   return 0;
 }

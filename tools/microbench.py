@@ -117,6 +117,36 @@ def ffnbwd_section(dev, T):
         report(f"dy T={TT} [T,2048]x[2048,192] +res32", t2, 2.0 * TT * D * F, TT * (F * 2 + D * 8))
         report(f"  sum of the two T={TT}", t1 + t2, 4.0 * TT * D * F, TT * (D * 10 + F * 4 + F / 8))
         report(f"ffn bwd fused T={TT} (dh stored once)", timeit(lambda: ops.ffn_bwd(dz, w2, w1, bits, dz32)), 4.0 * TT * D * F, TT * (D * 10 + F * 2 + F / 8))
+        b1, b2 = torch.randn(F, device=dev), torch.randn(D, device=dev)
+        report(f"ffn fwd + hidden store + bits T={TT} (for scale)", timeit(lambda: ops.ffn_fwd(dz, w1, b1, w2, b2, dz32, save_hidden=True, save_mask_bits=True)), 4.0 * TT * D * F)
+
+
+def kmajor_section(dev, T):
+    """Input-gradient products dX = dY W: the weight read in place as an MN-major B operand ([K, N] row-major) against a
+    pre-transposed K-major copy ([N, K]) — same math, same bytes, only the shared-memory layout the tensor core reads differs."""
+    D, F = 192, 2048
+    r = lambda *s: (torch.randn(*s, device=dev) * 0.5).to(bf16)  # noqa: E731
+    dz, dhid, dqkv, x32 = r(T, D), r(T, F), r(T, 3 * D), torch.randn(T, D, device=dev)
+    w2, w1, win, wo = r(D, F), r(F, D), r(3 * D, D), r(D, D)
+    bits = torch.randint(-2 ** 31, 2 ** 31 - 1, (F // 32, (T + 31) // 32 * 32), device=dev, dtype=torch.int32)
+    M, R = ops.EPI_RELU_MASK | ops.EPI_MASK_BITS, ops.EPI_RESIDUAL_F32 | ops.EPI_OUT_F32
+    o = torch.empty(T, F, device=dev, dtype=bf16)
+    w2t, w1t, wint, wot = (w.t().contiguous() for w in (w2, w1, win, wo))
+    report("dh   B = W2 MN-major", timeit(lambda: ops.gemm(dz, w2, b_mn=True, aux=bits, flags=M, out=o)), 2.0 * T * D * F)
+    report("dh   B = W2^T K-major", timeit(lambda: ops.gemm(dz, w2t, aux=bits, flags=M, out=o)), 2.0 * T * D * F)
+    report("fc1-like (no mask) B MN-major", timeit(lambda: ops.gemm(dz, w2, b_mn=True, out=o)), 2.0 * T * D * F)
+    report("fc1-like (no mask) B K-major", timeit(lambda: ops.gemm(dz, w2t, out=o)), 2.0 * T * D * F)
+    o = torch.empty(T, D, device=dev)
+    report("dy   B = W1 MN-major", timeit(lambda: ops.gemm(dhid, w1, b_mn=True, aux=x32, flags=R, out=o)), 2.0 * T * D * F)
+    report("dy   B = W1^T K-major", timeit(lambda: ops.gemm(dhid, w1t, aux=x32, flags=R, out=o)), 2.0 * T * D * F)
+    report("du   B = Win MN-major", timeit(lambda: ops.gemm(dqkv, win, b_mn=True, flags=ops.EPI_OUT_F32, out=o)), 2.0 * T * D * 3 * D)
+    report("du   B = Win^T K-major", timeit(lambda: ops.gemm(dqkv, wint, flags=ops.EPI_OUT_F32, out=o)), 2.0 * T * D * 3 * D)
+    o = torch.empty(T, D, device=dev, dtype=bf16)
+    report("datt B = Wo MN-major", timeit(lambda: ops.gemm(dz, wo, b_mn=True, out=o)), 2.0 * T * D * D)
+    report("datt B = Wo^T K-major", timeit(lambda: ops.gemm(dz, wot, out=o)), 2.0 * T * D * D)
+    b1, b2 = torch.randn(F, device=dev), torch.randn(D, device=dev)
+    report("ffn fwd + hidden store (K-major weights)", timeit(lambda: ops.ffn_fwd(dz, w1, b1, w2, b2, x32, save_hidden=True, save_mask_bits=True)), 4.0 * T * D * F)
+    report("ffn bwd fused (MN-major weights)", timeit(lambda: ops.ffn_bwd(dz, w2, w1, bits, x32)), 4.0 * T * D * F)
 
 
 def attn_section(dev):
@@ -146,6 +176,8 @@ def main():
         return dh_section("cuda", a.tokens)
     if a.only == "ffnbwd":
         return ffnbwd_section("cuda", a.tokens)
+    if a.only == "kmajor":
+        return kmajor_section("cuda", a.tokens)
     if a.only == "dw":
         return dw_section("cuda", a.tokens)
     if a.only == "attn":

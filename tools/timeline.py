@@ -26,7 +26,7 @@ qkv, do = r(lay.T, 3 * D), r(lay.T, D)
 lib = _lib.load()
 ROLES, LEN = 4, 4096
 buf = np.zeros((ROLES, LEN), dtype=np.uint64)
-rd = getattr(lib, f"cb_debug_timeline_{which}")
+rd = getattr(lib, "cb_debug_timeline_" + {"ffnstore": "ffn", "ffnbwd": "ffn"}.get(which, which))
 rd.argtypes, rd.restype = [C.c_void_p], C.c_int
 
 out, lse = ops.attn_fwd(qkv, lay, 2)
@@ -34,6 +34,7 @@ T, F = 68664, 2048
 x16, w1, b1 = r(T, D), r(F, D), torch.randn(F, device=dev)
 hid_out = torch.empty(T, F, device=dev, dtype=bf16)
 w2f, b2f, x32f = r(D, F), torch.randn(D, device=dev), torch.randn(T, D, device=dev)
+tl_bits = torch.randint(-2 ** 31, 2 ** 31 - 1, (F // 32, (T + 31) // 32 * 32), device=dev, dtype=torch.int32)
 
 
 def run():
@@ -43,6 +44,10 @@ def run():
         ops.attn_bwd(do, qkv, out, lse, lay, 2)
     elif which in ("ffn", "ffn2", "ffn3"):
         ops.ffn_fwd(x16, w1, b1, w2f, b2f, x32f, save_hidden=False)
+    elif which == "ffnstore":       # pair-of-tiles kernel with the hidden store + mask bits (student pass)
+        ops.ffn_fwd(x16, w1, b1, w2f, b2f, x32f, save_hidden=True, save_mask_bits=True, kernel=1)
+    elif which == "ffnbwd":         # fused backward through the hidden layer (same translation unit, same tags)
+        ops.ffn_bwd(x16, w2f, w1, tl_bits, x32f)
     else:   # gemm: fc1
         ops.gemm(x16, w1, bias=b1, flags=ops.EPI_RELU, out=hid_out)
 
