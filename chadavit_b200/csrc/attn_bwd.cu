@@ -460,6 +460,8 @@ extern "C" int cb_attn_varlen_bwd(const void* dout, const void* qkv, const void*
                                   float* delta_ws, float* dq_acc_ws, void* dqkv, int T, int D, int H, float softmax_scale, void* stream) {
   using namespace cb;
   CB_CHECK(T > 0 && H > 0 && D % H == 0 && n_work > 0 && D % 8 == 0, "attn_bwd: bad shape T=%d D=%d H=%d n_work=%d", T, D, H, n_work);
+  CB_CHECK(D % 16 == 0 && (D / H) % 16 == 0 && (reinterpret_cast<uintptr_t>(dqkv) & 31) == 0,
+           "attn_bwd: dK / dV leave as 32-byte sectors: D and head_dim must be multiples of 16 and dqkv 32-byte aligned (D=%d H=%d)", D, H);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   CB_CUDA(cudaMemsetAsync(dq_acc_ws, 0, (size_t)T * D * sizeof(float), s));
   attn_delta_kernel<<<(T + 7) / 8, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(dout), reinterpret_cast<const __nv_bfloat16*>(out), delta_ws, T, D, H);

@@ -26,6 +26,20 @@ namespace cb {
 static __device__ unsigned long long g_cb_timeline[CB_TL_ROLES][CB_TL_LEN];
 #endif
 
+// Work-item descriptor fetched ONE ITEM AHEAD (every role walks the same list): a plain load at the top of the item puts a
+// dependent global-memory round trip (descriptor -> addresses -> LSE / delta / TMA coordinates) into every item boundary
+// (in-kernel timeline, profiles/r02_timeline_attn_bwd_boundary.txt: ~4000 clk per role and boundary).
+__device__ __forceinline__ int4 ldg_int4_pinned(const int4* p) {
+  int4 v;
+  asm volatile("ld.global.nc.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+// L2 prefetch of one TMA box (no shared-memory destination, no barrier): the next item's K / V tiles and its first Q / dO tile
+// are HBM misses when the item starts (4500 clk from issue to landing at the boundary, ~1000 from L2).
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1) : "memory");
+}
+
 template <int HD>
 struct Bwd2Cfg : BwdCfg<HD> {
   static constexpr int COL_S = 0, COL_DP = 128, COL_DQ = 128 /* aliases dP^T */, COL_DK = 256, COL_DV = 256 + (HD < 32 ? 32 : HD), COL_PT = 448;
@@ -93,13 +107,18 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       uint32_t it = 0, wi = 0;
+      CB_TL_DECL(tlp);
+      int4 wk_next = ldg_int4_pinned(a.work + blockIdx.x);
       for (int w = blockIdx.x; w < a.n_work; w += gridDim.x) {
-        const int4 wk = a.work[w];
+        const int4 wk = wk_next;
+        if (w + (int)gridDim.x < a.n_work) wk_next = ldg_int4_pinned(a.work + w + gridDim.x); else wk_next = make_int4(0, 0, 0, 0);
         if (wk.z <= wk.y) continue;               // empty slot of the balanced schedule
         const int head = wk.w;
         const int nq = (wk.z - wk.y + 127) / 128;
+        CB_TL(3, tlp, 1);
         mbar_wait(kv_empty, (wi & 1) ^ 1);
         ++wi;
+        CB_TL(3, tlp, 2);
         mbar_expect_tx(kv_full, 2 * Cfg::TILE_BYTES);
 #pragma unroll
         for (int c = 0; c < Cfg::NCH; ++c) {
@@ -116,6 +135,17 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
             tma_load_2d(sQ + s * Cfg::TILE_BYTES + c * Cfg::CHUNK_BYTES, &tmQKV, &qdo_full[s], head * HD + c * Cfg::CHUNK, row);
             tma_load_2d(sDO + s * Cfg::TILE_BYTES + c * Cfg::CHUNK_BYTES, &tmDO, &qdo_full[s], head * HD + c * Cfg::CHUNK, row);
           }
+          // The next item's K, V and first Q / dO tile -> L2, issued BEHIND this item's own first loads (in front of them the
+          // prefetches delayed the first S^T of the item by ~4000 clk) and, for items of more than two tiles, one tile later still.
+          if (i == (nq > 2 ? 1 : 0) && wk_next.z > wk_next.y) {
+#pragma unroll
+            for (int c = 0; c < Cfg::NCH; ++c) {
+              tma_prefetch_l2_2d(&tmQKV, a.D + wk_next.w * HD + c * Cfg::CHUNK, wk_next.x);
+              tma_prefetch_l2_2d(&tmQKV, 2 * a.D + wk_next.w * HD + c * Cfg::CHUNK, wk_next.x);
+              tma_prefetch_l2_2d(&tmQKV, wk_next.w * HD + c * Cfg::CHUNK, wk_next.y);
+              tma_prefetch_l2_2d(&tmDO, wk_next.w * HD + c * Cfg::CHUNK, wk_next.y);
+            }
+          }
         }
       }
     }
@@ -125,8 +155,10 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     // tile blocks the issuing thread for ~1200 clk, so a warp of its own does it.
     if (lane == 0) {
       uint32_t it = 0;
+      int4 wk_next = ldg_int4_pinned(a.work + blockIdx.x);
       for (int w = blockIdx.x; w < a.n_work; w += gridDim.x) {
-        const int4 wk = a.work[w];
+        const int4 wk = wk_next;
+        if (w + (int)gridDim.x < a.n_work) wk_next = ldg_int4_pinned(a.work + w + gridDim.x);
         if (wk.z <= wk.y) continue;
         const int head = wk.w;
         const int nq = (wk.z - wk.y + 127) / 128;
@@ -162,12 +194,16 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     const uint64_t ds_kd = umma_smem_desc(smem_u32(sDS), 16, 1024, 3), ds_md = umma_smem_desc(smem_u32(sDS), 16384, 1024, 3);
     uint32_t it = 0, wi = 0;
     CB_TL_DECL(tl);
+    int4 wk_next = ldg_int4_pinned(a.work + blockIdx.x);
     for (int w = blockIdx.x; w < a.n_work; w += gridDim.x) {
-      const int4 wk = a.work[w];
+      const int4 wk = wk_next;
+      if (w + (int)gridDim.x < a.n_work) wk_next = ldg_int4_pinned(a.work + w + gridDim.x);
       if (wk.z <= wk.y) continue;
       const int nq = (wk.z - wk.y + 127) / 128;
+      CB_TL(0, tl, 7);
       mbar_wait(kv_full, wi & 1);
       ++wi;
+      CB_TL(0, tl, 8);
       auto issue_s = [&](uint32_t itx) {   // S^T = K Q^T of iteration itx: its Q tile has landed and the E phase has read S^T(itx-1)
         const int sx = itx % NS;
         const uint64_t q_kd = umma_desc_add(q_kd0, sx * Cfg::TILE_BYTES);
@@ -199,6 +235,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         __syncwarp();
       };
       issue_s(it);
+      CB_TL(0, tl, 9);
       issue_dp(it);
       for (int i = 0; i < nq; ++i, ++it) {
         const int s = it % NS;
@@ -256,8 +293,12 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     CB_TL_DECL(tl);
     const bool tl_on = (warp == 0 || warp == 4) && lane == 0;
     const int tl_role = warp == 0 ? 1 : 2;
+    int4 wk_next = ldg_int4_pinned(a.work + blockIdx.x);
+    float stage_pref = 0.f;      // LSE / delta of the NEXT item's first q tile, requested before this item's epilogue
+    bool have_pref = false;
     for (int w = blockIdx.x; w < a.n_work; w += gridDim.x) {
-      const int4 wk = a.work[w];
+      const int4 wk = wk_next;
+      if (w + (int)gridDim.x < a.n_work) wk_next = ldg_int4_pinned(a.work + w + gridDim.x); else wk_next = make_int4(0, 0, 0, 0);
       if (wk.z <= wk.y) continue;
       const int head = wk.w;
       const int nq = (wk.z - wk.y + 127) / 128;
@@ -275,7 +316,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         return ldg_f32_pinned(stage_src + (t < wk.z ? t : wk.y));
       };
       auto stage_fix = [&](float v, int i_) -> float { return (wk.y + i_ * 128 + tid128 < wk.z) ? v * stage_mul : stage_oob; };
-      float stage_val = stage_load(0);
+      float stage_val = have_pref ? stage_pref : stage_load(0);
       if (is_a) {
         for (int i = 0; i < nq; ++i, ++it) {
           float* lse_b = sLSE + (it & 1) * 128;
@@ -404,9 +445,16 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
       // ---- dV (A warps) / dK (B warps) of this kv tile -> bf16 into dqkv.  The roles are not arbitrary: the next item's first dV
       // product (which overwrites dV) is issued on pa_ready, i.e. after the A warps have left this epilogue, and its first dK
       // product on p_ready, after the B warps have.
+      have_pref = wk_next.z > wk_next.y;
+      if (have_pref) {   // first tile of the next item: in flight during this item's epilogue
+        const int t = wk_next.y + tid128;
+        stage_pref = ldg_f32_pinned((is_a ? a.lse : a.delta) + (long)wk_next.w * a.T + (t < wk_next.z ? t : wk_next.y));
+      }
+      if (tl_on) CB_TL(tl_role, tl, 10);
       mbar_wait(dkv_full, wi & 1);
       ++wi;
       tc_fence_after();
+      if (tl_on) CB_TL(tl_role, tl, 11);
       {
         __nv_bfloat16* dst = a.dqkv + (long)(wk.x + r) * (3 * a.D) + (is_a ? 2 * a.D : a.D) + head * HD;
         const uint32_t col = is_a ? Cfg::COL_DV : Cfg::COL_DK;
@@ -416,14 +464,18 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
           tmem_ld16(lane_addr + col + c, o);
           tmem_ld_wait();
           if (kv_ok) {
-            *reinterpret_cast<uint4*>(dst + c) = make_uint4(pack_bf16(__uint_as_float(o[0]), __uint_as_float(o[1])), pack_bf16(__uint_as_float(o[2]), __uint_as_float(o[3])),
-                                                            pack_bf16(__uint_as_float(o[4]), __uint_as_float(o[5])), pack_bf16(__uint_as_float(o[6]), __uint_as_float(o[7])));
-            *reinterpret_cast<uint4*>(dst + c + 8) = make_uint4(pack_bf16(__uint_as_float(o[8]), __uint_as_float(o[9])), pack_bf16(__uint_as_float(o[10]), __uint_as_float(o[11])),
-                                                                pack_bf16(__uint_as_float(o[12]), __uint_as_float(o[13])), pack_bf16(__uint_as_float(o[14]), __uint_as_float(o[15])));
+            // one FULL 32-byte sector per store (rows, the K / V column blocks and the head offsets are multiples of 32 bytes when
+            // HD % 16 == 0): as two 16-byte halves every sector was written twice, partially — the 128 x HD tile took ~5000 clk to
+            // leave the SM and held up the LSU for the next item's first loads (profiles/r02_timeline_attn_bwd_boundary.txt)
+            stg256(dst + c, pack_bf16(__uint_as_float(o[0]), __uint_as_float(o[1])), pack_bf16(__uint_as_float(o[2]), __uint_as_float(o[3])),
+                   pack_bf16(__uint_as_float(o[4]), __uint_as_float(o[5])), pack_bf16(__uint_as_float(o[6]), __uint_as_float(o[7])),
+                   pack_bf16(__uint_as_float(o[8]), __uint_as_float(o[9])), pack_bf16(__uint_as_float(o[10]), __uint_as_float(o[11])),
+                   pack_bf16(__uint_as_float(o[12]), __uint_as_float(o[13])), pack_bf16(__uint_as_float(o[14]), __uint_as_float(o[15])));
           }
         }
       }
       tc_fence_before();
+      if (tl_on) CB_TL(tl_role, tl, 12);
     }
   }
   tc_fence_before();

@@ -365,13 +365,12 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         uint32_t o[16];
         tmem_ld16(o_addr + c, o);
         tmem_ld_wait();
-        if (ok) {
-          *reinterpret_cast<uint4*>(dst + c) = make_uint4(
-              pack_bf16(__uint_as_float(o[0]) * inv_l, __uint_as_float(o[1]) * inv_l), pack_bf16(__uint_as_float(o[2]) * inv_l, __uint_as_float(o[3]) * inv_l),
-              pack_bf16(__uint_as_float(o[4]) * inv_l, __uint_as_float(o[5]) * inv_l), pack_bf16(__uint_as_float(o[6]) * inv_l, __uint_as_float(o[7]) * inv_l));
-          *reinterpret_cast<uint4*>(dst + c + 8) = make_uint4(
-              pack_bf16(__uint_as_float(o[8]) * inv_l, __uint_as_float(o[9]) * inv_l), pack_bf16(__uint_as_float(o[10]) * inv_l, __uint_as_float(o[11]) * inv_l),
-              pack_bf16(__uint_as_float(o[12]) * inv_l, __uint_as_float(o[13]) * inv_l), pack_bf16(__uint_as_float(o[14]) * inv_l, __uint_as_float(o[15]) * inv_l));
+        if (ok) {   // one full 32-byte sector per store (see attn_bwd2.cu: 16-byte halves write every sector twice, partially)
+          stg256(dst + c,
+                 pack_bf16(__uint_as_float(o[0]) * inv_l, __uint_as_float(o[1]) * inv_l), pack_bf16(__uint_as_float(o[2]) * inv_l, __uint_as_float(o[3]) * inv_l),
+                 pack_bf16(__uint_as_float(o[4]) * inv_l, __uint_as_float(o[5]) * inv_l), pack_bf16(__uint_as_float(o[6]) * inv_l, __uint_as_float(o[7]) * inv_l),
+                 pack_bf16(__uint_as_float(o[8]) * inv_l, __uint_as_float(o[9]) * inv_l), pack_bf16(__uint_as_float(o[10]) * inv_l, __uint_as_float(o[11]) * inv_l),
+                 pack_bf16(__uint_as_float(o[12]) * inv_l, __uint_as_float(o[13]) * inv_l), pack_bf16(__uint_as_float(o[14]) * inv_l, __uint_as_float(o[15]) * inv_l));
         }
       }
       if (ok && a.lse) a.lse[(long)wk.w * a.T + grow] = (m_used + log2f(l)) * 0.6931471805599453f;
@@ -426,6 +425,8 @@ extern "C" int cb_attn_varlen_fwd(const void* qkv, const int* work, int n_work, 
   using namespace cb;
   CB_CHECK(T > 0 && H > 0 && D % H == 0 && n_work > 0, "attn_fwd: bad shape T=%d D=%d H=%d n_work=%d", T, D, H, n_work);
   CB_CHECK((3 * D) % 8 == 0, "attn_fwd: 3*D must be a multiple of 8");
+  CB_CHECK(D % 16 == 0 && (D / H) % 16 == 0 && (reinterpret_cast<uintptr_t>(out) & 31) == 0,
+           "attn_fwd: the output leaves as 32-byte sectors: D and head_dim must be multiples of 16 and out 32-byte aligned (D=%d H=%d)", D, H);
   CB_CHECK(q_tile == 256, "attn_fwd: q_tile must be 256 (work items are pairs of 128-row query tiles)");
   return attn_fwd2_run(qkv, work, n_work, out, lse, T, D, H, softmax_scale, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -71,8 +71,10 @@ for role in range(ROLES):
         ev.append((int(v >> np.uint64(8)), role, int(v & np.uint64(255))))
 ev.sort()
 t0 = ev[0][0]
-print("# cycles role tag   (first 160 events)")
-for t, role, tag in ev[:160]:
+# optional window: python tools/timeline.py <which> <shape> <first_cycle> <last_cycle>  prints every event in that range instead
+win = (int(sys.argv[3]), int(sys.argv[4])) if len(sys.argv) > 4 else None
+print("# cycles role tag   " + (f"(window {win[0]}..{win[1]})" if win else "(first 160 events)"))
+for t, role, tag in (ev[:160] if win is None else [e for e in ev if win[0] <= e[0] - t0 <= win[1]]):
     print(f"{t - t0:9d}  {'   ' * role}r{role}:{tag}")
 # per role: average delta between consecutive events keyed by (tag_prev -> tag)
 for role in range(ROLES):
