@@ -365,11 +365,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             uint32_t o[16];
             tmem_ld16(lane_addr + col + c, o);
             tmem_ld_wait();
-            if (kv_ok) {
-              *reinterpret_cast<uint4*>(dst + c) = make_uint4(pack_bf16(__uint_as_float(o[0]), __uint_as_float(o[1])), pack_bf16(__uint_as_float(o[2]), __uint_as_float(o[3])),
-                                                              pack_bf16(__uint_as_float(o[4]), __uint_as_float(o[5])), pack_bf16(__uint_as_float(o[6]), __uint_as_float(o[7])));
-              *reinterpret_cast<uint4*>(dst + c + 8) = make_uint4(pack_bf16(__uint_as_float(o[8]), __uint_as_float(o[9])), pack_bf16(__uint_as_float(o[10]), __uint_as_float(o[11])),
-                                                                  pack_bf16(__uint_as_float(o[12]), __uint_as_float(o[13])), pack_bf16(__uint_as_float(o[14]), __uint_as_float(o[15])));
+            if (kv_ok) {   // one full 32-byte sector per store (see attn_bwd2.cu)
+              stg256(dst + c, pack_bf16(__uint_as_float(o[0]), __uint_as_float(o[1])), pack_bf16(__uint_as_float(o[2]), __uint_as_float(o[3])),
+                     pack_bf16(__uint_as_float(o[4]), __uint_as_float(o[5])), pack_bf16(__uint_as_float(o[6]), __uint_as_float(o[7])),
+                     pack_bf16(__uint_as_float(o[8]), __uint_as_float(o[9])), pack_bf16(__uint_as_float(o[10]), __uint_as_float(o[11])),
+                     pack_bf16(__uint_as_float(o[12]), __uint_as_float(o[13])), pack_bf16(__uint_as_float(o[14]), __uint_as_float(o[15])));
             }
           }
         }
