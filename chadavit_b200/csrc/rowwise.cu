@@ -2,6 +2,7 @@
 // 16-byte vector accesses, fp32 statistics), column sums (bias gradients), casts.
 #include "common.cuh"
 #include "chadavit_b200.h"
+#include <stdlib.h>
 
 namespace cb {
 
@@ -379,6 +380,94 @@ __global__ void __launch_bounds__(256) layernorm_bwd_g8_kernel(const float* __re
   }
 }
 
+// Same contract, 16 lanes per row (a lane owns 4 consecutive columns of every 64-column block; a warp = 2 rows per trip).
+// The 8-lane kernel above keeps 3 x 24 column accumulators, gamma and two copies of its 24 row elements per lane: 202
+// registers, i.e. ONE 8-warp block per SM for a kernel that only streams memory, and its `dres` loads are issued after the row
+// reduction (two dependent memory phases per trip): 3.7 TB/s.  Half the columns per lane halve all of that (two blocks per SM),
+// and dres is requested together with dy and x.
+__device__ __forceinline__ float group16_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 4); v += __shfl_xor_sync(0xffffffffu, v, 8);
+  return v;
+}
+template <int NJ>
+__global__ void __launch_bounds__(256, 2) layernorm_bwd_g16_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                                   const int* __restrict__ idx, const float* __restrict__ gamma,
+                                                                   const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                                                                   const float* __restrict__ dres, float* __restrict__ dx32,
+                                                                   __nv_bfloat16* __restrict__ dx16, float* __restrict__ dgamma,
+                                                                   float* __restrict__ dbeta, float* __restrict__ dcolsum, int rows) {
+  constexpr int D = NJ * 64;
+  __shared__ float red[3 * D];
+  const int lane = threadIdx.x & 31, grp = lane >> 4, gl = lane & 15;
+  const int wg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nwg = gridDim.x * (blockDim.x >> 5);
+  for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  float4 ag[NJ], ab[NJ], ac[NJ], gam[NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    gam[j] = *reinterpret_cast<const float4*>(gamma + j * 64 + gl * 4);
+    ag[j] = ab[j] = ac[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int rb = wg * 2; rb < rows; rb += nwg * 2) {
+    const int r = rb + grp;
+    const bool ok = r < rows;
+    const long xi = ok ? (idx ? idx[r] : r) : 0;
+    const float mean = ok ? mean_in[r] : 0.f, rstd = ok ? rstd_in[r] : 0.f;
+    float4 d[NJ], xh[NJ], e[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {   // every load of the trip is requested here, before the first use
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      d[j] = ok ? *reinterpret_cast<const float4*>(dy + (long)r * D + j * 64 + gl * 4) : z;
+      xh[j] = ok ? *reinterpret_cast<const float4*>(x + xi * D + j * 64 + gl * 4) : z;
+      e[j] = (ok && dres) ? *reinterpret_cast<const float4*>(dres + xi * D + j * 64 + gl * 4) : z;
+    }
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      if (ok) { xh[j].x = (xh[j].x - mean) * rstd; xh[j].y = (xh[j].y - mean) * rstd; xh[j].z = (xh[j].z - mean) * rstd; xh[j].w = (xh[j].w - mean) * rstd; }
+      ag[j].x += d[j].x * xh[j].x; ag[j].y += d[j].y * xh[j].y; ag[j].z += d[j].z * xh[j].z; ag[j].w += d[j].w * xh[j].w;
+      ab[j].x += d[j].x; ab[j].y += d[j].y; ab[j].z += d[j].z; ab[j].w += d[j].w;
+      d[j].x *= gam[j].x; d[j].y *= gam[j].y; d[j].z *= gam[j].z; d[j].w *= gam[j].w;          // d <- g = dy * gamma
+      s1 += (d[j].x + d[j].y) + (d[j].z + d[j].w);
+      s2 += (d[j].x * xh[j].x + d[j].y * xh[j].y) + (d[j].z * xh[j].z + d[j].w * xh[j].w);
+    }
+    s1 = group16_sum(s1) * (1.f / D); s2 = group16_sum(s2) * (1.f / D);
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      float4 o;
+      o.x = rstd * (d[j].x - s1 - xh[j].x * s2); o.y = rstd * (d[j].y - s1 - xh[j].y * s2);
+      o.z = rstd * (d[j].z - s1 - xh[j].z * s2); o.w = rstd * (d[j].w - s1 - xh[j].w * s2);
+      ac[j].x += o.x; ac[j].y += o.y; ac[j].z += o.z; ac[j].w += o.w;
+      if (ok) {
+        o.x += e[j].x; o.y += e[j].y; o.z += e[j].z; o.w += e[j].w;
+        if (dx32) *reinterpret_cast<float4*>(dx32 + xi * D + j * 64 + gl * 4) = o;
+        if (dx16) *reinterpret_cast<uint2*>(dx16 + xi * D + j * 64 + gl * 4) = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+      }
+    }
+  }
+  // fold the 2 row groups of the warp, then the warps of the block, then one atomic per column per block
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    float a4[4] = {ag[j].x, ag[j].y, ag[j].z, ag[j].w}, b4[4] = {ab[j].x, ab[j].y, ab[j].z, ab[j].w}, c4[4] = {ac[j].x, ac[j].y, ac[j].z, ac[j].w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float a = a4[k] + __shfl_xor_sync(0xffffffffu, a4[k], 16), b = b4[k] + __shfl_xor_sync(0xffffffffu, b4[k], 16),
+                  c = c4[k] + __shfl_xor_sync(0xffffffffu, c4[k], 16);
+      if (grp == 0) {
+        const int col = j * 64 + gl * 4 + k;
+        atomicAdd(&red[col], a); atomicAdd(&red[D + col], b); atomicAdd(&red[2 * D + col], c);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    if (dgamma) atomicAdd(dgamma + i, red[i]);
+    if (dbeta) atomicAdd(dbeta + i, red[D + i]);
+    if (dcolsum) atomicAdd(dcolsum + i, red[2 * D + i]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ column sums
 // out[n] += sum_t x[t, n]   (bias gradients of in_proj / linear1).  grid (row chunks, column groups of 2048 columns).
 // The 256 threads of a block are laid out as ncx column chunks (8 columns = one 16-byte load each) x nry rows, so narrow
@@ -496,6 +585,14 @@ extern "C" int cb_layernorm_bwd(const float* dy, const float* x, const int* idx,
 #define LNBG(N) layernorm_bwd_g8_kernel<N><<<gblocks, 256, 0, STREAM>>>(dy, x, idx, gamma, mean, rstd, dres, dx_f32, BFM(dx_bf16), dgamma, dbeta, dcolsum, rows)
   int gblocks = (rows + 31) / 32;
   if (gblocks > num_sms() * 4) gblocks = num_sms() * 4;
+  // D = 192 / 256: 16 lanes per row (two resident blocks per SM); `variant` (A/B, tests): 8 forces the 8-lane kernel
+  static const int variant = [] { const char* e = getenv("CB_LN_BWD_LANES"); return e ? atoi(e) : 0; }();
+  int g16blocks = (rows + 15) / 16;
+  if (g16blocks > num_sms() * 2) g16blocks = num_sms() * 2;
+#define LNBH(N) layernorm_bwd_g16_kernel<N><<<g16blocks, 256, 0, STREAM>>>(dy, x, idx, gamma, mean, rstd, dres, dx_f32, BFM(dx_bf16), dgamma, dbeta, dcolsum, rows)
+  if (variant != 8 && (D == 192 || D == 256)) { if (D == 192) LNBH(3); else LNBH(4); }
+  else
+#undef LNBH
   if (D == 64) LNBG(1); else if (D == 128) LNBG(2); else if (D == 192) LNBG(3); else if (D == 256) LNBG(4);
   else if (D <= 256) LNB(1); else if (D <= 512) LNB(2); else LNB(4);
 #undef LNBG
