@@ -173,9 +173,9 @@ def _worker(rank, world, port, out, overlap):
         b = _batch(COUNTS[rank], 500 + 50 * rank + step, dev=f"cuda:{rank}")
         losses.append(m.fused_train_step(b).item())
         if step == 0:
-            g_bb, g_hd = m.backbone.arena.grad.clone(), m.head.arena.grad.clone()
+            g_bb, g_hd, center1 = m.backbone.arena.grad.clone(), m.head.arena.grad.clone(), m.dino_loss_func.center.clone()
     torch.cuda.synchronize()
-    res = {"loss": losses, "g_bb": g_bb.cpu() / world, "g_hd": g_hd.cpu() / world, "center": m.dino_loss_func.center.cpu(),
+    res = {"loss": losses, "g_bb": g_bb.cpu() / world, "g_hd": g_hd.cpu() / world, "center1": center1.cpu(), "center": m.dino_loss_func.center.cpu(),
            "params": {k: v.detach().cpu() for k, v in m.named_parameters()}}
     torch.save(res, f"{out}.{rank}")
     dist.barrier()
@@ -204,13 +204,18 @@ def test_two_rank_step_equals_single_process_on_concatenated_batch(tmp_path, ove
         losses.append(single.fused_train_step((crops, None, [COUNTS[0] + COUNTS[1]] * 3)).item())
         if step == 0:
             g_bb, g_hd = single.backbone.arena.grad.clone().cpu(), single.head.arena.grad.clone().cpu()
+            center1 = single.dino_loss_func.center.clone().cpu()
     torch.cuda.synchronize()
     assert abs((r0["loss"][0] + r1["loss"][0]) / 2 - losses[0]) < 5e-5            # same parameters: mean of the rank losses == loss of the whole batch
     assert abs((r0["loss"][1] + r1["loss"][1]) / 2 - losses[1]) < LOSS_TOL        # after one Adam step (fp32 atomics order, see LOSS_TOL)
     assert torch.equal(r0["g_bb"], r1["g_bb"]) and torch.equal(r0["g_hd"], r1["g_hd"])          # all-reduced: bit-identical on both ranks
     assert rel_err(r0["g_bb"], g_bb) < 2e-3 and rel_err(r0["g_hd"], g_hd) < 2e-3                # == gradient of the mean loss
-    assert torch.equal(r0["center"], r1["center"])
-    assert (r0["center"] - single.dino_loss_func.center.cpu()).abs().max().item() < 1e-6
+    # centre: after step 1 the teachers are identical, so the all-reduced batch mean must equal the single process's to rounding;
+    # after step 2 the teacher has absorbed (1 - tau) of a student that took one Adam step on gradients that differ in their last
+    # bits (split-K / atomic order: per-rank batches vs the concatenated one), which Adam's first step turns into +-lr (see LOSS_TOL)
+    assert torch.equal(r0["center1"], r1["center1"]) and torch.equal(r0["center"], r1["center"])
+    assert (r0["center1"] - center1).abs().max().item() < 1e-6
+    assert (r0["center"] - single.dino_loss_func.center.cpu()).abs().max().item() < 2e-4
     for k, v in single.named_parameters():
         assert torch.equal(r0["params"][k], r1["params"][k]), k                                   # replicas stay bit-identical
         assert (r0["params"][k] - v.detach().cpu()).abs().max().item() <= 5e-3 * max(1.0, v.detach().abs().max().item()), k
