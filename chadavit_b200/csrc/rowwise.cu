@@ -297,6 +297,116 @@ __global__ void __launch_bounds__(256) layernorm2_fwd_g8_kernel(const float* __r
   }
 }
 
+
+// ---- 16 lanes per row (a lane owns 4 consecutive columns of every 64-column block; a warp = 2 rows per trip): half the per-lane
+// state of the 8-lane kernels above, i.e. more resident blocks per SM for kernels that only stream memory (see layernorm_bwd_g16).
+__device__ __forceinline__ float group16_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 4); v += __shfl_xor_sync(0xffffffffu, v, 8);
+  return v;
+}
+__device__ __forceinline__ float sum4(const float4& a) { return (a.x + a.y) + (a.z + a.w); }
+__device__ __forceinline__ float sq4(const float4& a, float m) {
+  const float x = a.x - m, y = a.y - m, z = a.z - m, w = a.w - m;
+  return (x * x + y * y) + (z * z + w * w);
+}
+__device__ __forceinline__ float4 affine4(const float4& a, float m, float r, const float4& g, const float4& b) {
+  return make_float4((a.x - m) * r * g.x + b.x, (a.y - m) * r * g.y + b.y, (a.z - m) * r * g.z + b.z, (a.w - m) * r * g.w + b.w);
+}
+
+template <int NJ>
+__global__ void __launch_bounds__(256, 4) layernorm_fwd_g16_kernel(const float* __restrict__ x, const int* __restrict__ in_idx,
+                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                   __nv_bfloat16* __restrict__ y, float* __restrict__ y32,
+                                                                   float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows, float eps) {
+  constexpr int D = NJ * 64;
+  const int lane = threadIdx.x & 31, grp = lane >> 4, gl = lane & 15;
+  const int wg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nwg = gridDim.x * (blockDim.x >> 5);
+  float4 gg[NJ], bb[NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    gg[j] = *reinterpret_cast<const float4*>(gamma + j * 64 + gl * 4);
+    bb[j] = *reinterpret_cast<const float4*>(beta + j * 64 + gl * 4);
+  }
+  for (int rb = wg * 2; rb < rows; rb += nwg * 2) {
+    const int r = rb + grp;
+    const bool ok = r < rows;
+    const long src = ok ? (in_idx ? in_idx[r] : r) : 0;
+    float4 v[NJ];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) v[j] = ok ? *reinterpret_cast<const float4*>(x + src * D + j * 64 + gl * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) s += sum4(v[j]);
+    const float mean = group16_sum(s) * (1.f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) q += sq4(v[j], mean);
+    const float rstd = rsqrtf(group16_sum(q) * (1.f / D) + eps);
+    if (ok) {
+      if (gl == 0) { if (mean_out) mean_out[r] = mean; if (rstd_out) rstd_out[r] = rstd; }
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const float4 o = affine4(v[j], mean, rstd, gg[j], bb[j]);
+        if (y) *reinterpret_cast<uint2*>(y + (long)r * D + j * 64 + gl * 4) = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+        if (y32) *reinterpret_cast<float4*>(y32 + (long)r * D + j * 64 + gl * 4) = o;
+      }
+    }
+  }
+}
+
+template <int NJ>
+__global__ void __launch_bounds__(256, 4) layernorm2_fwd_g16_kernel(const float* __restrict__ x, const float* __restrict__ gamma_a,
+                                                                    const float* __restrict__ beta_a, float eps_a, const float* __restrict__ gamma_b,
+                                                                    const float* __restrict__ beta_b, float eps_b, float* __restrict__ y1,
+                                                                    __nv_bfloat16* __restrict__ y2, float* __restrict__ mean_a,
+                                                                    float* __restrict__ rstd_a, float* __restrict__ mean_b, float* __restrict__ rstd_b,
+                                                                    int rows) {
+  constexpr int D = NJ * 64;
+  const int lane = threadIdx.x & 31, grp = lane >> 4, gl = lane & 15;
+  const int wg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nwg = gridDim.x * (blockDim.x >> 5);
+  for (int rb = wg * 2; rb < rows; rb += nwg * 2) {
+    const int r = rb + grp;
+    const bool ok = r < rows;
+    float4 v[NJ];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) v[j] = ok ? *reinterpret_cast<const float4*>(x + (long)r * D + j * 64 + gl * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) s += sum4(v[j]);
+    const float m_a = group16_sum(s) * (1.f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) q += sq4(v[j], m_a);
+    const float r_a = rsqrtf(group16_sum(q) * (1.f / D) + eps_a);
+    s = 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      v[j] = affine4(v[j], m_a, r_a, *reinterpret_cast<const float4*>(gamma_a + j * 64 + gl * 4), *reinterpret_cast<const float4*>(beta_a + j * 64 + gl * 4));
+      s += sum4(v[j]);
+      if (ok && y1) *reinterpret_cast<float4*>(y1 + (long)r * D + j * 64 + gl * 4) = v[j];
+    }
+    const float m_b = group16_sum(s) * (1.f / D);
+    q = 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) q += sq4(v[j], m_b);
+    const float r_b = rsqrtf(group16_sum(q) * (1.f / D) + eps_b);
+    if (ok) {
+      if (gl == 0) {
+        if (mean_a) mean_a[r] = m_a;
+        if (rstd_a) rstd_a[r] = r_a;
+        if (mean_b) mean_b[r] = m_b;
+        if (rstd_b) rstd_b[r] = r_b;
+      }
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const float4 o = affine4(v[j], m_b, r_b, *reinterpret_cast<const float4*>(gamma_b + j * 64 + gl * 4), *reinterpret_cast<const float4*>(beta_b + j * 64 + gl * 4));
+        *reinterpret_cast<uint2*>(y2 + (long)r * D + j * 64 + gl * 4) = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+      }
+    }
+  }
+}
+
 template <int NJ>
 __global__ void __launch_bounds__(256) layernorm_bwd_g8_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                                const int* __restrict__ idx, const float* __restrict__ gamma,
@@ -385,11 +495,6 @@ __global__ void __launch_bounds__(256) layernorm_bwd_g8_kernel(const float* __re
 // registers, i.e. ONE 8-warp block per SM for a kernel that only streams memory, and its `dres` loads are issued after the row
 // reduction (two dependent memory phases per trip): 3.7 TB/s.  Half the columns per lane halve all of that (two blocks per SM),
 // and dres is requested together with dy and x.
-__device__ __forceinline__ float group16_sum(float v) {
-  v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2);
-  v += __shfl_xor_sync(0xffffffffu, v, 4); v += __shfl_xor_sync(0xffffffffu, v, 8);
-  return v;
-}
 template <int NJ>
 __global__ void __launch_bounds__(256, 2) layernorm_bwd_g16_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                                    const int* __restrict__ idx, const float* __restrict__ gamma,
@@ -553,6 +658,13 @@ extern "C" int cb_layernorm_fwd(const float* x, const int* in_idx, const float* 
 #define LNFG(N) layernorm_fwd_g8_kernel<N><<<gblocks, 256, 0, STREAM>>>(x, in_idx, gamma, beta, BFM(y), y_f32, mean, rstd, rows, eps)
   int gblocks = (rows + 31) / 32;
   if (gblocks > num_sms() * 8) gblocks = num_sms() * 8;
+  static const int variant = [] { const char* e = getenv("CB_LN_FWD_LANES"); return e ? atoi(e) : 0; }();   // 8 forces the 8-lane kernels (A/B)
+  int hblocks = (rows + 15) / 16;
+  if (hblocks > num_sms() * 8) hblocks = num_sms() * 8;
+#define LNFH(N) layernorm_fwd_g16_kernel<N><<<hblocks, 256, 0, STREAM>>>(x, in_idx, gamma, beta, BFM(y), y_f32, mean, rstd, rows, eps)
+  if (variant != 8 && (D == 192 || D == 256)) { if (D == 192) LNFH(3); else LNFH(4); }
+  else
+#undef LNFH
   if (D == 64) LNFG(1); else if (D == 128) LNFG(2); else if (D == 192) LNFG(3); else if (D == 256) LNFG(4);
   else if (D <= 256) LNF(1); else if (D <= 512) LNF(2); else LNF(4);
 #undef LNFG
@@ -568,6 +680,13 @@ extern "C" int cb_layernorm2_fwd(const float* x, const float* gamma_a, const flo
   int gblocks = (rows + 31) / 32;
   if (gblocks > num_sms() * 8) gblocks = num_sms() * 8;
 #define LN2G(N) layernorm2_fwd_g8_kernel<N><<<gblocks, 256, 0, STREAM>>>(x, gamma_a, beta_a, eps_a, gamma_b, beta_b, eps_b, y1_f32, BFM(y2_bf16), mean_a, rstd_a, mean_b, rstd_b, rows)
+  static const int variant = [] { const char* e = getenv("CB_LN_FWD_LANES"); return e ? atoi(e) : 0; }();
+  int hblocks = (rows + 15) / 16;
+  if (hblocks > num_sms() * 8) hblocks = num_sms() * 8;
+#define LN2H(N) layernorm2_fwd_g16_kernel<N><<<hblocks, 256, 0, STREAM>>>(x, gamma_a, beta_a, eps_a, gamma_b, beta_b, eps_b, y1_f32, BFM(y2_bf16), mean_a, rstd_a, mean_b, rstd_b, rows)
+  if (variant != 8 && (D == 192 || D == 256)) { if (D == 192) LN2H(3); else LN2H(4); }
+  else
+#undef LN2H
   if (D == 64) LN2G(1); else if (D == 128) LN2G(2); else if (D == 192) LN2G(3); else LN2G(4);
 #undef LN2G
   CB_CUDA(cudaGetLastError());

@@ -236,6 +236,7 @@ def main():
     # ---- row-wise
     gam, bet = torch.ones(D, device=dev), torch.zeros(D, device=dev)
     report("layernorm fwd f32 -> bf16+f32", timeit(lambda: ops.layernorm_fwd(x32, gam, bet, 1e-5, out_f32=True)), 0, T * D * (4 + 2 + 4))
+    report("layernorm2 fwd f32 -> f32 + bf16 (norm2 + next norm1)", timeit(lambda: ops.layernorm2_fwd(x32, gam, bet, 1e-5, gam, bet, 1e-5)), 0, T * D * (4 + 4 + 2))
     _, _, mean, rstd = ops.layernorm_fwd(x32, gam, bet, 1e-5)
     dg, db, dc = (torch.zeros(D, device=dev) for _ in range(3))
     report("layernorm bwd f32 (+dres) -> f32+bf16", timeit(lambda: ops.layernorm_bwd(x32, x32, gam, mean, rstd, dgamma=dg, dbeta=db, dcolsum=dc, dres=x32, want_bf16=True)), 0, T * D * (4 * 3 + 4 + 2))
