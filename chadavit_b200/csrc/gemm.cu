@@ -238,7 +238,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const bool has_res = mode == EM_F32 && (g.flags & CB_EPI_RESIDUAL_F32);
       // EM_BF16_MASK: fused bias gradient of linear1 = column sums of the STORED (masked, bf16-rounded) values.  Lane c of this
       // warp accumulates column 32 sl + c of its slabs over all row tiles of the CTA (the column tile is fixed), one atomic each
-      // at the end.  csum[j] belongs to slab half + 2 j.
+      // at the end.  csum[j] belongs to this warp's j-th slab (s0 .. s3 below).
       float csum[4] = {0.f, 0.f, 0.f, 0.f};
       int it = 0;
       for (int tile = WRES ? w_m_first : blockIdx.x; tile < (WRES ? num_m : num_tiles); tile += (WRES ? w_m_step : gridDim.x), ++it) {
@@ -345,8 +345,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         };
         // this warp's slabs (BN <= 256: at most four): PAIRS of adjacent slabs, so that a thread writes 128 contiguous bytes of a
-        // bf16 row (a whole line) back to back instead of leaving every line half-written until the partner warp gets to it
-        const int s0 = 2 * half, s1 = 2 * half + 1, s2 = 2 * half + 4, s3 = 2 * half + 5;
+        // bf16 row (a whole line) back to back instead of leaving every line half-written until the partner warp gets to it.
+        // BN = 192 has six slabs: dealt in pairs that is {0,1,4,5} / {2,3} — one warp of every lane quarter does twice the work
+        // of its partner and the tile's epilogue takes four slab times — so there the warps take three consecutive slabs each.
+        constexpr bool TRI = (BN == 192);
+        const int s0 = TRI ? 3 * half : 2 * half, s1 = s0 + 1, s2 = TRI ? s0 + 2 : 2 * half + 4, s3 = TRI ? 1 << 20 : 2 * half + 5;
         uint32_t xa[32], xb[32], ma[NAUX], mb[NAUX];
         if (mode != EM_BF16) { if (s0 < n_slabs) aux_load(ma, s0); if (s1 < n_slabs) aux_load(mb, s1); }
         mbar_wait(&acc_full[buf], aph);
@@ -361,7 +364,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       if (mode == EM_BF16_MASK && g.colsum) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int sj = 2 * half + (j & 1) + 4 * (j >> 1);
+          const int sj = (BN == 192) ? (j < 3 ? 3 * half + j : 1 << 20) : 2 * half + (j & 1) + 4 * (j >> 1);   // the slab csum[j] belongs to (s0 .. s3 above)
           const int col = n0 + sj * 32 + lane;
           if (sj < n_slabs && col < g.N) atomicAdd(g.colsum + col, csum[j]);
         }
