@@ -560,11 +560,14 @@ def main():
     # ---- timed region 2: end to end through the public API from pinned host buffers (new ragged batch every step)
     host_pools = make_pools(1234 + rank, dev, pin=True)
     for _ in range(2):
-        model.fused_train_step(model.stage_batch(next_batch(host_pools))).item()
+        model.fused_train_step(model.stage_batch(next_batch(host_pools)), loss_to_host=True).item()
     sync()
     # Every step's crops are copied from pinned host memory inside the timed region (K copies for K steps) and every step's
-    # loss is read back; DINO.stage_batch issues the copy of batch i+1 on the engine's copy stream right after step i has
-    # been launched, so it runs under that step's compute (the first copy is exposed).
+    # loss is read by the host; DINO.stage_batch issues the copy of batch i+1 on the engine's copy stream right after step i has
+    # been launched, so it runs under that step's compute (the first copy is exposed).  The loss travels through
+    # fused_train_step(loss_to_host=True): its 4 bytes are copied to pinned memory right behind the loss kernel, and .item() waits
+    # for that copy alone — a plain tensor.item() queues its copy behind the whole step and lets the launch queue run dry
+    # (+1.1 ms per step, tools/e2e_probe.py; the serial loop below still reads that way).
     h2d = 0
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
@@ -572,12 +575,12 @@ def main():
     h2d += sum(c.numel() * 4 for c in nb[0])
     nxt = model.stage_batch(nb)
     for i in range(args.steps):
-        l = model.fused_train_step(nxt)        # waits for its H2D on the device, then the step
+        l = model.fused_train_step(nxt, loss_to_host=True)        # waits for its H2D on the device, then the step
         if i + 1 < args.steps:
             nb = next_batch(host_pools)
             h2d += sum(c.numel() * 4 for c in nb[0])
             nxt = model.stage_batch(nb)
-        _ = l.item()                           # D2H read of the step's loss
+        _ = l.item()                           # host read of THIS step's loss (D2H issued mid-step)
     e3.record()
     sync()
     ms_e2e = e2.elapsed_time(e3)
@@ -742,7 +745,9 @@ def main():
         "clocks": clk.summary(),
         "e2e": {"value": imgs * args.steps / (ms_e2e * 1e-3), "unit": "imgs/s", "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps, "ms_per_step_serial_copy": ms_e2e_serial,
-                "pipeline": "H2D of batch i+1 on a copy stream under the compute of batch i (DINO.stage_batch), 2 device buffer sets"},
+                "pipeline": "H2D of batch i+1 on a copy stream under the compute of batch i (DINO.stage_batch), 2 device buffer sets; every "
+                            "step's loss copied to pinned memory right behind the loss kernel and read by the host in the same iteration "
+                            "(fused_train_step(loss_to_host=True))"},
         "gpu_launches": launches,
         "roofline": roofline,
         "attn_tflops": {"fwd": roof["cb_attn_varlen_fwd"]["achieved_tflops"], "bwd": roof["cb_attn_varlen_bwd"]["achieved_tflops"],

@@ -49,6 +49,8 @@ class ParamArena:
         self.bf16 = torch.empty(self.numel, device=dev, dtype=torch.bfloat16) if dev.type == "cuda" else None
         self.grad = None
         self._bf16_key = None
+        self._views32, self._views16 = {}, {}     # per-name views of the two arenas (rebuilt with the arenas)
+        self._viewsg_of, self._viewsg = None, {}
 
     def ensure(self) -> None:
         """Re-flatten if some code replaced ``p.data`` (e.g. ``.to()``, the reference's EMA ``mp.data = ...``)."""
@@ -70,17 +72,34 @@ class ParamArena:
             self._bf16_key = key
 
     # ------------------------------------------------------------------ views
+    # The views are cached: a training step asks for ~800 of them, and slice + view cost ~5 us each on the host.
     def v32(self, name: str) -> torch.Tensor:
-        off, n, shape = self.offsets[name]
-        return self.fp32[off:off + n].view(shape)
+        t = self._views32.get(name)
+        if t is None:
+            off, n, shape = self.offsets[name]
+            t = self._views32[name] = self.fp32[off:off + n].view(shape)
+        return t
 
     def v16(self, name: str) -> torch.Tensor:
-        off, n, shape = self.offsets[name]
-        return self.bf16[off:off + n].view(shape)
+        t = self._views16.get(name)
+        if t is None:
+            off, n, shape = self.offsets[name]
+            t = self._views16[name] = self.bf16[off:off + n].view(shape)
+        return t
 
     def g32(self, name: str, grad_flat: torch.Tensor) -> torch.Tensor:
+        """View of parameter `name` inside an arena-shaped gradient buffer.  Cached only for the arena's OWN gradient buffer (the
+        engine's persistent one), keyed by object identity: a view can never alias memory it was not made for, and temporary
+        buffers (tests, the autograd bridge) are not kept alive by a cache."""
         off, n, shape = self.offsets[name]
-        return grad_flat[off:off + n].view(shape)
+        if grad_flat is not self.grad or grad_flat is None:
+            return grad_flat[off:off + n].view(shape)
+        if self._viewsg_of is not grad_flat:
+            self._viewsg_of, self._viewsg = grad_flat, {}
+        t = self._viewsg.get(name)
+        if t is None:
+            t = self._viewsg[name] = grad_flat[off:off + n].view(shape)
+        return t
 
     def segment_maps(self):
         """(seg_start_block int32 [P+1], seg_of_block int32 [numel/64]) on the arena's device: which parameter owns each

@@ -200,6 +200,24 @@ class StagedBatch(tuple):
         return self
 
 
+class HostLoss:
+    """The loss of one ``fused_train_step(..., loss_to_host=True)`` on its way to the host: a 4-byte copy into pinned memory issued
+    in stream order right behind the loss kernel (the backward and the optimizer are still queued behind it) plus the event that
+    marks it.  ``item()`` / ``float()`` wait for THAT event only — a plain ``loss.item()`` enqueues its copy behind everything the
+    host has already queued (the whole step) and lets the launch queue run dry every step (+1.1 ms per 40 ms step)."""
+    __slots__ = ("buf", "event")
+
+    def __init__(self):
+        self.buf = torch.zeros(1, dtype=torch.float32).pin_memory()
+        self.event = torch.cuda.Event()
+
+    def item(self) -> float:
+        self.event.synchronize()
+        return float(self.buf[0])
+
+    __float__ = item
+
+
 class DINO(nn.Module):
     """DINO method without the Lightning shell: same sub-module names as the reference LightningModule
     (``backbone``, ``momentum_backbone``, ``head``, ``momentum_head``, ``dino_loss_func``, ``momentum_updater``) so
@@ -274,6 +292,7 @@ class DINO(nn.Module):
         # other's launch gaps and tails (every kernel is one persistent wave)
         self.overlap_forward = bool(_cfg(cfg, "engine.overlap_forward", True))
         self._side: Optional[List[torch.cuda.Stream]] = None
+        self._host_losses: Optional[List["HostLoss"]] = None     # fused_train_step(loss_to_host=True): four rotating pinned slots
         self._graphs: "collections.OrderedDict[tuple, dict]" = collections.OrderedDict()
         self._staging: Optional[dict] = None
         self._comm: Optional[torch.cuda.Stream] = None
@@ -466,7 +485,7 @@ class DINO(nn.Module):
 
     @torch.no_grad()
     def _step_device_work(self, X, list_num_channels, *, lr: float, tau: float, step: int, world: int, dev_hyper=None,
-                          step_late: Optional[int] = None) -> torch.Tensor:
+                          step_late: Optional[int] = None, host_loss: Optional["HostLoss"] = None) -> torch.Tensor:
         """All device work of one step (zero grads .. fused AdamW+EMA); no host-side state is touched, so the sequence can be
         captured once into a CUDA graph and replayed (per-step scalars then come from ``dev_hyper``)."""
         nl = self.num_large_crops
@@ -533,6 +552,9 @@ class DINO(nn.Module):
         L = self.dino_loss_func
         temp = float(L.teacher_temp_schedule[L.epoch])
         loss, _, d16 = ops.dino_loss_fwd_bwd(logits, tlogits, L.center.view(-1), L.num_large_crops, L.student_temp, temp)
+        if host_loss is not None:            # D2H of the loss right here: the host can read it while the backward is still running
+            host_loss.buf.copy_(loss.reshape(-1)[:1], non_blocking=True)
+            host_loss.event.record(cur)
         # Collectives (C1 gradient mean, C2 centre) run on a side stream under the backward kernels: the centre sum right away,
         # the head arena once the head is differentiated, the backbone arena in buckets as the blocks retire.  The compute
         # stream joins the side stream once, in front of the optimizer.
@@ -630,13 +652,16 @@ class DINO(nn.Module):
         return StagedBatch((s["x"], targets, list_num_channels), s)
 
     @torch.no_grad()
-    def fused_train_step(self, batch: Sequence[Any], lr: Optional[float] = None) -> torch.Tensor:
+    def fused_train_step(self, batch: Sequence[Any], lr: Optional[float] = None, loss_to_host: bool = False):
         """One complete DINO step (forward, loss, backward, gradient all-reduce, AdamW, teacher EMA, tau update) without an
         autograd graph.  Semantics identical to training_step + on_after_backward + AdamW.step + on_train_batch_end.
 
         With ``self.use_cuda_graph`` the device work of a batch *signature* (channel counts per crop + shapes) is captured
         into a CUDA graph the second time that signature is seen and replayed afterwards (inputs are copied into static
-        buffers; lr / bias corrections / tau are read from device memory), which removes the per-launch host overhead."""
+        buffers; lr / bias corrections / tau are read from device memory), which removes the per-launch host overhead.
+
+        ``loss_to_host=True`` returns a :class:`HostLoss` instead of the device tensor: the loss is copied to pinned host memory
+        right behind the loss kernel, and ``.item()`` waits for that copy alone (four handles rotate: read each within 3 steps)."""
         staged = batch.set if isinstance(batch, StagedBatch) else None
         X, _targets, list_num_channels = batch
         X = [X] if isinstance(X, torch.Tensor) else list(X)
@@ -656,12 +681,20 @@ class DINO(nn.Module):
         tau = self.momentum_updater.cur_tau
         step, step_late = self.global_step, max(1, self.last_layer_steps)
         loss = None
+        hl = None
+        if loss_to_host:
+            if self._host_losses is None:
+                self._host_losses = [HostLoss() for _ in range(4)]
+            hl = self._host_losses[self.global_step % 4]
         if self.use_cuda_graph:
             loss = self._graph_step(X, list_num_channels, lr, tau, step, step_late, world)
+            if loss is not None and hl is not None:      # replayed graph: the copy follows the replay in stream order
+                hl.buf.copy_(loss.reshape(-1)[:1], non_blocking=True)
+                hl.event.record()
         if loss is None:
             dev = bb.arena.fp32.device
             X = [x if x.is_cuda else x.to(dev, non_blocking=True) for x in X]    # host (pinned) crops are accepted
-            loss = self._step_device_work(X, list_num_channels, lr=lr, tau=tau, step=step, step_late=step_late, world=world)
+            loss = self._step_device_work(X, list_num_channels, lr=lr, tau=tau, step=step, step_late=step_late, world=world, host_loss=hl)
         if staged is not None:
             staged["consumed"] = torch.cuda.Event()
             staged["consumed"].record()
@@ -669,7 +702,7 @@ class DINO(nn.Module):
             ar.mark_dirty()
             ar._bf16_key = (ar.manual_version, sum(p._version for p in ar.params))   # shadows were refreshed by the kernel
         self.momentum_updater.update_tau(cur_step=self.global_step, max_steps=self.max_steps)
-        return loss[0]
+        return hl if hl is not None else loss[0]
 
     def _graph_step(self, X, list_num_channels, lr, tau, step, step_late, world):
         L = self.dino_loss_func

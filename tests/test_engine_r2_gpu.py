@@ -158,6 +158,25 @@ def test_engine_state_dict_round_trip():
         assert d.mean().item() < 1.5e-3 and d.max().item() < 9e-3, k
 
 
+@pytest.mark.parametrize("graph", [False, True])
+def test_loss_to_host_handle_returns_the_device_loss(graph):
+    """fused_train_step(loss_to_host=True) hands back the SAME loss through pinned memory (copied right behind the loss kernel,
+    readable while the backward is still queued); eager steps and CUDA-graph replays."""
+    a, b = _build(_cfg(freeze=0, graph=graph)), _build(_cfg(freeze=0, graph=graph))
+    for step in range(4):            # the same batch signature: with graph=True steps 2, 3 are replays
+        la = a.fused_train_step(_batch([2, 1, 3], 700 + step))
+        lb = b.fused_train_step(_batch([2, 1, 3], 700 + step), loss_to_host=True)
+        assert not isinstance(lb, torch.Tensor) and lb.item() == float(lb)
+        if step == 0:
+            assert lb.item() == la.item()                   # same parameters, deterministic forward: the very same number
+        else:                                               # two engines drift in the last bits after an optimizer step (see LOSS_TOL)
+            assert abs(lb.item() - la.item()) < LOSS_TOL
+    # one engine: the handle and the device tensor of the SAME step (the handle's slot is filled mid-step)
+    hl = b.fused_train_step(_batch([2, 1, 3], 710), loss_to_host=True)
+    torch.cuda.synchronize()
+    assert hl.buf.item() == hl.item()
+
+
 # ---------------------------------------------------------------------------------------------------- 2 ranks, NCCL
 COUNTS = [[1, 3, 2], [4, 1, 2]]     # per-rank images
 
