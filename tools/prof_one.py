@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Launch ONE kernel class a few times so that `ncu --set full` can capture it in isolation.
-    python tools/prof_one.py fc1|qkv|dh|fc2|attn_fwd|attn_bwd|ffn|ffn_save"""
+    python tools/prof_one.py fc1|qkv|dh|fc2|attn_fwd|attn_bwd|ffn|ffn_save|ffn_bwd|ln_bwd"""
 import os
 import sys
 
@@ -30,6 +30,15 @@ fns = {
     "ffn": lambda: ops.ffn_fwd(x16, w1, b1, w2, b2, x32, save_hidden=False),
     "ffn_save": lambda: ops.ffn_fwd(x16, w1, b1, w2, b2, x32, save_hidden=True),
 }
+if which == "ffn_bwd":
+    bits = torch.randint(-2 ** 31, 2 ** 31 - 1, (F // 32, (T + 31) // 32 * 32), device=dev, dtype=torch.int32)
+    fns["ffn_bwd"] = lambda: ops.ffn_bwd(x16, w2, w1, bits, x32)
+if which == "ln_bwd":
+    gam = torch.ones(D, device=dev)
+    _, _, mean, rstd = ops.layernorm_fwd(x32, gam, torch.zeros(D, device=dev), 1e-5)
+    dy32, dres32 = torch.randn(T, D, device=dev), torch.randn(T, D, device=dev)
+    acc = [torch.zeros(D, device=dev) for _ in range(3)]
+    fns["ln_bwd"] = lambda: ops.layernorm_bwd(dy32, x32, gam, mean, rstd, dgamma=acc[0], dbeta=acc[1], dcolsum=acc[2], dres=dres32, want_bf16=True)
 if which == "attn_bwd":
     out, lse = ops.attn_fwd(qkv, lay, 2)
     fns["attn_bwd"] = lambda: ops.attn_bwd(do, qkv, out, lse, lay, 2)
