@@ -21,6 +21,7 @@ SIGNATURES = {
     "cb_sync_check": [_vp],
     "cb_attn_schedule": [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp],
     "cb_gemm_bf16": [_vp, _i, _i, _vp, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _f, _i, _vp, _vp],
+    "cb_gemm_ln_fwd": [_vp, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp],
     "cb_ffn_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "cb_ffn_bwd": [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp],
     "cb_im2col_bf16": [_vp, _vp, _i, _i, _i, _i, _vp],

@@ -262,8 +262,12 @@ class ChAdaViT(nn.Module):
             u, _, m1a, r1a = ops.layernorm_fwd(x, g1, b1, eps, save_stats=save)
         qkv = ops.gemm(u, a.v16(pre + "self_attn.in_proj_weight"), bias=a.v32(pre + "self_attn.in_proj_bias"))
         att, lse = ops.attn_fwd(qkv, lay, self.num_heads, need_lse=save)
-        z1 = ops.gemm(att, a.v16(pre + "self_attn.out_proj.weight"), bias=a.v32(pre + "self_attn.out_proj.bias"), aux=x, flags=R)
-        y, y32, m1b, r1b = ops.layernorm_fwd(z1, g1, b1, eps, out_f32=True, save_stats=save)
+        if ops.gemm_ln_ok(x.shape[0], x.shape[1], x.shape[1]):   # out-projection + residual + second use of norm1 in ONE kernel
+            z1, y, y32, m1b, r1b = ops.gemm_ln_fwd(att, a.v16(pre + "self_attn.out_proj.weight"), a.v32(pre + "self_attn.out_proj.bias"), x,
+                                                    g1, b1, eps, keep_z=save, save_stats=save)
+        else:
+            z1 = ops.gemm(att, a.v16(pre + "self_attn.out_proj.weight"), bias=a.v32(pre + "self_attn.out_proj.bias"), aux=x, flags=R)
+            y, y32, m1b, r1b = ops.layernorm_fwd(z1, g1, b1, eps, out_f32=True, save_stats=save)
         if ops.ffn_fused_ok(x.shape[1], FFN_DIM):   # linear1 -> ReLU -> linear2 -> +residual in one kernel; hidden stored only if saved
             z2, hid, bits = ops.ffn_fwd(y, a.v16(pre + "linear1.weight"), a.v32(pre + "linear1.bias"), a.v16(pre + "linear2.weight"),
                                         a.v32(pre + "linear2.bias"), y32, save_hidden=save, save_mask_bits=save and _MASK_BITS)

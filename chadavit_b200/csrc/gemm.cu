@@ -78,11 +78,12 @@ __device__ __forceinline__ void tmem_ld1(uint32_t taddr, uint32_t& r) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
 }
 
-template <int BN, int AMODE, int BMODE, int EM, bool WRES, bool CSUM = false>
+template <int BN, int AMODE, int BMODE, int EM, bool WRES, bool CSUM = false, bool LNF = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
   using Cfg = GemmCfg<BN>;
   static_assert(!CSUM || (BN == 192 && BMODE == 1 && EM == EM_ATOMIC && !WRES), "CSUM: split-K weight-gradient product with BN = 192 and MN-major B only");
+  static_assert(!LNF || (BN == 192 && EM == EM_F32 && WRES && AMODE == 0), "LNF: weights-resident 192-wide fp32 product only");
   constexpr int B_STRIDE = Cfg::B_BYTES + (CSUM ? CSUM_ONES_BYTES : 0);   // smem distance between two B stages
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
@@ -227,6 +228,116 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // synchronisation, ~95 instead of ~170 instructions per slab; the bias of the column tile sits in smem (broadcast LDS).
     // In-kernel timeline of fc1 (profiles/r01_timeline_gemm.txt): the staged epilogue needed 1100 clk per slab, 4400 clk per
     // 128 x 256 tile against 1536 clk of MMA — the tensor pipe waited for the epilogue 60 % of the time.
+
+    // ---------------- LayerNorm fused into the row epilogue (LNF; the encoder's  y = norm1(x + attn W_o^T + b_o),  chada_vit.py:99).
+    // The 192-wide tile holds whole rows; a row is shared by the two warps of its lane quarter (columns 0..95 / 96..191), which
+    // exchange their partial sums through shared memory: once for the mean, once for the centred sum of squares (the same
+    // two-pass arithmetic as layernorm_fwd_g16_kernel).  A thread keeps its 96 values in registers: the residual is loaded INTO
+    // that buffer before the accumulator wait and every TMEM slab is folded into it in place.  Replaces the separate LayerNorm
+    // launch (36 per training step) and its read of z1; z1 itself is stored only when the caller keeps it for the backward.
+    if constexpr (LNF) {
+      float* sBias = reinterpret_cast<float*>(sEpi);
+      float* sGam = sBias + 192;
+      float* sBet = sGam + 192;
+      float* sEx = sBet + 192;                     // [tile parity 2][pass 2][half 2][128 rows]
+      for (int i = threadIdx.x; i < 192; i += 256) {
+        sBias[i] = g.bias != nullptr ? __ldg(g.bias + i) : 0.f;
+        sGam[i] = __ldg(g.ln_gamma + i);
+        sBet[i] = __ldg(g.ln_beta + i);
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const bool has_res = (g.flags & CB_EPI_RESIDUAL_F32) != 0;
+      const int c0 = 96 * half;                    // this warp's columns
+      const int rr = q * 32 + lane;                // row inside the tile
+      int it = 0;
+      for (int tile = w_m_first; tile < num_m; tile += w_m_step, ++it) {
+        const int m0 = tile * BM;
+        const int buf = it & 1; const uint32_t aph = (it >> 1) & 1;
+        const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + buf * Cfg::ACC_STRIDE + c0;
+        const long row = (long)m0 + rr;
+        const bool row_ok = row < g.M;
+        uint32_t v[3][32];
+        if (row_ok && has_res) {
+          const float* rp = reinterpret_cast<const float*>(g.aux) + row * g.ld_aux + c0;
+#pragma unroll
+          for (int j = 0; j < 3; ++j)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) ldg256(rp + j * 32 + 8 * k, *reinterpret_cast<uint32_t(*)[8]>(&v[j][8 * k]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 3; ++j)
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[j][e] = 0u;
+        }
+        mbar_wait(&acc_full[buf], aph);
+        tc_fence_after();
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          uint32_t x[32];
+          tmem_ld32(t_addr + j * 32, x);
+          tmem_ld_wait();
+          if (j == 2) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&acc_empty[buf]); }   // accumulator fully read
+#pragma unroll
+          for (int e = 0; e < 32; e += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(sBias + c0 + j * 32 + e);
+            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float val = fmaf(__uint_as_float(x[e + t]), g.alpha, bb[t]) + __uint_as_float(v[j][e + t]);
+              v[j][e + t] = __float_as_uint(val);
+              s += val;
+            }
+          }
+        }
+        if (g.C != nullptr && row_ok) {
+          float* dst = reinterpret_cast<float*>(g.C) + row * g.ldc + c0;
+#pragma unroll
+          for (int j = 0; j < 3; ++j)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              stg256(dst + j * 32 + 8 * k, v[j][8 * k], v[j][8 * k + 1], v[j][8 * k + 2], v[j][8 * k + 3], v[j][8 * k + 4], v[j][8 * k + 5], v[j][8 * k + 6], v[j][8 * k + 7]);
+        }
+        float* ex = sEx + (it & 1) * 512;
+        ex[half * 128 + rr] = s;
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
+        const float mean = (ex[rr] + ex[128 + rr]) * (1.f / 192.f);
+        float qq = 0.f;
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+          for (int e = 0; e < 32; ++e) { const float d = __uint_as_float(v[j][e]) - mean; qq += d * d; }
+        ex[256 + half * 128 + rr] = qq;
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
+        const float rstd = rsqrtf((ex[256 + rr] + ex[256 + 128 + rr]) * (1.f / 192.f) + g.ln_eps);
+        if (row_ok) {
+          if (half == 0) { if (g.ln_mean) g.ln_mean[row] = mean; if (g.ln_rstd) g.ln_rstd[row] = rstd; }
+          __nv_bfloat16* d16 = g.ln_y16 + row * 192 + c0;
+          float* d32 = g.ln_y32 ? g.ln_y32 + row * 192 + c0 : nullptr;
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            uint32_t o[32];
+#pragma unroll
+            for (int e = 0; e < 32; e += 4) {
+              const float4 g4 = *reinterpret_cast<const float4*>(sGam + c0 + j * 32 + e), b4 = *reinterpret_cast<const float4*>(sBet + c0 + j * 32 + e);
+              o[e] = __float_as_uint((__uint_as_float(v[j][e]) - mean) * rstd * g4.x + b4.x);
+              o[e + 1] = __float_as_uint((__uint_as_float(v[j][e + 1]) - mean) * rstd * g4.y + b4.y);
+              o[e + 2] = __float_as_uint((__uint_as_float(v[j][e + 2]) - mean) * rstd * g4.z + b4.z);
+              o[e + 3] = __float_as_uint((__uint_as_float(v[j][e + 3]) - mean) * rstd * g4.w + b4.w);
+            }
+            if (d32) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) stg256(d32 + j * 32 + 8 * k, o[8 * k], o[8 * k + 1], o[8 * k + 2], o[8 * k + 3], o[8 * k + 4], o[8 * k + 5], o[8 * k + 6], o[8 * k + 7]);
+            }
+            uint32_t pk[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) pk[e] = pack_bf16(__uint_as_float(o[2 * e]), __uint_as_float(o[2 * e + 1]));
+            stg256(d16 + j * 32, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
+            stg256(d16 + j * 32 + 16, pk[8], pk[9], pk[10], pk[11], pk[12], pk[13], pk[14], pk[15]);
+          }
+        }
+      }
+    } else
     if ((mode == EM_BF16 || mode == EM_F32 || mode == EM_BF16_MASK) && g.direct && (WRES || num_n == 1)) {
       float* sBias = reinterpret_cast<float*>(sEpi);
       const int n0 = WRES ? w_n0 : 0;
@@ -642,7 +753,7 @@ static int encode_operand(CUtensorMap* tm, const void* base, int rows, int K, in
   return make_tmap(tm, base, 3, dims, strides, box, mode == 1 ? 3 : 2);
 }
 
-template <int BN, int AMODE, int BMODE, int EM, bool WRES, bool CSUM = false>
+template <int BN, int AMODE, int BMODE, int EM, bool WRES, bool CSUM = false, bool LNF = false>
 static int launch_k(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   const int kb_total = (g.K + BK - 1) / BK;
@@ -651,7 +762,7 @@ static int launch_k(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmAr
   static_assert(!CSUM || Cfg::SMEM_BYTES + Cfg::STAGES * CSUM_ONES_BYTES <= 227 * 1024, "CSUM: ones blocks do not fit");
   static int attr_set = 0;
   if (attr_set < smem_bytes) {
-    CB_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, AMODE, BMODE, EM, WRES, CSUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    CB_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, AMODE, BMODE, EM, WRES, CSUM, LNF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     attr_set = smem_bytes;
   }
   const int num_m = (g.M + BM - 1) / BM, num_n = (g.N + BN - 1) / BN;
@@ -661,7 +772,7 @@ static int launch_k(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmAr
     const int per_n = max(1, min(num_sms() / num_n, num_m));
     grid = per_n * num_n;
   }
-  gemm_kernel<BN, AMODE, BMODE, EM, WRES, CSUM><<<grid, GEMM_THREADS, smem_bytes, stream>>>(tmA, tmB, g);
+  gemm_kernel<BN, AMODE, BMODE, EM, WRES, CSUM, LNF><<<grid, GEMM_THREADS, smem_bytes, stream>>>(tmA, tmB, g);
   CB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -699,6 +810,7 @@ int gemm_run(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn,
   CB_CHECK(g.N % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && g.ldc % 8 == 0, "gemm: N, lda, ldb, ldc must be multiples of 8 (N=%d lda=%d ldb=%d ldc=%d)", g.N, lda, ldb, g.ldc);
   CB_CHECK((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.C) & 15) == 0,
            "gemm: operands must be 16-byte aligned");
+  CB_CHECK(g.C != nullptr || g.ln_gamma != nullptr, "gemm: output pointer is null");
   int am = 0, bm = 0;
   if (a_mn) { CB_CHECK(g.M % 32 == 0, "gemm: MN-major A needs M %% 32 == 0 (M=%d)", g.M); am = (g.M % 64 == 0) ? 1 : 2; }
   if (b_mn) { CB_CHECK(g.N % 32 == 0, "gemm: MN-major B needs N %% 32 == 0 (N=%d)", g.N); bm = (g.N % 64 == 0) ? 1 : 2; }
@@ -725,6 +837,12 @@ int gemm_run(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn,
   if (encode_operand(&tmB, B, g.N, g.K, ldb, bm, BN)) return 1;
   const int em = (g.flags & CB_EPI_TOKENIZE) ? EM_TOKENIZE : (g.flags & CB_EPI_ATOMIC) ? EM_ATOMIC : (g.flags & CB_EPI_OUT_F32) ? EM_F32
                  : (g.flags & CB_EPI_RELU_MASK) ? EM_BF16_MASK : EM_BF16;
+  if (g.ln_gamma != nullptr) {   // LayerNorm in the row epilogue (see LNF)
+    const int kbt = (g.K + BK - 1) / BK;
+    CB_CHECK(g.N == 192 && BN == 192 && am == 0 && bm == 0 && em == EM_F32 && g.k_splits == 1 && kbt <= 3 && g.M >= 4 * BM && g.direct,
+             "gemm_ln: needs N = 192, K <= 192, M >= %d, K-major operands, 32-byte aligned rows (N=%d K=%d M=%d direct=%d)", 4 * BM, g.N, g.K, g.M, g.direct);
+    return launch_k<192, 0, 0, EM_F32, true, false, true>(tmA, tmB, g, stream);
+  }
   if (g.colsum != nullptr && em == EM_ATOMIC) {   // bias gradient on the tensor pipe (see CSUM above)
     CB_CHECK(BN == 192 && am == 1 && bm == 1, "gemm: colsum with the atomic epilogue needs N %% 192 == 0 (N %% 256 != 0) and both operands MN-major "
              "with M, N multiples of 64 (N=%d M=%d a_mn=%d b_mn=%d)", g.N, g.M, a_mn, b_mn);
@@ -763,4 +881,20 @@ extern "C" int cb_gemm_bf16(const void* A, int lda, int a_mn, const void* B, int
   CB_CHECK(!(flags & CB_EPI_MASK_BITS) || ((flags & CB_EPI_RELU_MASK) && ld_aux >= M && (reinterpret_cast<uintptr_t>(aux) & 3) == 0),
            "cb_gemm_bf16: CB_EPI_MASK_BITS needs CB_EPI_RELU_MASK and a uint32 [N/32, ld_aux >= M] bit mask");
   return cb::gemm_run(A, lda, a_mn, B, ldb, b_mn, g, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int cb_gemm_ln_fwd(const void* A, int lda, const void* W, int ldw, const float* bias, const float* resid, int ld_res,
+                              const float* ln_gamma, const float* ln_beta, float ln_eps, float* z, void* y_bf16, float* y_f32, float* mean,
+                              float* rstd, int M, int N, int K, void* stream) {
+  CB_CHECK(A && W && ln_gamma && ln_beta && y_bf16, "cb_gemm_ln_fwd: null argument");
+  CB_CHECK(N == 192 && K % 8 == 0 && K <= 192 && M >= 512, "cb_gemm_ln_fwd: N must be 192, K <= 192, M >= 512 (N=%d K=%d M=%d); use cb_gemm_bf16 + cb_layernorm_fwd otherwise", N, K, M);
+  CB_CHECK(((reinterpret_cast<uintptr_t>(y_bf16) | reinterpret_cast<uintptr_t>(y_f32) | reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(resid)) & 31) == 0 &&
+           (resid == nullptr || ld_res % 8 == 0), "cb_gemm_ln_fwd: z / y / resid must be 32-byte aligned (resid pitch a multiple of 8 floats)");
+  cb::GemmArgs g{};
+  g.M = M; g.N = N; g.K = K; g.k_splits = 1; g.C = z; g.ldc = N; g.bias = bias;
+  g.aux = reinterpret_cast<const __nv_bfloat16*>(resid); g.ld_aux = ld_res; g.alpha = 1.f;
+  g.flags = CB_EPI_OUT_F32 | (resid ? CB_EPI_RESIDUAL_F32 : 0);
+  g.ln_gamma = ln_gamma; g.ln_beta = ln_beta; g.ln_eps = ln_eps; g.ln_y16 = reinterpret_cast<__nv_bfloat16*>(y_bf16); g.ln_y32 = y_f32;
+  g.ln_mean = mean; g.ln_rstd = rstd;
+  return cb::gemm_run(A, lda, 0, W, ldw, 0, g, reinterpret_cast<cudaStream_t>(stream));
 }

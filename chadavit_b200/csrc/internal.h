@@ -17,6 +17,15 @@ struct GemmArgs {
   int direct;             // set by gemm_run: C / aux are 32-byte aligned with 32-byte row pitches -> row-direct epilogue allowed
   float* colsum;          // optional fp32, accumulated.  EM_BF16_MASK: [N] column sums of the stored C (bias gradient of linear1);
                           // EM_ATOMIC (dW = dY^T X): [M] sums of op(A) over K, formed on the tensor pipe (bias gradient next to dW)
+  // LayerNorm fused into the fp32 row epilogue (cb_gemm_ln_fwd; N = 192 only): y = LN(C) with C = alpha A B^T + bias + aux.
+  // C itself is stored only when g.C != nullptr (the backward needs it; the no-grad passes do not).
+  const float* ln_gamma;  // [N]; non-null selects the fused epilogue
+  const float* ln_beta;   // [N]
+  float ln_eps;
+  __nv_bfloat16* ln_y16;  // [M, N] bf16 (next GEMM operand)
+  float* ln_y32;          // [M, N] fp32 or null (next residual)
+  float* ln_mean;         // [M] or null
+  float* ln_rstd;         // [M] or null
   // tokenizer epilogue (CB_EPI_TOKENIZE): A rows are already in packed token order (CLS rows hold zeros);
   // row t of sequence b (cu[b] <= t < cu[b+1]): off = t - cu[b]; off == 0 -> CLS row = cls_row, else
   // c = (off-1)/npatch, p = (off-1)%npatch: acc + bias + pos[p] + chan_tok[c]        (chada_vit.py:245-265)

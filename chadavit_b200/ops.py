@@ -91,6 +91,32 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     return out
 
 
+_GEMM_LN = os.environ.get("CB_NO_GEMM_LN", "") != "1"   # A/B switch (read once): LayerNorm fused into the out-projection epilogue
+
+
+def gemm_ln_ok(M: int, N: int, K: int) -> bool:
+    return _GEMM_LN and N == 192 and K <= 192 and K % 8 == 0 and M >= 512
+
+
+def gemm_ln_fwd(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], resid: Optional[torch.Tensor], gamma: torch.Tensor,
+                beta: torch.Tensor, eps: float, *, keep_z: bool, out_f32: bool = True, save_stats: bool = True):
+    """z = A W^T + bias + resid ; y = LayerNorm(z) in one kernel (N = 192).  Returns (z fp32 | None, y bf16, y fp32 | None, mean, rstd)."""
+    M, K = A.shape
+    N = W.shape[0]
+    assert A.dtype == bf16 and W.dtype == bf16 and A.stride(1) == 1 and W.stride(1) == 1 and W.shape[1] == K
+    assert resid is None or (resid.dtype == torch.float32 and resid.shape == (M, N) and resid.stride(1) == 1)
+    dev = A.device
+    z = torch.empty(M, N, device=dev, dtype=torch.float32) if keep_z else None
+    y = torch.empty(M, N, device=dev, dtype=bf16)
+    y32 = torch.empty(M, N, device=dev, dtype=torch.float32) if out_f32 else None
+    mean = torch.empty(M, device=dev, dtype=torch.float32) if save_stats else None
+    rstd = torch.empty(M, device=dev, dtype=torch.float32) if save_stats else None
+    _call("cb_gemm_ln_fwd", _p(A), A.stride(0), _p(W), W.stride(0), _p(bias), _p(resid), resid.stride(0) if resid is not None else 0,
+          _p(gamma), _p(beta), float(eps), _p(z), _p(y), _p(y32), _p(mean), _p(rstd), M, N, K, _stream(), work=2.0 * M * N * K,
+          pkey="cb_gemm_bf16", nbytes=float(M) * (K * 2 + N * (4 + 2 + (4 if out_f32 else 0) + (4 if keep_z else 0))) + 2.0 * N * K)
+    return z, y, y32, mean, rstd
+
+
 _GEMM_ROWSUM = os.environ.get("CB_NO_GEMM_ROWSUM", "") != "1"   # A/B switch (read once): bias gradients on the tensor pipe of the dW products
 
 

@@ -72,6 +72,19 @@ int cb_gemm_bf16(const void* A, int lda, int a_mn, const void* B, int ldb, int b
                  float* colsum, void* stream);
 
 /*
+ * Linear + residual + LayerNorm in one kernel — the encoder's  y = norm1(x + self_attn_out W_o^T + b_o)  (chada_vit.py:99 with
+ * nn.MultiheadAttention's out_proj, :105-111):
+ *   z = A W^T + bias + resid        A bf16 [M, K] (lda), W bf16 [N, K] (ldw), bias fp32 [N], resid fp32 [M, N] (ld_res) or NULL
+ *   y = LayerNorm(z; ln_gamma, ln_beta, ln_eps)   two-pass fp32 statistics, as cb_layernorm_fwd
+ * Outputs: y_bf16 [M, N] (required), y_f32 [M, N] or NULL, mean / rstd fp32 [M] or NULL (saved for cb_layernorm_bwd), z fp32 [M, N]
+ * or NULL (kept only when the backward needs it).  N must be 192 (the row tile of the tensor-core kernel holds whole rows),
+ * K <= 192, M >= 512; other shapes: cb_gemm_bf16 (CB_EPI_RESIDUAL_F32 | CB_EPI_OUT_F32) followed by cb_layernorm_fwd.
+ */
+int cb_gemm_ln_fwd(const void* A, int lda, const void* W, int ldw, const float* bias, const float* resid, int ld_res,
+                   const float* ln_gamma, const float* ln_beta, float ln_eps, float* z, void* y_bf16, float* y_f32, float* mean,
+                   float* rstd, int M, int N, int K, void* stream);
+
+/*
  * TokenLearner + channel_aware_tokenization (chada_vit.py:118-134, 219-270) on the packed layout.
  *   x           fp32 (G,1,H,W): channel images in one_channel_collate_fn order (channels_strategies.py:31-85)
  *   cu_seqlens  int32 [B+1];  chan_img int32 [G] = image index b of channel image g

@@ -203,3 +203,30 @@ def test_ffn_bwd_fused(T, F):
     assert e_dy <= 3e-3 * max(1.0, ref_dy.abs().max().item())
     assert d_dh <= 1.6e-2 * max(1.0, ref_dh.float().abs().max().item()) and d_dy <= 3e-3 * max(1.0, ref_dy.abs().max().item())
     assert (dh.float() != 0).sum().item() == ((hid.float() > 0) & (dh.float() != 0)).sum().item()   # nothing leaks through the mask
+
+
+@pytest.mark.parametrize("T,keep_z", [(512, True), (1000, False), (68664, True), (128 * 148 + 77, False)])
+def test_gemm_ln_fused(T, keep_z):
+    """cb_gemm_ln_fwd == out_proj + residual followed by LayerNorm (chada_vit.py:99, :105-111): against the two kernels it
+    replaces (same bf16 operands, fp32 accumulation and two-pass statistics) and against torch in fp32."""
+    import torch.nn.functional as F
+    from chadavit_b200 import ops
+    D = 192
+    assert ops.gemm_ln_ok(T, D, D)
+    att, w = _rand((T, D), 41), _rand((D, D), 42, 0.07)
+    g = torch.Generator(device="cpu").manual_seed(43)
+    bias, x = (torch.randn(D, generator=g) * 0.1).cuda(), (torch.randn(T, D, generator=g) * 1.5).cuda()
+    gamma, beta = (1 + 0.2 * torch.randn(D, generator=g)).cuda(), (0.1 * torch.randn(D, generator=g)).cuda()
+    z, y, y32, mean, rstd = ops.gemm_ln_fwd(att, w, bias, x, gamma, beta, 1e-5, keep_z=keep_z)
+    ops.sync_check()
+    z_ref = ops.gemm(att, w, bias=bias, aux=x, flags=ops.EPI_RESIDUAL_F32 | ops.EPI_OUT_F32)
+    y_u, y32_u, mean_u, rstd_u = ops.layernorm_fwd(z_ref, gamma, beta, 1e-5, out_f32=True)
+    ops.sync_check()
+    assert (z is None) == (not keep_z)
+    if keep_z:
+        assert torch.equal(z, z_ref)                                    # the same accumulator, bias and residual arithmetic
+    assert (y32 - y32_u).abs().max().item() < 2e-5 and (mean - mean_u).abs().max().item() < 1e-6
+    assert ((rstd - rstd_u).abs() / rstd_u).max().item() < 1e-5
+    assert (y.float() - y_u.float()).abs().max().item() <= 0.04        # one bf16 ulp where the fp32 values straddle a rounding boundary
+    t = F.layer_norm(att.float() @ w.float().t() + bias + x, (D,), gamma, beta, 1e-5)
+    assert (y32 - t).abs().max().item() < 2e-3

@@ -196,6 +196,10 @@ def main():
     report("qkv   [T,192]x[192,576] +bias -> bf16", timeit(lambda: ops.gemm(x16, w_in, bias=b_in, out=o)), 2.0 * T * D * 3 * D, T * (D + 3 * D) * 2)
     o = torch.empty(T, D, device=dev)
     report("proj  [T,192]x[192,192] +bias +res32 -> f32", timeit(lambda: ops.gemm(x16, w_o, bias=b_o, aux=x32, flags=R, out=o)), 2.0 * T * D * D, T * D * (2 + 4 + 4))
+    gam_, bet_ = torch.ones(D, device=dev), torch.zeros(D, device=dev)
+    report("proj + LayerNorm, two kernels (z kept)", timeit(lambda: ops.layernorm_fwd(ops.gemm(x16, w_o, bias=b_o, aux=x32, flags=R), gam_, bet_, 1e-5, out_f32=True)), 2.0 * T * D * D, T * D * (2 + 4 + 4 + 4 + 2 + 4))
+    report("proj + LayerNorm fused (z kept: student)", timeit(lambda: ops.gemm_ln_fwd(x16, w_o, b_o, x32, gam_, bet_, 1e-5, keep_z=True)), 2.0 * T * D * D, T * D * (2 + 4 + 4 + 2 + 4))
+    report("proj + LayerNorm fused (z dropped: no-grad)", timeit(lambda: ops.gemm_ln_fwd(x16, w_o, b_o, x32, gam_, bet_, 1e-5, keep_z=False, save_stats=False)), 2.0 * T * D * D, T * D * (2 + 4 + 2 + 4))
     o = torch.empty(T, F, device=dev, dtype=bf16)
     report("fc1   [T,192]x[192,2048] +bias relu -> bf16", timeit(lambda: ops.gemm(x16, w1, bias=b1, flags=ops.EPI_RELU, out=o)), 2.0 * T * D * F, T * (D + F) * 2)
     o = torch.empty(T, D, device=dev)
