@@ -325,12 +325,11 @@ class ChAdaViT(nn.Module):
         x, u, m1a, r1a, qkv, att, lse, z1, m1b, r1b, y, hid, z2, m2, r2, bits = sv
         T, D = x.shape
         A = ops.EPI_ATOMIC
-        sk = lambda tiles: ops.splitk_for(T, tiles)  # noqa: E731
-        mt = lambda n: (n + 127) // 128  # noqa: E731
+        sk = lambda m, n: ops.splitk_wave(T, m, n)  # noqa: E731   (split-K of dW[m, n]: one full wave of CTAs)
         # x' = LN2(z2), z2 = y + relu(y W1^T + b1) W2^T + b2
         dz2, dz2h = ops.layernorm_bwd(dxo, z2, a.v32(pre + "norm2.weight"), m2, r2, dgamma=g("norm2.weight"), dbeta=g("norm2.bias"),
                                       dcolsum=g("linear2.bias"), want_bf16=True)
-        ops.gemm(dz2h, hid, a_mn=True, b_mn=True, flags=A, out=g("linear2.weight"), k_splits=sk(mt(D) * (FFN_DIM // 256)))
+        ops.gemm(dz2h, hid, a_mn=True, b_mn=True, flags=A, out=g("linear2.weight"), k_splits=sk(D, FFN_DIM))
         # d(hidden) = (dz2 W2) o (hidden > 0): the mask comes as 1 bit per unit from the fused forward (hid itself: 16x the bytes)
         # bias gradients db = dY.sum(0) ride on the weight-gradient products dW = dY^T X where the kernel supports it
         # (ops.gemm_rowsum_ok: tensor-pipe sums of the A operand); otherwise the d(hidden) epilogue / a column-sum pass form them
@@ -341,19 +340,19 @@ class ChAdaViT(nn.Module):
         else:
             dh = ops.gemm(dz2h, a.v16(pre + "linear2.weight"), b_mn=True, aux=hid if bits is None else bits,
                           flags=ops.EPI_RELU_MASK | (0 if bits is None else ops.EPI_MASK_BITS), colsum=None if cs else g("linear1.bias"))
-        ops.gemm(dh, y, a_mn=True, b_mn=True, flags=A, out=g("linear1.weight"), k_splits=sk(mt(FFN_DIM) * mt(D)),
+        ops.gemm(dh, y, a_mn=True, b_mn=True, flags=A, out=g("linear1.weight"), k_splits=sk(FFN_DIM, D),
                  colsum=g("linear1.bias") if cs else None)
         if not fused:
             dy = ops.gemm(dh, a.v16(pre + "linear1.weight"), b_mn=True, aux=dz2, flags=ops.EPI_RESIDUAL_F32 | ops.EPI_OUT_F32)
         # y = LN1(z1), z1 = x + att Wo^T + bo      (second use of norm1: gradients accumulate)
         dz1, dz1h = ops.layernorm_bwd(dy, z1, a.v32(pre + "norm1.weight"), m1b, r1b, dgamma=g("norm1.weight"), dbeta=g("norm1.bias"),
                                       dcolsum=g("self_attn.out_proj.bias"), want_bf16=True)
-        ops.gemm(dz1h, att, a_mn=True, b_mn=True, flags=A, out=g("self_attn.out_proj.weight"), k_splits=sk(mt(D) * mt(D)))
+        ops.gemm(dz1h, att, a_mn=True, b_mn=True, flags=A, out=g("self_attn.out_proj.weight"), k_splits=sk(D, D))
         datt = ops.gemm(dz1h, a.v16(pre + "self_attn.out_proj.weight"), b_mn=True)
         dqkv = ops.attn_bwd(datt, qkv, att, lse, lay, self.num_heads)
         if not cs:
             ops.colsum(dqkv, g("self_attn.in_proj_bias"))
-        ops.gemm(dqkv, u, a_mn=True, b_mn=True, flags=A, out=g("self_attn.in_proj_weight"), k_splits=sk(mt(3 * D) * mt(D)),
+        ops.gemm(dqkv, u, a_mn=True, b_mn=True, flags=A, out=g("self_attn.in_proj_weight"), k_splits=sk(3 * D, D),
                  colsum=g("self_attn.in_proj_bias") if cs else None)
         du = ops.gemm(dqkv, a.v16(pre + "self_attn.in_proj_weight"), b_mn=True, flags=ops.EPI_OUT_F32)
         # u = LN1(x) (first use) ; dx = dLN1(du) + dz1 (residual into z1)

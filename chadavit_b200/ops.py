@@ -176,6 +176,28 @@ def splitk_for(K: int, tiles: int, target_ctas: int = 148) -> int:
     return max(1, min(kb, (target_ctas + tiles - 1) // tiles))
 
 
+_SPLITK_LEGACY = os.environ.get("CB_SPLITK_LEGACY", "") == "1"
+
+
+def gemm_tiles(M: int, N: int) -> int:
+    """Output tiles of cb_gemm_bf16 for an [M, N] result: 128-row tiles x the column tile the kernel picks (gemm.cu, gemm_run:
+    192 when N is a multiple of 192 but not of 256, else 256 for N >= 256, else 128)."""
+    bn = 192 if (N % 192 == 0 and N % 256 != 0) else (256 if N >= 256 else 128)
+    return ((M + 127) // 128) * ((N + bn - 1) // bn)
+
+
+def splitk_wave(K: int, M: int, N: int, n_ctas: int = 148) -> int:
+    """Split-K factor of a weight-gradient product dW[M, N] = dY^T X over K tokens such that tiles x splits fills ONE wave of the
+    persistent kernel (<= n_ctas CTAs, as close to it as the tile count allows).  The products are HBM-bound: with the tile
+    counts the call sites used to estimate (128-wide column tiles; the kernel uses 192 / 256) dW1 ran 80 CTAs on 148 SMs, dWqkv 75,
+    dWo 74, and dW2 a full wave plus a 12-CTA tail: 145 / 172 / 58 / 29 us per 137 k tokens against 107 / 117 / 41 / 21 us with one
+    full wave (profiles/r02_microbench_splitk.txt)."""
+    kb = (K + 63) // 64
+    if _SPLITK_LEGACY:      # A/B only: the round-1 estimate (128-wide column tiles, rounded up)
+        return splitk_for(K, ((M + 127) // 128) * (N // 256 if N >= 2048 else (N + 127) // 128))
+    return max(1, min(kb, n_ctas // max(1, gemm_tiles(M, N))))
+
+
 # ------------------------------------------------------------------------------------------------ LayerNorm
 def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, *, in_idx: Optional[torch.Tensor] = None,
                   out_bf16: bool = True, out_f32: bool = False, save_stats: bool = True):

@@ -149,6 +149,25 @@ def kmajor_section(dev, T):
     report("ffn bwd fused (MN-major weights)", timeit(lambda: ops.ffn_bwd(dz, w2, w1, bits, x32)), 4.0 * T * D * F)
 
 
+def splitk_section(dev, T):
+    """Split-K factor of the weight-gradient products: CTAs in flight = row tiles x column tiles x splits (148 SMs)."""
+    D, F = 192, 2048
+    r = lambda *s: (torch.randn(*s, device=dev) * 0.5).to(bf16)  # noqa: E731
+    for TT in (T, 2 * T):
+        y, dh, dqkv, dz = r(TT, D), r(TT, F), r(TT, 3 * D), r(TT, D)
+        A = ops.EPI_ATOMIC
+        g1, g2, gq, go = torch.zeros(F, D, device=dev), torch.zeros(D, F, device=dev), torch.zeros(3 * D, D, device=dev), torch.zeros(D, D, device=dev)
+        cs, cq = torch.zeros(F, device=dev), torch.zeros(3 * D, device=dev)
+        for ks in (5, 9, 18):
+            report(f"dW1  T={TT} [2048,T]x[T,192] 16 tiles x {ks} splits (+db1)", timeit(lambda: ops.gemm(dh, y, a_mn=True, b_mn=True, flags=A, out=g1, k_splits=ks, colsum=cs)), 2.0 * TT * D * F, TT * (D + F) * 2)
+        for ks in (10, 9, 18):
+            report(f"dW2  T={TT} [192,T]x[T,2048] 16 tiles x {ks} splits", timeit(lambda: ops.gemm(dz, dh, a_mn=True, b_mn=True, flags=A, out=g2, k_splits=ks)), 2.0 * TT * D * F, TT * (D + F) * 2)
+        for ks in (15, 29, 58):
+            report(f"dWin T={TT} [576,T]x[T,192] 5 tiles x {ks} splits (+db)", timeit(lambda: ops.gemm(dqkv, y, a_mn=True, b_mn=True, flags=A, out=gq, k_splits=ks, colsum=cq)), 2.0 * TT * D * 3 * D, TT * 4 * D * 2)
+        for ks in (37, 74, 148):
+            report(f"dWo  T={TT} [192,T]x[T,192] 2 tiles x {ks} splits", timeit(lambda: ops.gemm(dz, y, a_mn=True, b_mn=True, flags=A, out=go, k_splits=ks)), 2.0 * TT * D * D, TT * 2 * D * 2)
+
+
 def attn_section(dev):
     """Attention forward / backward alone: the bench's ragged global-crop batch, 32 uniform 1961-token sequences, and the
     base/16 stress shape (D = 768, 12 heads of 64)."""
@@ -178,6 +197,8 @@ def main():
         return ffnbwd_section("cuda", a.tokens)
     if a.only == "kmajor":
         return kmajor_section("cuda", a.tokens)
+    if a.only == "splitk":
+        return splitk_section("cuda", a.tokens)
     if a.only == "dw":
         return dw_section("cuda", a.tokens)
     if a.only == "attn":
