@@ -212,6 +212,21 @@ def _timed(fn, reps, sync):
     return e0.elapsed_time(e1) / reps
 
 
+def _median_ms(fn, reps, sync):
+    """Median of per-repetition CUDA-event times: a side measurement of a third-party kernel must not be decided by one stall
+    (an allocation, a lazy initialisation) inside a short mean."""
+    ts = []
+    for i in range(reps):
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn(i)
+        e1.record()
+        sync()
+        ts.append(e0.elapsed_time(e1))
+    return float(np.median(ts))
+
+
 def _guard(fn):
     try:
         return fn()
@@ -384,26 +399,28 @@ def measure_gpu_yardstick(dev, sync, counts, crops):
 
         def fwd(i):
             return flash_attn_varlen_func(qkv[:, 0], qkv[:, 1], qkv[:, 2], cu, cu, lay.max_seqlen, lay.max_seqlen)
-        o = fwd(0)
-        o.backward(do)
-        ms_f = _timed(fwd, 5, sync)
+        for _ in range(2):
+            qkv.grad = None
+            fwd(0).backward(do)
+        ms_f = _median_ms(fwd, 9, sync)
 
         def fb(i):
             qkv.grad = None
             fwd(i).backward(do)
-        ms_fb = _timed(fb, 5, sync)
+        ms_fb = _median_ms(fb, 9, sync)
         ms_b = ms_fb - ms_f
         q2 = qkv.detach().reshape(lay.T, 3 * D_MODEL)
         out, lse = ops.attn_fwd(q2, lay, H)
         do2 = do.reshape(lay.T, D_MODEL)
         ops.attn_bwd(do2, q2, out, lse, lay, H)
-        ours_f = _timed(lambda i: ops.attn_fwd(q2, lay, H), 5, sync)
-        ours_b = _timed(lambda i: ops.attn_bwd(do2, q2, out, lse, lay, H), 5, sync)
+        ours_f = _median_ms(lambda i: ops.attn_fwd(q2, lay, H), 9, sync)
+        ours_b = _median_ms(lambda i: ops.attn_bwd(do2, q2, out, lse, lay, H), 9, sync)
         ff, fbw = 4.0 * D_MODEL * lay.sum_sq, 10.0 * D_MODEL * lay.sum_sq
         return {"workload": f"packed QKV of the two global crops: T = {lay.T}, 2 heads x 96", "flash_attn_fwd_ms": ms_f, "flash_attn_bwd_ms": ms_b,
                 "flash_attn_fwd_tflops": ff / (ms_f * 1e-3) / 1e12, "flash_attn_bwd_tflops": fbw / (ms_b * 1e-3) / 1e12,
                 "ours_fwd_ms": ours_f, "ours_bwd_ms": ours_b, "ours_fwd_tflops": ff / (ours_f * 1e-3) / 1e12,
-                "ours_bwd_tflops": fbw / (ours_b * 1e-3) / 1e12, "flash_attn_version": __import__("flash_attn").__version__}
+                "ours_bwd_tflops": fbw / (ours_b * 1e-3) / 1e12, "flash_attn_version": __import__("flash_attn").__version__,
+                "timing": "median of 9 single launches each (CUDA events); flash-attn backward = (forward + backward) - forward"}
     res["flash_attn_varlen_vs_ours"] = _guard(flash)
     return res
 
