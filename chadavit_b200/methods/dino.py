@@ -496,9 +496,14 @@ class DINO(nn.Module):
         # Crops of equal resolution are independent sequences, so they are packed into ONE backbone call per network
         # (student large crops, student small crops, teacher large crops): same arithmetic per image as the reference's
         # per-crop loop (base.py:695-707,1216-1218), 8x fewer launches and fuller waves.  Feature rows stay in crop order.
+        packed = {}         # crops of one resolution concatenated ONCE per step: student and teacher read the same large crops
+
         def batched(net, crops, counts, save):
             if len(crops) > 1 and all(c.shape[1:] == crops[0].shape[1:] for c in crops):
-                return [net._forward_impl(torch.cat(crops), [n for cs in counts for n in cs], save=save)]
+                key = tuple(id(c) for c in crops)
+                if key not in packed:
+                    packed[key] = torch.cat(crops)
+                return [net._forward_impl(packed[key], [n for cs in counts for n in cs], save=save)]
             return [net._forward_impl(x, cs, save=save) for x, cs in zip(crops, counts)]
         # Three independent kernel chains: student large crops (saved for backward), teacher large crops, student small crops
         # (reference wiring: forward only, output discarded — base.py:701-707).  The last two run on side streams; the packed
@@ -506,6 +511,11 @@ class DINO(nn.Module):
         cur = torch.cuda.current_stream()
         dev = gb.device
         side = None
+        # the large crops feed BOTH the student and the teacher: packed here, on the compute stream, before the side streams fork
+        # (a tensor produced inside one of the forked chains could not be shared without another cross-stream dependency)
+        big = X[:nl]
+        if len(big) > 1 and all(c.shape[1:] == big[0].shape[1:] for c in big):
+            packed[tuple(id(c) for c in big)] = torch.cat(big)
         if self.overlap_forward:
             if self._side is None or self._side[0].device != dev:
                 self._side = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
