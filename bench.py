@@ -724,8 +724,9 @@ def main():
                 "peak_source": peak_src, "algorithmic_flops_per_launch": tp["work"] / max(1, tp["launches"]),
                 "algorithmic_bytes_per_launch": tp["bytes"] / max(1, tp["launches"]),
                 "avg_launch_ms": tp["ms_total"] / max(1, tp["launches"]), "share_of_step": roof[top]["share_of_step"], "all": roof,
-                "hbm_note": "a one-directional HBM stream tops out near 3.9 TB/s (write) / 4.3 TB/s (read) on this part; only mixed "
-                            "traffic reaches the 6.55 TB/s copy figure (tools/membw.py, profiles/r01_hw_probes.txt)",
+                "hbm_note": "frac_hbm is against the copy figure of MEASURED_PEAKS.json; a plain one-directional stream on this part writes "
+                            "6.3-7.4 TB/s and reads 7.3 TB/s (tools/ubench/hbm_stream.cu, profiles/r02_hw_probe_hbm_stream.txt), so the "
+                            "store-heavy epilogues are bound by scattered 32-byte sectors, not by HBM",
                 "timing": "CUDA events around every launch of the class in an instrumented eager pass over the same kind of steps, all "
                           "launches on one stream (the timed steps run the teacher / local-crop forwards on side streams) "
                           f"({ms_eager / args.steps:.1f} ms/step instrumented vs {ms / args.steps:.1f} ms/step timed)"}

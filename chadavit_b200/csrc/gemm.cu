@@ -64,6 +64,22 @@ constexpr int GEMM_W_TMA = 8, GEMM_W_MMA = 9;
 // tile for every row tile was the avoidable third of that.
 constexpr int WRES_A_STAGES = 2;
 
+// TSTORE (weights-resident, bf16 output, BN = 192: the qkv projection and the out-projection's input gradient): the output tile
+// leaves through shared memory and THREE TMA stores instead of per-thread 32-byte stores.  A "thread = row" store instruction
+// writes one sector into each of 32 different lines, and that pattern is what bounds the row-direct epilogues (~3 clk per sector
+// per SM: qkv stored at 2.6 TB/s where a contiguous stream writes 6.3, profiles/r02_hw_probe_hbm_stream.txt).  The tile is staged
+// as three [128 rows x 64 columns] 128B-swizzled boxes (16-byte writes, conflict-free per quarter warp); one thread issues the
+// stores, and the staging area is reused once the previous tile's stores have read it (cp.async.bulk.wait_group.read).
+constexpr int TSTORE_BYTES = 3 * 128 * 128;        // 48 KB
+template <int BN, int EM, bool WRES, bool CSUM, bool LNF>
+__host__ __device__ constexpr bool use_tstore() {
+#ifdef CB_NO_TSTORE      // A/B variant build (CB_VARIANT=prev CB_NVCC_EXTRA=-DCB_NO_TSTORE): the row-direct epilogue everywhere
+  return false;
+#else
+  return BN == 192 && EM == 0 /* EM_BF16 */ && WRES && !CSUM && !LNF;
+#endif
+}
+
 // CSUM (weight-gradient products dW = dY^T X, both operands MN-major, split-K, fp32 atomics): the sums of op(A) over K — the
 // bias gradient that belongs to dW (rows of dY^T summed over the tokens) — are formed by the SAME tcgen05.mma that forms the
 // tile: an 8 KB block of bf16 ones sits behind every B stage, exactly where a fourth 64-column block of an MN-major B tile
@@ -80,8 +96,11 @@ __device__ __forceinline__ void tmem_ld1(uint32_t taddr, uint32_t& r) {
 
 template <int BN, int AMODE, int BMODE, int EM, bool WRES, bool CSUM = false, bool LNF = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
+            const GemmArgs g) {
   using Cfg = GemmCfg<BN>;
+  constexpr bool TSTORE = use_tstore<BN, EM, WRES, CSUM, LNF>();
+  constexpr int EPI_SZ = TSTORE ? TSTORE_BYTES + 1024 : EPI_BYTES;   // staging boxes + bias
   static_assert(!CSUM || (BN == 192 && BMODE == 1 && EM == EM_ATOMIC && !WRES), "CSUM: split-K weight-gradient product with BN = 192 and MN-major B only");
   static_assert(!LNF || (BN == 192 && EM == EM_F32 && WRES && AMODE == 0), "LNF: weights-resident 192-wide fp32 product only");
   constexpr int B_STRIDE = Cfg::B_BYTES + (CSUM ? CSUM_ONES_BYTES : 0);   // smem distance between two B stages
@@ -92,7 +111,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint8_t* sB = WRES ? smem : smem + Cfg::STAGES * Cfg::A_BYTES;
   uint8_t* sA = WRES ? smem + kb_total * Cfg::B_BYTES : smem;
   uint8_t* sEpi = WRES ? sA + WRES_A_STAGES * kb_total * Cfg::A_BYTES : smem + Cfg::STAGES * (Cfg::A_BYTES + B_STRIDE);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + EPI_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + EPI_SZ);
   uint64_t* full = bars;                         // WRES: full[0..1] = A stage landed, full[2] = weights landed
   uint64_t* empty = bars + Cfg::STAGES;          // WRES: empty[0..1]
   uint64_t* acc_full = bars + 2 * Cfg::STAGES;
@@ -229,6 +248,53 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // In-kernel timeline of fc1 (profiles/r01_timeline_gemm.txt): the staged epilogue needed 1100 clk per slab, 4400 clk per
     // 128 x 256 tile against 1536 clk of MMA — the tensor pipe waited for the epilogue 60 % of the time.
 
+    // ---------------- TSTORE: bf16 tile -> swizzled shared-memory boxes -> TMA stores (see above)
+    if constexpr (TSTORE) {
+      float* sBias = reinterpret_cast<float*>(sEpi + TSTORE_BYTES);
+      const int n0 = w_n0;
+      for (int i = threadIdx.x; i < BN; i += 256) sBias[i] = (g.bias != nullptr && n0 + i < g.N) ? __ldg(g.bias + n0 + i) : 0.f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float lo = (g.flags & CB_EPI_RELU) ? 0.f : -INFINITY;
+      const int rr = q * 32 + lane;
+      int it = 0;
+      for (int tile = w_m_first; tile < num_m; tile += w_m_step, ++it) {
+        const int m0 = tile * BM;
+        const int buf = it & 1; const uint32_t aph = (it >> 1) & 1;
+        const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + buf * Cfg::ACC_STRIDE;
+        mbar_wait(&acc_full[buf], aph);
+        tc_fence_after();
+        if (it > 0 && threadIdx.x == 0) tma_store_wait_read<0>();    // the previous tile's stores have read the staging boxes
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const int sl = 3 * half + j, c = sl * 32;
+          uint32_t x[32];
+          tmem_ld32(t_addr + c, x);
+          tmem_ld_wait();
+          if (j == 2) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&acc_empty[buf]); }   // accumulator fully read
+          uint32_t pk[16];
+#pragma unroll
+          for (int e = 0; e < 32; e += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(sBias + c + e);
+            pk[e >> 1] = pack_bf16(fmaxf(fmaf(__uint_as_float(x[e]), g.alpha, b4.x), lo), fmaxf(fmaf(__uint_as_float(x[e + 1]), g.alpha, b4.y), lo));
+            pk[(e >> 1) + 1] = pack_bf16(fmaxf(fmaf(__uint_as_float(x[e + 2]), g.alpha, b4.z), lo), fmaxf(fmaf(__uint_as_float(x[e + 3]), g.alpha, b4.w), lo));
+          }
+          // slab sl = columns [32 sl, 32 sl + 32) = half (sl & 1) of the 128-byte row rr of box sl >> 1: 16-byte chunks 4 (sl & 1) + k
+          uint8_t* rowp = sEpi + (sl >> 1) * (128 * 128) + rr * 128;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            *reinterpret_cast<uint4*>(rowp + (((4 * (sl & 1) + k) ^ (rr & 7)) << 4)) = make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
+        }
+        fence_proxy_async();      // generic-proxy writes of the boxes -> visible to the TMA (async proxy)
+        asm volatile("bar.sync 3, 256;" ::: "memory");
+        if (threadIdx.x == 0) {
+#pragma unroll
+          for (int b = 0; b < 3; ++b) tma_store_2d(&tmC, sEpi + b * (128 * 128), n0 + 64 * b, m0);
+          tma_store_commit();
+        }
+      }
+      if (threadIdx.x == 0) tma_store_wait_all<0>();
+    } else
     // ---------------- LayerNorm fused into the row epilogue (LNF; the encoder's  y = norm1(x + attn W_o^T + b_o),  chada_vit.py:99).
     // The 192-wide tile holds whole rows; a row is shared by the two warps of its lane quarter (columns 0..95 / 96..191), which
     // exchange their partial sums through shared memory: once for the mean, once for the centred sum of squares (the same
@@ -767,7 +833,15 @@ template <int BN, int AMODE, int BMODE, int EM, bool WRES, bool CSUM = false, bo
 static int launch_k(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   const int kb_total = (g.K + BK - 1) / BK;
-  const int smem_bytes = WRES ? kb_total * Cfg::B_BYTES + WRES_A_STAGES * kb_total * Cfg::A_BYTES + EPI_BYTES + 1024 + 256
+  constexpr int EPI_SZ = use_tstore<BN, EM, WRES, CSUM, LNF>() ? TSTORE_BYTES + 1024 : EPI_BYTES;
+  CUtensorMap tmC = tmA;          // placeholder for the kernels that do not store through TMA
+  if (use_tstore<BN, EM, WRES, CSUM, LNF>()) {   // bf16 C [M, N] (ldc): boxes of 64 columns x 128 rows, 128B swizzle
+    uint64_t dims[2] = {(uint64_t)g.N, (uint64_t)g.M};
+    uint64_t strides[1] = {(uint64_t)g.ldc * 2};
+    uint32_t box[2] = {64, 128};
+    if (make_tmap(&tmC, g.C, 2, dims, strides, box, 3)) return 1;
+  }
+  const int smem_bytes = WRES ? kb_total * Cfg::B_BYTES + WRES_A_STAGES * kb_total * Cfg::A_BYTES + EPI_SZ + 1024 + 256
                               : Cfg::SMEM_BYTES + (CSUM ? Cfg::STAGES * CSUM_ONES_BYTES : 0);
   static_assert(!CSUM || Cfg::SMEM_BYTES + Cfg::STAGES * CSUM_ONES_BYTES <= 227 * 1024, "CSUM: ones blocks do not fit");
   static int attr_set = 0;
@@ -782,7 +856,7 @@ static int launch_k(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmAr
     const int per_n = max(1, min(num_sms() / num_n, num_m));
     grid = per_n * num_n;
   }
-  gemm_kernel<BN, AMODE, BMODE, EM, WRES, CSUM, LNF><<<grid, GEMM_THREADS, smem_bytes, stream>>>(tmA, tmB, g);
+  gemm_kernel<BN, AMODE, BMODE, EM, WRES, CSUM, LNF><<<grid, GEMM_THREADS, smem_bytes, stream>>>(tmA, tmB, tmC, g);
   CB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -793,9 +867,12 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs
   using Cfg = GemmCfg<BN>;
   if constexpr (AMODE == 0 && (EM == EM_BF16 || EM == EM_BF16_MASK || EM == EM_F32)) {
     const int kb_total = (g.K + BK - 1) / BK;
-    const bool fits = kb_total * Cfg::B_BYTES + WRES_A_STAGES * kb_total * Cfg::A_BYTES + EPI_BYTES + 1024 + 256 <= 227 * 1024;
+    constexpr bool TS = use_tstore<BN, EM, true, false, false>();
+    const bool fits = kb_total * Cfg::B_BYTES + WRES_A_STAGES * kb_total * Cfg::A_BYTES + (TS ? TSTORE_BYTES + 1024 : EPI_BYTES) + 1024 + 256 <= 227 * 1024;
     const int num_n = (g.N + BN - 1) / BN;
-    if (g.k_splits == 1 && kb_total <= 3 && fits && num_n <= num_sms() && g.M >= 4 * BM) return launch_k<BN, AMODE, BMODE, EM, true>(tmA, tmB, g, stream);
+    // the TMA-store epilogue needs whole 64-column boxes and the aligned rows of the row-direct epilogue
+    const bool ts_ok = !TS || (g.direct && g.N % 192 == 0 && g.ldc % 8 == 0);
+    if (g.k_splits == 1 && kb_total <= 3 && fits && ts_ok && num_n <= num_sms() && g.M >= 4 * BM) return launch_k<BN, AMODE, BMODE, EM, true>(tmA, tmB, g, stream);
   }
   return launch_k<BN, AMODE, BMODE, EM, false>(tmA, tmB, g, stream);
 }

@@ -78,6 +78,28 @@ def test_gemm_epilogues():
     assert (acc - 1 - _ref(A, B, False, False)).abs().max().item() < 1e-2
 
 
+@pytest.mark.parametrize("M,N,K", [(512, 576, 192), (4999, 576, 192), (68664, 576, 192), (1000, 192, 192), (777, 192, 64), (129 * 128 + 1, 384, 128)])
+@pytest.mark.parametrize("relu", [False, True])
+def test_gemm_bf16_tma_store_epilogue(M, N, K, relu):
+    """bf16 outputs of the weights-resident 192-wide products (qkv projection, chada_vit.py:105-111 in_proj; the out-projection's
+    input gradient) leave through swizzled shared-memory boxes and TMA stores.  Ragged last row tile (clipped by the tensor map),
+    bias, alpha, ReLU, and an output that is a column slice of a wider buffer (ldc > N); the neighbouring columns stay untouched."""
+    from chadavit_b200 import ops
+    A, B = _rand((M, K), 31), _rand((N, K), 32, 0.1)
+    bias = torch.randn(N, device="cuda")
+    ref = 0.5 * _ref(A, B, False, False) + bias
+    ref = ref.relu() if relu else ref
+    C = ops.gemm(A, B, bias=bias, alpha=0.5, flags=ops.EPI_RELU if relu else 0)
+    ops.sync_check()
+    assert C.dtype == torch.bfloat16
+    assert torch.equal(C, ref.to(torch.bfloat16)) or (C.float() - ref).abs().max().item() <= 8e-3 * max(1.0, ref.abs().max().item())
+    wide = torch.full((M, N + 64), 7.0, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(A, B, bias=bias, alpha=0.5, flags=ops.EPI_RELU if relu else 0, out=wide[:, 32:32 + N])
+    ops.sync_check()
+    assert torch.equal(wide[:, 32:32 + N], C)
+    assert bool((wide[:, :32] == 7.0).all()) and bool((wide[:, 32 + N:] == 7.0).all())
+
+
 def test_gemm_weight_grad_splitk():
     """dW[out,in] += dY^T X with both operands MN-major and split-K (the encoder's weight-gradient product)."""
     from chadavit_b200 import ops
