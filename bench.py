@@ -556,7 +556,7 @@ def main():
     keep_graph, model.use_cuda_graph = model.use_cuda_graph, False
     keep_ovl, model.overlap_forward = model.overlap_forward, False
     classes = ["cb_attn_varlen_fwd", "cb_attn_varlen_bwd", "cb_gemm_bf16", "cb_ffn_fwd", "cb_ffn_fwd:nostore", "cb_ffn_bwd", "cb_layernorm_fwd",
-               "cb_layernorm2_fwd", "cb_layernorm_bwd"]
+               "cb_layernorm2_fwd", "cb_layernorm_bwd", "cb_attn_cls_fwd", "cb_attn_cls_bwd"]
     ops.PROFILE = {k: [0, 0.0, [], 0.0] for k in classes}
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()

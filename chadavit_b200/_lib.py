@@ -50,6 +50,8 @@ SIGNATURES = {
     "cb_ema_update": [_vp, _vp, _vp, _f, _l, _vp],
     "cb_adamw_step": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _l, _f, _f, _f, _f, _f, _i, _i, _f, _f, _vp, _vp],
     "cb_attn_probs": [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp],
+    "cb_attn_cls_fwd": [_vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp],
+    "cb_attn_cls_bwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp],
     "cb_split_bf16x3": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "cb_inv_euclid": [_vp, _vp, _vp, _i, _i, _i, _f, _vp],
     "cb_param_norms": [_vp, _vp, _vp, _vp, _vp, _vp, _l, _i, _f, _f, _vp],

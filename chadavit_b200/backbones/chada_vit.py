@@ -77,7 +77,7 @@ class TokenLearner(nn.Module):
 
 class _Saved:
     """Activations kept for the backward pass of one backbone call."""
-    __slots__ = ("lay", "patches", "blocks", "x_last", "fin_idx", "fin_mean", "fin_rstd", "interp", "hw")
+    __slots__ = ("lay", "patches", "blocks", "x_last", "fin_idx", "fin_mean", "fin_rstd", "interp", "hw", "tail")
 
 
 class _BackboneFn(torch.autograd.Function):
@@ -236,17 +236,53 @@ class ChAdaViT(nn.Module):
         tok, lay, patches, interp = self._tokenize(x, counts)
         blocks = []
         h, pre = tok, None          # pre = (u, mean, rstd) of this block's norm1(x) when the previous block already produced it
-        for i in range(self.depth):
+        # Only the CLS row of the final norm is returned (chada_vit.py:289) and every op behind the last attention is row-wise:
+        # the last block then runs its attention for the CLS queries only and the rest on the B CLS rows (_tail_fwd).
+        tail = ops.cls_tail_ok(self.depth, self.return_all_tokens, self.embed_dim // self.num_heads)
+        for i in range(self.depth - 1 if tail else self.depth):
             h, sv, pre = self._block_fwd(i, h, lay, save, pre)
             blocks.append(sv)
-        idx = lay.non_cls_rows() if self.return_all_tokens else lay.cu[:-1]
+        if tail:
+            h, sv = self._tail_fwd(h, lay, save, pre)      # h: fp32 [B, D], the CLS rows only
+            blocks.append(sv)
+            idx = None
+        else:
+            idx = lay.non_cls_rows() if self.return_all_tokens else lay.cu[:-1]
         _, out, mean, rstd = ops.layernorm_fwd(h, a.v32("norm.weight"), a.v32("norm.bias"), self.norm.eps, in_idx=idx, out_bf16=False,
                                                out_f32=True, save_stats=save)
         if not save:
             return out, None
         s = _Saved()
         s.lay, s.patches, s.blocks, s.x_last, s.fin_idx, s.fin_mean, s.fin_rstd, s.interp, s.hw = lay, patches, blocks, h, idx, mean, rstd, interp, (H, W)
+        s.tail = tail
         return out, s
+
+    def _tail_fwd(self, x: torch.Tensor, lay: ops.PackedLayout, save: bool, pre_u=None):
+        """The last encoder block when only the CLS embedding leaves the backbone.  x fp32 [T, D] -> x' fp32 [B, D] (CLS rows).
+        qkv is still formed for every token (all of them are keys / values of the CLS query, chada_vit.py:105-111); the
+        attention runs for the CLS queries only (cb_attn_cls_fwd), and the out-projection, norm1, feed-forward and norm2
+        (chada_vit.py:99-100, :113-116) on the B CLS rows: identical results, the other rows were never read by anyone."""
+        i = self.depth - 1
+        a, pre = self.arena, f"blocks.{i}."
+        eps = self.blocks[i].norm1.eps
+        g1, b1 = a.v32(pre + "norm1.weight"), a.v32(pre + "norm1.bias")
+        R = ops.EPI_RESIDUAL_F32 | ops.EPI_OUT_F32
+        if pre_u is not None:
+            u, m1a, r1a = pre_u
+        else:
+            u, _, m1a, r1a = ops.layernorm_fwd(x, g1, b1, eps, save_stats=save)
+        qkv = ops.gemm(u, a.v16(pre + "self_attn.in_proj_weight"), bias=a.v32(pre + "self_attn.in_proj_bias"))
+        att, lse = ops.attn_cls_fwd(qkv, lay, self.num_heads)
+        xc = x.index_select(0, lay.cls_rows64())
+        z1 = ops.gemm(att, a.v16(pre + "self_attn.out_proj.weight"), bias=a.v32(pre + "self_attn.out_proj.bias"), aux=xc, flags=R)
+        y, y32, m1b, r1b = ops.layernorm_fwd(z1, g1, b1, eps, out_f32=True, save_stats=save)
+        hid = ops.gemm(y, a.v16(pre + "linear1.weight"), bias=a.v32(pre + "linear1.bias"), flags=ops.EPI_RELU)
+        z2 = ops.gemm(hid, a.v16(pre + "linear2.weight"), bias=a.v32(pre + "linear2.bias"), aux=y32, flags=R)
+        _, out, m2, r2 = ops.layernorm_fwd(z2, a.v32(pre + "norm2.weight"), a.v32(pre + "norm2.bias"), self.blocks[i].norm2.eps,
+                                           out_bf16=False, out_f32=True, save_stats=save)
+        if not save:
+            return out, None
+        return out, (x, u, m1a, r1a, qkv, att, lse, z1, m1b, r1b, y, hid, z2, m2, r2)
 
     def _block_fwd(self, i: int, x: torch.Tensor, lay: ops.PackedLayout, save: bool, pre_u=None):
         """x fp32 [T,D] -> x' fp32 [T,D].  The residual stream and every LayerNorm input stay fp32; bf16 is used only for
@@ -303,7 +339,10 @@ class ChAdaViT(nn.Module):
                                   dbeta=g("norm.bias"), idx=s.fin_idx)
         dx16 = None
         for i in reversed(range(self.depth)):
-            dx, dx16 = self._block_bwd(i, s.blocks[i], dx, lay, gflat, last=(i == 0))
+            if s.tail and i == self.depth - 1:
+                dx = self._tail_bwd(s.blocks[i], dx, lay, gflat)
+            else:
+                dx, dx16 = self._block_bwd(i, s.blocks[i], dx, lay, gflat, last=(i == 0))
             s.blocks[i] = None
             if block_done is not None:
                 block_done(i)
@@ -317,6 +356,39 @@ class ChAdaViT(nn.Module):
             ops.small_matmul_f32(s.interp, dpos_patch, trans_a=True, out=dpos[1:], accumulate=True)
         if block_done is not None:
             block_done(-1)
+
+    def _tail_bwd(self, sv, dxo: torch.Tensor, lay: ops.PackedLayout, gflat: torch.Tensor) -> torch.Tensor:
+        """Backward of _tail_fwd: dxo fp32 [B, D] (gradient of the B CLS rows) -> dx fp32 [T, D].  Up to d(attention output)
+        everything lives on the CLS rows (the gradient of every other row is exactly zero); cb_attn_cls_bwd turns it into the
+        dense dqkv (dK / dV of every token), from where the block continues as _block_bwd does."""
+        i = self.depth - 1
+        a, pre = self.arena, f"blocks.{i}."
+        g = lambda n: a.g32(pre + n, gflat)  # noqa: E731
+        x, u, m1a, r1a, qkv, att, lse, z1, m1b, r1b, y, hid, z2, m2, r2 = sv
+        T, D = x.shape
+        Bc = z2.shape[0]
+        A = ops.EPI_ATOMIC
+        cs = ops.gemm_rowsum_ok(D)
+        dz2, dz2h = ops.layernorm_bwd(dxo, z2, a.v32(pre + "norm2.weight"), m2, r2, dgamma=g("norm2.weight"), dbeta=g("norm2.bias"),
+                                      dcolsum=g("linear2.bias"), want_bf16=True)
+        ops.gemm(dz2h, hid, a_mn=True, b_mn=True, flags=A, out=g("linear2.weight"), k_splits=ops.splitk_wave(Bc, D, FFN_DIM))
+        dh = ops.gemm(dz2h, a.v16(pre + "linear2.weight"), b_mn=True, aux=hid, flags=ops.EPI_RELU_MASK, colsum=None if cs else g("linear1.bias"))
+        ops.gemm(dh, y, a_mn=True, b_mn=True, flags=A, out=g("linear1.weight"), k_splits=ops.splitk_wave(Bc, FFN_DIM, D),
+                 colsum=g("linear1.bias") if cs else None)
+        dy = ops.gemm(dh, a.v16(pre + "linear1.weight"), b_mn=True, aux=dz2, flags=ops.EPI_RESIDUAL_F32 | ops.EPI_OUT_F32)
+        dz1, dz1h = ops.layernorm_bwd(dy, z1, a.v32(pre + "norm1.weight"), m1b, r1b, dgamma=g("norm1.weight"), dbeta=g("norm1.bias"),
+                                      dcolsum=g("self_attn.out_proj.bias"), want_bf16=True)
+        ops.gemm(dz1h, att, a_mn=True, b_mn=True, flags=A, out=g("self_attn.out_proj.weight"), k_splits=ops.splitk_wave(Bc, D, D))
+        datt = ops.gemm(dz1h, a.v16(pre + "self_attn.out_proj.weight"), b_mn=True)
+        dqkv = ops.attn_cls_bwd(datt, qkv, att, lse, lay, self.num_heads)
+        if not cs:
+            ops.colsum(dqkv, g("self_attn.in_proj_bias"))
+        ops.gemm(dqkv, u, a_mn=True, b_mn=True, flags=A, out=g("self_attn.in_proj_weight"), k_splits=ops.splitk_wave(T, 3 * D, D),
+                 colsum=g("self_attn.in_proj_bias") if cs else None)
+        du = ops.gemm(dqkv, a.v16(pre + "self_attn.in_proj_weight"), b_mn=True, flags=ops.EPI_OUT_F32)
+        dx, _ = ops.layernorm_bwd(du, x, a.v32(pre + "norm1.weight"), m1a, r1a, dgamma=g("norm1.weight"), dbeta=g("norm1.bias"))
+        dx.index_add_(0, lay.cls_rows64(), dz1)      # residual into z1 = x + attn: non-zero on the CLS rows only
+        return dx
 
     def _block_bwd(self, i: int, sv, dxo: torch.Tensor, lay: ops.PackedLayout, gflat: torch.Tensor, last: bool):
         """dxo fp32 [T,D] -> (dx fp32, dx bf16 if last).  Gradient residual stream fp32; bf16 only for MMA operands."""

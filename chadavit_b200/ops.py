@@ -286,6 +286,11 @@ class PackedLayout:
         self.cu = torch.from_numpy(cu).to(device, non_blocking=True)
         self.chan_img = torch.from_numpy(chan_img).to(device, non_blocking=True)
         self.chan_idx = torch.from_numpy(chan_idx).to(device, non_blocking=True)
+        # int64 copy of the CLS rows for torch gathers / scatters.  Made HERE, with the other index tensors: the training engine
+        # creates its layouts on the compute stream before it forks the teacher / local-crop chains onto side streams, and a
+        # tensor first uploaded inside one chain would be read by the others without a stream dependency.
+        self._cls64_host = cu[:-1].astype(np.int64)
+        self._cls64 = torch.from_numpy(self._cls64_host).to(device, non_blocking=True)
         self._work = {}
         self._work_host = {}
 
@@ -322,6 +327,10 @@ class PackedLayout:
             self._work_host[key] = host[:n_out.value]
             w = self._work[key] = torch.from_numpy(self._work_host[key]).to(self.device, non_blocking=True)
         return w
+
+    def cls_rows64(self) -> torch.Tensor:
+        """Packed row of every sequence's CLS token (its first row) as an int64 index for torch gathers / scatters."""
+        return self._cls64
 
     def non_cls_rows(self) -> torch.Tensor:
         """Packed rows of all patch tokens in (b, c, p) order (return_all_tokens=True output order, chada_vit.py:283-287)."""
@@ -407,6 +416,41 @@ def attn_bwd(dout: torch.Tensor, qkv: torch.Tensor, out: torch.Tensor, lse: torc
     dqkv = torch.empty(T, D3, device=qkv.device, dtype=bf16)
     _call("cb_attn_varlen_bwd", _p(dout), _p(qkv), _p(out), _p(lse), _p(work), work.shape[0], _p(delta), _p(dq_acc), _p(dqkv), T, D,
           nheads, float(d) ** -0.5, _stream(), work=10.0 * D * lay.sum_sq, nbytes=18.0 * T * D)
+    return dqkv
+
+
+_CLS_TAIL = os.environ.get("CB_NO_CLS_TAIL", "") != "1"   # A/B switch (read once): CLS-only tail of the last block
+
+
+def cls_tail_ok(depth: int, return_all_tokens: bool, head_dim: int) -> bool:
+    """True when the last encoder block may run its attention for the CLS queries only and everything behind it on the CLS rows
+    only: the backbone returns ``x[:, 0]`` (chada_vit.py:289), every op behind the last attention is row-wise."""
+    return _CLS_TAIL and not return_all_tokens and depth >= 2 and head_dim in (16, 32, 64, 96, 128)
+
+
+def attn_cls_fwd(qkv: torch.Tensor, lay: PackedLayout, nheads: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Attention output of the CLS query of every sequence: (out bf16 [B, D], lse fp32 [B, H])."""
+    T, D3 = qkv.shape
+    D = D3 // 3
+    d = D // nheads
+    assert qkv.dtype == bf16 and qkv.is_contiguous() and T == lay.T
+    out = torch.empty(lay.B, D, device=qkv.device, dtype=bf16)
+    lse = torch.empty(lay.B, nheads, device=qkv.device, dtype=torch.float32)
+    _call("cb_attn_cls_fwd", _p(qkv), _p(lay.cu), lay.B, nheads, d, float(d) ** -0.5, _p(out), _p(lse), _stream(),
+          work=4.0 * D * T, nbytes=4.0 * T * D)
+    return out, lse
+
+
+def attn_cls_bwd(dout: torch.Tensor, qkv: torch.Tensor, out: torch.Tensor, lse: torch.Tensor, lay: PackedLayout, nheads: int) -> torch.Tensor:
+    """dqkv bf16 [T, 3D] (every element written) from d(attention output) of the CLS rows, bf16 [B, D]."""
+    T, D3 = qkv.shape
+    D = D3 // 3
+    d = D // nheads
+    assert dout.dtype == bf16 and dout.is_contiguous() and dout.shape == (lay.B, D) and out.shape == (lay.B, D) and out.is_contiguous()
+    assert lse.shape == (lay.B, nheads) and qkv.is_contiguous() and T == lay.T
+    dqkv = torch.empty(T, D3, device=qkv.device, dtype=bf16)
+    _call("cb_attn_cls_bwd", _p(dout), _p(qkv), _p(out), _p(lse), _p(lay.cu), lay.B, nheads, d, float(d) ** -0.5, _p(dqkv), _stream(),
+          work=10.0 * D * T, nbytes=10.0 * T * D)
     return dqkv
 
 

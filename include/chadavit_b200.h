@@ -239,6 +239,18 @@ int cb_adamw_step(float* p, const float* g, float* m, float* v, const unsigned c
 int cb_attn_probs(const void* qkv, const int* cu_seqlens, int nseq, int num_heads, int head_dim, int max_seqlen, float scale,
                   float* out, void* stream);
 
+/* Self-attention of the LAST encoder block when the backbone returns only the CLS embedding (`return x[:, 0]`,
+ * src/backbones/vit/chada_vit.py:289; the SDPA of nn.MultiheadAttention, :105-111).  Everything behind that attention is row-wise,
+ * so only the CLS query of every sequence is used: out_cls[b, h*d..] = softmax_j(q_cls(b) . k_j * scale) V over the tokens of packed
+ * sequence b (bf16 [nseq, H*d]); lse_cls fp32 [nseq, H] (log2 domain, consumed by cb_attn_cls_bwd).  qkv as in cb_attn_varlen_fwd. */
+int cb_attn_cls_fwd(const void* qkv, const int* cu_seqlens, int nseq, int num_heads, int head_dim, float scale, void* out_cls,
+                    float* lse_cls, void* stream);
+
+/* Backward of cb_attn_cls_fwd: dout_cls bf16 [nseq, H*d] = d(attention output) of the CLS rows (all other rows are zero by
+ * construction).  Writes EVERY element of dqkv (bf16 [T, 3*H*d]): dK / dV of all tokens, dQ of the CLS rows, zeros elsewhere. */
+int cb_attn_cls_bwd(const void* dout_cls, const void* qkv, const void* out_cls, const float* lse_cls, const int* cu_seqlens, int nseq,
+                    int num_heads, int head_dim, float scale, void* dqkv, void* stream);
+
 /* Weighted k-NN evaluation (src/utils/knn.py:96-177): operand preparation for an fp32-accurate similarity matrix on the bf16
  * tensor cores.  Row r of x (fp32 [rows, D]) is optionally L2-normalised (F.normalize, knn.py:114-116) and written as bf16
  * [hi | hi | lo] (role_b = 0) or [hi | lo | hi] (role_b = 1) of length 3*D, so that ONE cb_gemm_bf16 over K = 3*D yields
