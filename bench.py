@@ -237,6 +237,7 @@ def _guard(fn):
 
 def measure_cfg1_extraction(dev, sync, tf_peak):
     """BASELINE configs[1]: moyen/16 embedding extraction (main_knn.py:45-70 -> base.py:929-981), ragged batch of 256, one GPU."""
+    from chadavit_b200 import ops
     from chadavit_b200.backbones import vit_channels
     from chadavit_b200.methods import extract_features
     torch.manual_seed(1)
@@ -257,7 +258,12 @@ def measure_cfg1_extraction(dev, sync, tf_peak):
     flops = []
     for x, c in batches:
         S = np.array([1 + k * 196 for k in c], dtype=np.float64)
-        flops.append(12 * (1_867_776.0 * S.sum() + 4 * D_MODEL * (S ** 2).sum()) + 2.0 * 256 * D_MODEL * sum(c) * 196)
+        dense = 1_867_776.0 * S.sum() + 4 * D_MODEL * (S ** 2).sum()          # one dense block: linear layers + attention
+        if ops._CLS_TAIL:   # work actually done: the last block forms qkv for every token, the rest on the CLS rows only
+            last = 6.0 * D_MODEL ** 2 * S.sum() + 4.0 * D_MODEL * S.sum() + len(c) * 2.0 * (D_MODEL ** 2 + 2 * D_MODEL * 2048)
+            flops.append(11 * dense + last + 2.0 * 256 * D_MODEL * sum(c) * 196)
+        else:
+            flops.append(12 * dense + 2.0 * 256 * D_MODEL * sum(c) * 196)
 
     def run_e2e(i):
         xh, c = host[i % 2]
@@ -655,6 +661,18 @@ def main():
         extras["multicrop_v8"] = _guard(multicrop)
         torch.cuda.empty_cache()
         if world == 1:
+            def no_dead_local():
+                model.run_unused_local_crops = False
+                try:
+                    for _ in range(3):
+                        model.fused_train_step(next_batch())
+                    t_ms = _timed(lambda i: model.fused_train_step(next_batch()), max(5, args.steps // 2), lsync)
+                finally:
+                    model.run_unused_local_crops = True
+                return {"value": BATCH / (t_ms * 1e-3), "unit": "imgs/s", "ms_per_step": t_ms,
+                        "workload": "the headline step WITHOUT the reference's unused local-crop passes (base.py:701-707: backbone only, "
+                                    "features dropped, SURVEY Q11) — same loss and gradients; NOT the headline, which keeps them"}
+            extras["without_unused_local_crop_passes"] = _guard(no_dead_local)
             extras["cfg1_extraction"] = _guard(lambda: measure_cfg1_extraction(dev, lsync, tf_peak))
             torch.cuda.empty_cache()
             extras["gpu_yardstick"] = _guard(lambda: measure_gpu_yardstick(dev, lsync, fixed[2][0], [c.clone() for c in fixed[0]]))
@@ -757,6 +775,11 @@ def main():
                    "parallelism": f"dp{world}", "sharding": ("contiguous" if args.unbalanced else "token-balanced (data/balance.py)") +
                    f": rank r runs shard r of the {SHARD_WORLD}-GPU job's global batch at every N",
                    "rank_work_spread": spread, "cuda_graph": bool(args.fixed_batch),
+                   "last_block": ("dense (CB_NO_CLS_TAIL=1)" if not ops._CLS_TAIL else
+                                  "the backbone returns x[:, 0] (chada_vit.py:289): the last block's attention runs for the CLS queries only "
+                                  "(cb_attn_cls_fwd / cb_attn_cls_bwd) and its row-wise remainder on the B CLS rows; outputs and gradients "
+                                  "identical to the dense form (tests/test_backbone_gpu.py), which measures 38.55 ms against 36.07 ms "
+                                  "(profiles/r02_ab_cls_tail.txt)"),
                    "grad_allreduce": ("flat, after the backward" if args.no_overlap else
                                       f"bucketed ({model.grad_bucket_blocks} blocks per bucket) on a side stream under the backward") if world > 1 else None,
                    "l2_policy": "working set per step (~10 GB of activations) >> 126 MB L2; no explicit flush"},

@@ -291,6 +291,10 @@ class DINO(nn.Module):
         # teacher forward and the (discarded) student local-crop forward on side streams: independent kernel chains fill each
         # other's launch gaps and tails (every kernel is one persistent wave)
         self.overlap_forward = bool(_cfg(cfg, "engine.overlap_forward", True))
+        # Reference wiring (base.py:701-707): the local crops go through the student backbone and their features are
+        # dropped — they reach neither the head nor the loss.  True (the default, and what bench.py's headline times) keeps
+        # that pass; False is for a user who knows it is dead compute (same loss, same gradients, ~10 % less work per step).
+        self.run_unused_local_crops = bool(_cfg(cfg, "engine.run_unused_local_crops", True))
         self._side: Optional[List[torch.cuda.Stream]] = None
         self._host_losses: Optional[List["HostLoss"]] = None     # fused_train_step(loss_to_host=True): four rotating pinned slots
         self._graphs: "collections.OrderedDict[tuple, dict]" = collections.OrderedDict()
@@ -545,7 +549,7 @@ class DINO(nn.Module):
         tlogits = on_side(0, teacher)
         saved, feats = [], []
         local_on_side = len(X) > nl and not self.multicrop_loss
-        if local_on_side:                                 # base.py:701-707: the small crops index list_num_channels from 0 (Q12)
+        if local_on_side and self.run_unused_local_crops:   # base.py:701-707: the small crops index list_num_channels from 0 (Q12)
             on_side(1, lambda: batched(bb, X[nl:], list_num_channels[:len(X) - nl], False))
         for f, s_ in batched(bb, X[:nl], list_num_channels[:nl], True):
             saved.append(s_)

@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Summarise an ncu launch list (--metrics gpu__time_duration.sum --csv) by kernel: launches, total/avg us, share."""
+"""Summarise an ncu launch list (--metrics gpu__time_duration.sum --csv) by kernel: launches, total/avg us, share.
+    python tools/ncu_summary.py launches.csv [--one-step]"""
 import csv
 import re
 import sys
@@ -15,6 +16,10 @@ for r in csv.DictReader(lines):
         v *= {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(unit, 1e-3)
         name = re.sub(r"\(.*", "", r["Kernel Name"])
         rows.append((name, v))
+if "--one-step" in sys.argv:      # the launches between the last two dino_loss_kernel launches = one training step (phase-shifted)
+    marks = [i for i, (n, _) in enumerate(rows) if "dino_loss_kernel" in n]
+    if len(marks) >= 2:
+        rows = rows[marks[-2]:marks[-1]]
 agg = defaultdict(lambda: [0, 0.0])
 for n, v in rows:
     agg[n][0] += 1

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Launch ONE kernel class a few times so that `ncu --set full` can capture it in isolation.
-    python tools/prof_one.py fc1|qkv|dh|fc2|attn_fwd|attn_bwd|ffn|ffn_save|ffn_bwd|ln_bwd"""
+    python tools/prof_one.py fc1|qkv|dh|fc2|attn_fwd|attn_bwd|ffn|ffn_save|ffn_bwd|ln_bwd|attn_cls_fwd|attn_cls_bwd"""
 import os
 import sys
 
@@ -42,6 +42,12 @@ if which == "ln_bwd":
 if which == "attn_bwd":
     out, lse = ops.attn_fwd(qkv, lay, 2)
     fns["attn_bwd"] = lambda: ops.attn_bwd(do, qkv, out, lse, lay, 2)
+if which in ("attn_cls_fwd", "attn_cls_bwd"):
+    lay2 = ops.PackedLayout(counts + counts, 196, dev)        # the two packed global crops, as the engine runs them
+    qkv2, do2 = r(lay2.T, 3 * D), r(lay2.B, D)
+    oc, lc = ops.attn_cls_fwd(qkv2, lay2, 2)
+    fns["attn_cls_fwd"] = lambda: ops.attn_cls_fwd(qkv2, lay2, 2)
+    fns["attn_cls_bwd"] = lambda: ops.attn_cls_bwd(do2, qkv2, oc, lc, lay2, 2)
 for _ in range(5):
     fns[which]()
 torch.cuda.synchronize()
