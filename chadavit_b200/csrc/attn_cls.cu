@@ -48,7 +48,7 @@ __device__ __forceinline__ float ex2(float x) {
 }  // namespace acls
 
 template <int HD>
-__global__ void __launch_bounds__(acls::NT) attn_cls_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int* __restrict__ cu, int H,
+__global__ void __launch_bounds__(acls::NT, 2) attn_cls_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int* __restrict__ cu, int H,
                                                                 float scale_log2, __nv_bfloat16* __restrict__ out_cls,
                                                                 float* __restrict__ lse_cls) {
   using namespace acls;
