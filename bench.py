@@ -444,10 +444,17 @@ def measure_parity(dev, cpu_parity, n_img):
     lnc = [counts] * (N_GLOBAL + N_LOCAL)
     with torch.no_grad():
         cls = m.backbone(crops[0], 0, lnc).float().cpu()
+        m.backbone.linear_precision = "split3"          # fp32 parity run: hi + lo bf16 operands in every linear layer
+        try:
+            cls32 = m.backbone(crops[0], 0, lnc).float().cpu()
+        finally:
+            m.backbone.linear_precision = "bf16"
     loss = float(m.fused_train_step((crops, None, lnc)).item())
     ref = cpu_parity["cls"].double()
     rel = float((cls.double() - ref).norm() / ref.norm())
+    rel32 = float((cls32.double() - ref).norm() / ref.norm())
     return {"loss_gpu": loss, "loss_cpu": cpu_parity["loss"], "abs_diff": abs(loss - cpu_parity["loss"]), "cls_rel_err": rel,
+            "cls_rel_err_fp32_parity_run": rel32,
             "tolerance": {"loss_abs": 1e-3, "cls_rel": 1.5e-2},
             "note": f"same {n_img} images x 8 crops and det weights as cpu_baseline (fp32 oracle port); the CLS bound at D = 192 is 1.5e-2 "
                     "(bf16 rounding of the weights alone moves the fp32 reference by 9.9e-3, DESIGN.md section 4)",

@@ -133,6 +133,11 @@ class ChAdaViT(nn.Module):
         self.apply(self._init_weights)          # chada_vit.py:171-183 (Conv2d / in_proj keep torch defaults)
         self._arena: Optional[ParamArena] = None
         self._interp: Dict[tuple, torch.Tensor] = {}
+        # "bf16": tensor-core operands rounded to bf16 (the product path).  "split3": the fp32 parity run of the linear layers
+        # (no-grad forward only): every operand of the qkv / out / linear1 / linear2 products is split into bf16 hi + lo and the
+        # product runs over a three times longer K (x_hi w_hi + x_hi w_lo + x_lo w_hi, the k-NN kernel's operand layout,
+        # csrc/knn.cu), i.e. to ~2^-16 — what remains of bf16 is the attention kernel's q / k / v / P and the patch embedding.
+        self.linear_precision = "bf16"
 
     @staticmethod
     def _init_weights(m):
@@ -236,6 +241,14 @@ class ChAdaViT(nn.Module):
         tok, lay, patches, interp = self._tokenize(x, counts)
         blocks = []
         h, pre = tok, None          # pre = (u, mean, rstd) of this block's norm1(x) when the previous block already produced it
+        if self.linear_precision != "bf16":               # fp32 parity run of the linear layers (see __init__)
+            if self.linear_precision != "split3" or save:
+                raise ValueError("linear_precision must be 'bf16' or 'split3' (split3: no-grad forward only)")
+            for i in range(self.depth):
+                h = self._block_fwd_split3(i, h, lay)
+            idx = lay.non_cls_rows() if self.return_all_tokens else lay.cu[:-1]
+            return ops.layernorm_fwd(h, a.v32("norm.weight"), a.v32("norm.bias"), self.norm.eps, in_idx=idx, out_bf16=False, out_f32=True,
+                                     save_stats=False)[1], None
         # Only the CLS row of the final norm is returned (chada_vit.py:289) and every op behind the last attention is row-wise:
         # the last block then runs its attention for the CLS queries only and the rest on the B CLS rows (_tail_fwd).
         tail = ops.cls_tail_ok(self.depth, self.return_all_tokens, self.embed_dim // self.num_heads)
@@ -256,6 +269,29 @@ class ChAdaViT(nn.Module):
         s.lay, s.patches, s.blocks, s.x_last, s.fin_idx, s.fin_mean, s.fin_rstd, s.interp, s.hw = lay, patches, blocks, h, idx, mean, rstd, interp, (H, W)
         s.tail = tail
         return out, s
+
+    def _block_fwd_split3(self, i: int, x: torch.Tensor, lay: ops.PackedLayout) -> torch.Tensor:
+        """One encoder block (chada_vit.py:95-116) with fp32-grade linear layers: activations and weights enter cb_gemm_bf16 as
+        [hi | hi | lo] x [hi | lo | hi] bf16 operands over K = 3 x in_features (cb_split_bf16x3).  The parity run that shows what
+        bf16 operand rounding of the linear layers costs; ~3x the tensor work and unfused, never the training path."""
+        a, pre = self.arena, f"blocks.{i}."
+        eps = self.blocks[i].norm1.eps
+        g1, b1 = a.v32(pre + "norm1.weight"), a.v32(pre + "norm1.bias")
+        R = ops.EPI_RESIDUAL_F32 | ops.EPI_OUT_F32
+
+        def lin(inp32, wname, bname, **kw):
+            A, _ = ops.split_bf16x3(inp32.contiguous(), role_b=False, normalize=False)
+            W, _ = ops.split_bf16x3(a.v32(pre + wname).contiguous(), role_b=True, normalize=False)
+            return ops.gemm(A, W, bias=a.v32(pre + bname), **kw)
+        u32 = ops.layernorm_fwd(x, g1, b1, eps, out_bf16=False, out_f32=True, save_stats=False)[1]
+        qkv = lin(u32, "self_attn.in_proj_weight", "self_attn.in_proj_bias")                      # bf16: the attention kernel's input
+        att, _ = ops.attn_fwd(qkv, lay, self.num_heads, need_lse=False)
+        z1 = lin(att.float(), "self_attn.out_proj.weight", "self_attn.out_proj.bias", aux=x, flags=R)
+        y32 = ops.layernorm_fwd(z1, g1, b1, eps, out_bf16=False, out_f32=True, save_stats=False)[1]
+        hid = lin(y32, "linear1.weight", "linear1.bias", flags=ops.EPI_OUT_F32).relu_()
+        z2 = lin(hid, "linear2.weight", "linear2.bias", aux=y32, flags=R)
+        return ops.layernorm_fwd(z2, a.v32(pre + "norm2.weight"), a.v32(pre + "norm2.bias"), self.blocks[i].norm2.eps, out_bf16=False,
+                                 out_f32=True, save_stats=False)[1]
 
     def _tail_fwd(self, x: torch.Tensor, lay: ops.PackedLayout, save: bool, pre_u=None):
         """The last encoder block when only the CLS embedding leaves the backbone.  x fp32 [T, D] -> x' fp32 [B, D] (CLS rows).

@@ -57,6 +57,36 @@ def test_forward_matches_reference_golden(name):
     assert eo <= TOL_BF16_ORACLE
 
 
+@pytest.mark.parametrize("name", ["moyen_224_cls", "moyen_h12_cls", "tiny_224_all"])
+def test_forward_fp32_parity_run(name):
+    """north_star: "<= 1e-2 relative on the CLS embedding ... with fp32 parity runs also reported".  The product path rounds every
+    tensor-core operand to bf16, which alone moves the D = 192 embedding by ~1e-2 (TOL_FP32 above).  With the linear layers run
+    fp32-grade (ChAdaViT.linear_precision = "split3": hi + lo bf16 operands over 3x K, the attention kernel unchanged) the SAME
+    kernels land well inside the example tolerance against the fp32 reference outputs (chada_vit.py:272-289)."""
+    c = CASES[name]
+    P, x, nhead, eps = backbone_case(c)
+    m = _build(c)
+    m.load_state_dict(P)
+    m = m.cuda().eval()
+    m.linear_precision = "split3"
+    with torch.no_grad():
+        y = m(x.cuda(), 0, [c["counts"]])
+    torch.cuda.synchronize()
+    ref = torch.from_numpy(G[f"bb.{name}.out"])
+    got = (y if y.shape[0] <= 64 else y[::37]).cpu()
+    e = rel_err(got, ref)
+    m.linear_precision = "bf16"
+    with torch.no_grad():
+        y16 = m(x.cuda(), 0, [c["counts"]])
+    e16 = rel_err((y16 if y16.shape[0] <= 64 else y16[::37]).cpu(), ref)
+    print(f"{name}: rel L2 err vs reference(fp32): split3 linear layers {e:.3e} | bf16 operands (product path) {e16:.3e}")
+    assert e <= 6e-3
+    with pytest.raises(ValueError):
+        m.linear_precision = "split3"
+        m.train()
+        m(x.cuda(), 0, [c["counts"]])          # training goes through the bf16 product path only
+
+
 @pytest.mark.parametrize("name", ["tiny_224_cls", "tiny_96_cls", "moyen_224_cls"])
 def test_backward_matches_oracle_and_golden(name):
     """Gradients of every parameter.  Tight against the oracle with bf16 operand rounding (same arithmetic as the kernels);
