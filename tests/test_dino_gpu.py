@@ -172,6 +172,32 @@ def test_dino_step_matches_reference_and_fused_path():
     assert abs(model.momentum_updater.cur_tau - fused.momentum_updater.cur_tau) < 1e-12
 
 
+def test_unused_local_crop_passes_change_nothing():
+    """Reference wiring (base.py:701-707): the local crops run through the student backbone and the features are
+    dropped.  engine.run_unused_local_crops = False skips those passes; loss, centre and every parameter after two steps are
+    the same as with the default — which is what makes them dead compute (bench.py reports the step both ways, labelled)."""
+    st = cases()["step"]
+    counts, K = st["counts"], st["K"]
+    torch.manual_seed(3)
+    a = _make_dino(K).cuda()
+    b = _make_dino(K).cuda()
+    b.load_state_dict(a.state_dict())
+    assert a.run_unused_local_crops and b.run_unused_local_crops
+    b.run_unused_local_crops = False
+    g = torch.Generator(device="cpu").manual_seed(5)
+    n = sum(counts)
+    for _ in range(2):
+        crops = [torch.randn(n, 1, 224, 224, generator=g).cuda() for _ in range(2)] + [torch.randn(n, 1, 96, 96, generator=g).cuda() for _ in range(2)]
+        la = a.fused_train_step((crops, None, [counts] * 4))
+        lb = b.fused_train_step((crops, None, [counts] * 4))
+        torch.cuda.synchronize()
+        assert abs(la.item() - lb.item()) <= 1e-6
+    # not torch.equal: the split-K weight-gradient products accumulate with fp32 atomics, whose order differs from run to run
+    for (k, p), (_, q) in zip(a.named_parameters(), b.named_parameters()):
+        assert (p.detach() - q.detach()).abs().max().item() <= 1e-6, k
+    assert (a.dino_loss_func.center - b.dino_loss_func.center).abs().max().item() <= 1e-7
+
+
 def test_multicrop_loss_variant_runs():
     model = _make_dino(4096, multicrop=True).cuda()
     counts = [1, 2]
