@@ -473,6 +473,7 @@ def main():
     ap.add_argument("--fixed-batch", action="store_true", help="headline = one batch replayed from a CUDA graph (round-1 behaviour)")
     ap.add_argument("--unbalanced", action="store_true", help="N > 1: contiguous shards instead of token-balanced ones")
     ap.add_argument("--no-overlap", action="store_true", help="N > 1: flat all-reduces after the backward instead of bucketed overlap")
+    ap.add_argument("--bucket-blocks", type=int, default=0, help="N > 1: encoder blocks per gradient all-reduce bucket (default: the engine's, 3)")
     ap.add_argument("--serial-forward", action="store_true", help="teacher / local-crop forwards on the compute stream instead of side streams")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -514,6 +515,8 @@ def main():
         cfg["engine"]["overlap_comm"] = False
     if args.serial_forward:
         cfg["engine"]["overlap_forward"] = False
+    if args.bucket_blocks > 0:
+        cfg["engine"]["grad_bucket_blocks"] = args.bucket_blocks
     model = DINO(cfg).to(dev)
     pools = make_pools(1234 + rank, dev)
     n_total = args.warmup + 3 * args.steps + 16
