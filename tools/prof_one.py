@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Launch ONE kernel class a few times so that `ncu --set full` can capture it in isolation.
-    python tools/prof_one.py fc1|qkv|dh|fc2|attn_fwd|attn_bwd|ffn|ffn_save|ffn_bwd|ln_bwd|attn_cls_fwd|attn_cls_bwd"""
+    python tools/prof_one.py fc1|qkv|dh|fc2|attn_fwd|attn_bwd|ffn|ffn_save|ffn_bwd|ln_bwd|proj_ln|attn_cls_fwd|attn_cls_bwd"""
 import os
 import sys
 
@@ -42,6 +42,9 @@ if which == "ln_bwd":
 if which == "attn_bwd":
     out, lse = ops.attn_fwd(qkv, lay, 2)
     fns["attn_bwd"] = lambda: ops.attn_bwd(do, qkv, out, lse, lay, 2)
+if which == "proj_ln":
+    w_o, b_o, gam, bet = r(D, D), torch.randn(D, device=dev), torch.ones(D, device=dev), torch.zeros(D, device=dev)
+    fns["proj_ln"] = lambda: ops.gemm_ln_fwd(x16, w_o, b_o, x32, gam, bet, 1e-5, keep_z=True)
 if which in ("attn_cls_fwd", "attn_cls_bwd"):
     lay2 = ops.PackedLayout(counts + counts, 196, dev)        # the two packed global crops, as the engine runs them
     qkv2, do2 = r(lay2.T, 3 * D), r(lay2.B, D)
