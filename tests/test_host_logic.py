@@ -15,6 +15,14 @@ from oracle import chada_oracle as O
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def test_cls_tail_applies_only_to_cls_backbones():
+    """The CLS-only last block is taken only when the backbone returns x[:, 0] (chada_vit.py:289) and there is a block in front of it."""
+    from chadavit_b200 import ops
+    assert ops.cls_tail_ok(12, False, 96) and ops.cls_tail_ok(2, False, 16)
+    assert not ops.cls_tail_ok(12, True, 96)        # return_all_tokens: every row of the last block is an output
+    assert not ops.cls_tail_ok(1, False, 96)
+
+
 @pytest.mark.parametrize("counts,npatch", [([1, 3, 5, 10], 196), ([2, 10, 1], 36), ([10] * 7, 196), ([1], 4)])
 def test_packed_layout_is_bit_exact(counts, npatch):
     """cu_seqlens / channel->image maps / row order == the reference's split-pad-stack order at the unmasked positions."""
@@ -41,6 +49,8 @@ def test_packed_layout_is_bit_exact(counts, npatch):
     assert (np.diff(lens) <= 0).all()                                 # longest sequences first
     nc = lay.non_cls_rows().numpy()
     assert len(nc) == sum(counts) * npatch and not set(nc) & set(cu[:-1])
+    c64 = lay.cls_rows64()                                            # CLS rows for the CLS-only last block (chada_vit.py:289)
+    assert c64.dtype == torch.int64 and c64.tolist() == cu[:-1]
     with pytest.raises(ValueError):
         PackedLayout([11], npatch, "cpu")
     with pytest.raises(ValueError):
