@@ -12,8 +12,10 @@ token-balanced to the ranks, chadavit_b200/data/balance.py) — no CUDA-graph re
 rebuilt on the host every step, inputs resident in HBM.  `e2e` = the same through the public API from pinned HOST buffers
 (H2D of every crop + D2H of the loss inside the timed region).  Extra keys (same run): `fixed_batch_graph` (round-1 style
 best case: one batch replayed from a CUDA graph), `roofline` (dominant kernel, CUDA events), `multicrop_v8` (true multi-crop
-loss), `cfg1_extraction` (BASELINE configs[1]), `cfg4_attention_stress` (configs[4]), `parity_check` (GPU vs CPU oracle on the
-cpu_baseline sample), `gpu_yardstick` (stock PyTorch / flash-attn on the same box), `cpu_baseline` (oracle port on the host).
+loss), `without_unused_local_crop_passes` (the step minus the reference's dead local-crop passes — labelled, never the headline),
+`cfg1_extraction` (BASELINE configs[1]), `cfg4_attention_stress` (configs[4]), `parity_check` (GPU vs CPU oracle on the
+cpu_baseline sample, product path and fp32 parity run), `gpu_yardstick` (stock PyTorch / flash-attn on the same box),
+`cpu_baseline` (oracle port on the host).
 `--impl reference` times that CPU port as its own arm (the reference is pure Python/PyTorch; /root/reference does not
 exist on the GPU box, so the arm runs oracle/chada_oracle.py, which is pinned to the reference by tests/golden).
 """
