@@ -676,7 +676,10 @@ def main():
             def no_dead_local():
                 model.run_unused_local_crops = False
                 try:
-                    for _ in range(3):
+                    # allocator settle first (the caches were emptied above): the worst-case batch, then ordinary ones — a ragged
+                    # batch larger than anything seen since would otherwise hit cudaMalloc inside the timed steps
+                    model.fused_train_step(([p for p in pools], None, [[10] * BATCH] * (N_GLOBAL + N_LOCAL)))
+                    for _ in range(4):
                         model.fused_train_step(next_batch())
                     t_ms = _timed(lambda i: model.fused_train_step(next_batch()), max(5, args.steps // 2), lsync)
                 finally:
